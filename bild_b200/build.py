@@ -1,0 +1,45 @@
+"""
+Build libbild_b200.so (CUDA kernels + C ABI) in-tree for sm_100a.
+
+    python -m bild_b200.build [--force]
+
+nvcc cross-compiles without a GPU.  The library sits next to this file so that it travels with a
+snapshot of the repository; it is git-ignored.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = [os.path.join(HERE, "csrc", "bildk.cu")]
+DEPS = SRC + [os.path.join(HERE, "csrc", "bildk_kernels.cuh"),
+              os.path.join(os.path.dirname(HERE), "include", "bild_b200.h")]
+OUT = os.path.join(HERE, "libbild_b200.so")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false"]
+
+
+def needs_build():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    return any(os.path.getmtime(f) > t for f in DEPS)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return OUT
+    nvcc = os.environ.get("NVCC", "nvcc")
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,648 @@
+// Host side of libbild_b200.so: the C ABI declared in include/bild_b200.h.
+//
+// Replaces the per-call Python->C setup of /root/reference/bild/src/MSRouse_logL.pyx:143-199 by two
+// handles (model, trajectory) that live on the GPU, and the serial per-profile map of
+// /root/reference/bild/amis.py:735-739 by one batched kernel launch.
+#include "../../include/bild_b200.h"
+#include "bildk_kernels.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace bildk;
+
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(x)                                                                                        \
+    do {                                                                                             \
+        cudaError_t e_ = (x);                                                                        \
+        if (e_ != cudaSuccess) return fail(BILDK_ECUDA, "%s: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+template <typename T>
+struct DevBuf {   // growable device buffer
+    T* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t n) {
+        if (n <= cap) return BILDK_OK;
+        size_t want = std::max(n, cap * 2);
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e != cudaSuccess) return fail(BILDK_ENOMEM, "cudaMalloc(%zu bytes): %s", want * sizeof(T), cudaGetErrorString(e));
+        cap = want;
+        return BILDK_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+struct bildk_model {
+    int N, D, S, device;
+    // tile layout (fixed per model)
+    int TS, G, BS, LD, NP;
+    bool tile_ok;          // the tile kernel can hold this model on chip
+    bool hasG;
+    int nnz;
+    int wz_idx[NZMAX];
+    double wz_val[NZMAX];
+    // device arrays
+    double *dB = nullptr, *dSig = nullptr, *dC0 = nullptr;            // unpadded [S][N][N]
+    double *dBpad = nullptr, *dSigpad = nullptr, *dC0pad = nullptr;   // padded   [S][NP][LD]
+    double *dG = nullptr, *dM0 = nullptr, *dw = nullptr;
+    // per-model scratch for the host-pointer entry points
+    DevBuf<int32_t> starts;
+    DevBuf<uint8_t> states;
+    DevBuf<double> out, part, work;
+    DevBuf<int> meta;          // traj_first / cta maps / prof_traj
+    DevBuf<const double*> xptrs;
+    DevBuf<const uint8_t*> vptrs;
+    int max_smem_optin = 0;
+    int n_sm = 0;
+};
+
+struct bildk_traj {
+    bildk_model* m;
+    int T, dstar;
+    double* dx = nullptr;        // (T,D)
+    uint8_t* dvalid = nullptr;   // (T)
+    double s2[DMAX];
+    int ncols[DMAX];
+    int cols[DMAX][DMAX];
+    // single-trajectory launch metadata, resident
+    const double** d_xptr = nullptr;
+    const uint8_t** d_vptr = nullptr;
+    int* d_T = nullptr;
+    int* d_first = nullptr;      // [2] = {0, P}; P patched per call
+    int n_valid;
+    std::string plan;
+};
+
+// ------------------------------------------------------------------------------------------------
+static const int TS_CAND[] = {5, 4, 6, 8};
+static double ts_penalty(int TS) {   // relative cost per FMA, from tools/fp64_peak.cu on B200
+    switch (TS) {
+        case 4: return 1.12;
+        case 5: return 1.00;
+        case 6: return 0.97;
+        default: return 1.08;
+    }
+}
+static int maxt_for(int TS, bool ws) { return ws ? 128 : (TS <= 6 ? 512 : 256); }
+
+static size_t filter_doubles(int NP, int LD, bool densew) {
+    return static_cast<size_t>(NP) * LD + 2 * static_cast<size_t>(NP) * MSTRIDE + (densew ? 2 : NZMAX) * static_cast<size_t>(NP) + DMAX;
+}
+
+// Pick the register-tile edge for a model: least padded arithmetic among the variants that fit.
+static void choose_tile(bildk_model* m) {
+    const int forced = env_int("BILDK_TS", 0);
+    double best = 1e300;
+    m->tile_ok = false;
+    for (int TS : TS_CAND) {
+        if (forced && TS != forced) continue;
+        const int G = (m->N + TS - 1) / TS;
+        const int BS = TS + (TS & 1);
+        const int LD = G * BS, NP = G * TS;
+        if (G < m->D) continue;                       // mean columns ride on thread columns b < d
+        const bool ws = G * G <= 32;
+        if (G * G > maxt_for(TS, ws)) continue;
+        const size_t matb = static_cast<size_t>(NP) * LD * 8;
+        const size_t need = 16 + matb /*one B*/ + filter_doubles(NP, LD, m->nnz > NZMAX) * 8;
+        if (need > static_cast<size_t>(m->max_smem_optin)) continue;
+        int tpfs = G * G;
+        if (ws) { tpfs = 1; while (tpfs < G * G) tpfs *= 2; }
+        const double cost = static_cast<double>(NP) * NP * ts_penalty(TS) * tpfs / (G * G);
+        if (cost < best) {
+            best = cost;
+            m->TS = TS; m->G = G; m->BS = BS; m->LD = LD; m->NP = NP;
+            m->tile_ok = true;
+        }
+    }
+}
+
+static void pad_matrix(const double* src, int N, int TS, int BS, int LD, int NP, double* dst, bool symmetrize_lower) {
+    std::fill(dst, dst + static_cast<size_t>(NP) * LD, 0.0);
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) {
+            // dsymv("u") on C-ordered memory reads the lower triangle of the row-major array (pyx:55, 210, 227, 235)
+            const double v = symmetrize_lower ? src[static_cast<size_t>(std::max(i, j)) * N + std::min(i, j)] : src[static_cast<size_t>(i) * N + j];
+            dst[static_cast<size_t>(i) * LD + (j / TS) * BS + (j % TS)] = v;
+        }
+}
+
+extern "C" int bildk_version(void) { return 1000; }
+extern "C" const char* bildk_last_error(void) { return g_err.c_str(); }
+extern "C" long long bildk_launch_count(void) { return g_launches.load(); }
+
+extern "C" int bildk_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int bildk_model_destroy(bildk_model_t m) {
+    if (!m) return BILDK_OK;
+    cudaSetDevice(m->device);
+    for (double* p : {m->dB, m->dSig, m->dC0, m->dBpad, m->dSigpad, m->dC0pad, m->dG, m->dM0, m->dw})
+        if (p) cudaFree(p);
+    m->starts.release(); m->states.release(); m->out.release(); m->part.release(); m->work.release();
+    m->meta.release(); m->xptrs.release(); m->vptrs.release();
+    delete m;
+    return BILDK_OK;
+}
+
+extern "C" int bildk_model_create(int N, int d, int S, const double* B, const double* G, const double* Sig,
+                                  const double* M0, const double* C0, const double* w, int device,
+                                  bildk_model_t* out) {
+    if (!out) return fail(BILDK_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (N < 1 || d < 1 || d > DMAX || S < 1 || S > 255)
+        return fail(BILDK_EINVAL, "need N >= 1, 1 <= d <= %d, 1 <= S <= 255 (got N=%d d=%d S=%d)", DMAX, N, d, S);
+    if (!B || !G || !Sig || !M0 || !C0 || !w) return fail(BILDK_EINVAL, "NULL array argument");
+    const size_t NN = static_cast<size_t>(N) * N, ND = static_cast<size_t>(N) * d;
+    for (size_t i = 0; i < S * NN; ++i)
+        if (!std::isfinite(B[i]) || !std::isfinite(Sig[i]) || !std::isfinite(C0[i])) return fail(BILDK_EINVAL, "non-finite entry in B, Sig or C0");
+    for (size_t i = 0; i < S * ND; ++i)
+        if (!std::isfinite(G[i]) || !std::isfinite(M0[i])) return fail(BILDK_EINVAL, "non-finite entry in G or M0");
+    int ndev = bildk_device_count();
+    if (ndev == 0) return fail(BILDK_ECUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(BILDK_EINVAL, "device %d out of range [0,%d)", device, ndev);
+    CU(cudaSetDevice(device));
+
+    bildk_model* m = new bildk_model();
+    m->N = N; m->D = d; m->S = S; m->device = device;
+    CU(cudaDeviceGetAttribute(&m->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    CU(cudaDeviceGetAttribute(&m->n_sm, cudaDevAttrMultiProcessorCount, device));
+    m->hasG = false;
+    for (size_t i = 0; i < S * ND; ++i) if (G[i] != 0.0) m->hasG = true;
+    m->nnz = 0;
+    for (int i = 0; i < N; ++i) {
+        if (!std::isfinite(w[i])) { delete m; return fail(BILDK_EINVAL, "non-finite measurement vector"); }
+        if (w[i] != 0.0) {
+            if (m->nnz < NZMAX) { m->wz_idx[m->nnz] = i; m->wz_val[m->nnz] = w[i]; }
+            ++m->nnz;
+        }
+    }
+    choose_tile(m);
+
+    auto upload = [&](double** dst, const double* src, size_t n) -> int {
+        CU(cudaMalloc(dst, n * sizeof(double)));
+        CU(cudaMemcpy(*dst, src, n * sizeof(double), cudaMemcpyHostToDevice));
+        return BILDK_OK;
+    };
+    int rc = BILDK_OK;
+    // unpadded copies (catch-all kernel); B symmetrised from its lower triangle like dsymv("u") reads it
+    std::vector<double> Bs(S * NN);
+    for (int s = 0; s < S; ++s)
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j) Bs[s * NN + static_cast<size_t>(i) * N + j] = B[s * NN + static_cast<size_t>(std::max(i, j)) * N + std::min(i, j)];
+    if ((rc = upload(&m->dB, Bs.data(), S * NN)) || (rc = upload(&m->dSig, Sig, S * NN)) || (rc = upload(&m->dC0, C0, S * NN)) ||
+        (rc = upload(&m->dG, G, S * ND)) || (rc = upload(&m->dM0, M0, S * ND)) || (rc = upload(&m->dw, w, N))) {
+        bildk_model_destroy(m);
+        return rc;
+    }
+    if (m->tile_ok) {
+        const size_t matd = static_cast<size_t>(m->NP) * m->LD;
+        std::vector<double> pad(S * matd);
+        for (int s = 0; s < S; ++s) pad_matrix(B + s * NN, N, m->TS, m->BS, m->LD, m->NP, pad.data() + s * matd, true);
+        if ((rc = upload(&m->dBpad, pad.data(), S * matd))) { bildk_model_destroy(m); return rc; }
+        for (int s = 0; s < S; ++s) pad_matrix(Sig + s * NN, N, m->TS, m->BS, m->LD, m->NP, pad.data() + s * matd, false);
+        if ((rc = upload(&m->dSigpad, pad.data(), S * matd))) { bildk_model_destroy(m); return rc; }
+        for (int s = 0; s < S; ++s) pad_matrix(C0 + s * NN, N, m->TS, m->BS, m->LD, m->NP, pad.data() + s * matd, false);
+        if ((rc = upload(&m->dC0pad, pad.data(), S * matd))) { bildk_model_destroy(m); return rc; }
+    }
+    *out = m;
+    return BILDK_OK;
+}
+
+extern "C" int bildk_traj_destroy(bildk_traj_t t) {
+    if (!t) return BILDK_OK;
+    cudaSetDevice(t->m->device);
+    if (t->dx) cudaFree(t->dx);
+    if (t->dvalid) cudaFree(t->dvalid);
+    if (t->d_xptr) cudaFree(t->d_xptr);
+    if (t->d_vptr) cudaFree(t->d_vptr);
+    if (t->d_T) cudaFree(t->d_T);
+    if (t->d_first) cudaFree(t->d_first);
+    delete t;
+    return BILDK_OK;
+}
+
+extern "C" int bildk_traj_create(bildk_model_t m, int T, const double* x, int dstar, const double* s2,
+                                 const uint32_t* Cind, bildk_traj_t* out) {
+    if (!out) return fail(BILDK_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (!m || !x || !s2 || !Cind) return fail(BILDK_EINVAL, "NULL argument");
+    if (T < 1) return fail(BILDK_EINVAL, "trajectory needs at least one frame");
+    if (dstar < 1 || dstar > m->D) return fail(BILDK_EINVAL, "dstar=%d must be in [1, d=%d]", dstar, m->D);
+    for (int e = 0; e < dstar; ++e)
+        if (!std::isfinite(s2[e]) || s2[e] < 0) return fail(BILDK_EINVAL, "localisation error must be finite and non-negative");
+    for (int j = 0; j < m->D; ++j)
+        if (Cind[j] >= static_cast<uint32_t>(dstar)) return fail(BILDK_EINVAL, "Cind[%d]=%u out of range", j, Cind[j]);
+    CU(cudaSetDevice(m->device));
+    bildk_traj* t = new bildk_traj();
+    t->m = m; t->T = T; t->dstar = dstar;
+    for (int e = 0; e < DMAX; ++e) { t->s2[e] = 0; t->ncols[e] = 0; for (int c = 0; c < DMAX; ++c) t->cols[e][c] = 0; }
+    for (int e = 0; e < dstar; ++e) t->s2[e] = s2[e];
+    for (int j = 0; j < m->D; ++j) { int e = Cind[j]; t->cols[e][t->ncols[e]++] = j; }
+    std::vector<uint8_t> valid(T);
+    t->n_valid = 0;
+    for (int i = 0; i < T; ++i) {   // pyx:178: a frame is valid iff no component is NaN
+        bool ok = true;
+        for (int j = 0; j < m->D; ++j) if (std::isnan(x[static_cast<size_t>(i) * m->D + j])) ok = false;
+        valid[i] = ok;
+        t->n_valid += ok;
+    }
+    const size_t nx = static_cast<size_t>(T) * m->D;
+    CU(cudaMalloc(&t->dx, nx * sizeof(double)));
+    CU(cudaMemcpy(t->dx, x, nx * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&t->dvalid, T));
+    CU(cudaMemcpy(t->dvalid, valid.data(), T, cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&t->d_xptr, sizeof(double*)));
+    CU(cudaMalloc(&t->d_vptr, sizeof(uint8_t*)));
+    CU(cudaMalloc(&t->d_T, sizeof(int)));
+    CU(cudaMalloc(&t->d_first, 2 * sizeof(int)));
+    const double* xp = t->dx;
+    const uint8_t* vp = t->dvalid;
+    CU(cudaMemcpy(t->d_xptr, &xp, sizeof xp, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(t->d_vptr, &vp, sizeof vp, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(t->d_T, &T, sizeof T, cudaMemcpyHostToDevice));
+    *out = t;
+    return BILDK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct Plan {
+    bool tile;
+    bool ws, densew, b_all;
+    int TS, FPC, TPFS, threads, maxt;
+    size_t smem;
+    int fstride;
+};
+
+static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
+    Plan pl{};
+    pl.tile = m->tile_ok && !env_int("BILDK_FORCE_GENERIC", 0);
+    if (!pl.tile) return pl;
+    const int G = m->G, TPF = G * G;
+    pl.TS = m->TS;
+    pl.densew = m->nnz > NZMAX;
+    pl.ws = TPF <= 32;
+    pl.maxt = maxt_for(m->TS, pl.ws);
+    const size_t matb = static_cast<size_t>(m->NP) * m->LD * 8;
+    const size_t fbytes = filter_doubles(m->NP, m->LD, pl.densew) * 8;
+    pl.fstride = static_cast<int>(fbytes / 8);
+    const size_t cap = static_cast<size_t>(m->max_smem_optin);
+    pl.b_all = 16 + matb * m->S + fbytes <= cap;
+    const size_t bbytes = matb * (pl.b_all ? m->S : 1);
+    int fpc_smem = static_cast<int>((cap - 16 - bbytes) / fbytes);
+    if (!pl.b_all) fpc_smem = 1;
+    if (pl.ws) {
+        pl.TPFS = 1;
+        while (pl.TPFS < TPF) pl.TPFS *= 2;
+        const int per_warp = 32 / pl.TPFS;
+        int warps = env_int("BILDK_WARPS", 2);
+        warps = std::max(1, std::min(warps, pl.maxt / 32));
+        pl.FPC = std::min(warps * per_warp, std::max(per_warp, (fpc_smem / per_warp) * per_warp));
+        pl.threads = (pl.FPC / per_warp) * 32;
+    } else {
+        pl.TPFS = TPF;
+        int fpc = std::max(1, std::min(pl.maxt / TPF, fpc_smem));
+        // keep enough CTAs to cover the SMs
+        while (fpc > 1 && (P_per_traj_hint + fpc - 1) / fpc < 2 * m->n_sm) --fpc;
+        const int forced = env_int("BILDK_FPC", 0);
+        if (forced > 0) fpc = std::max(1, std::min(forced, std::min(pl.maxt / TPF, fpc_smem)));
+        pl.FPC = fpc;
+        pl.threads = ((fpc * TPF + 31) / 32) * 32;
+    }
+    pl.smem = 16 + bbytes + static_cast<size_t>(pl.FPC) * fbytes;
+    return pl;
+}
+
+template <int TS, bool WS, bool DW, int MAXT>
+static cudaError_t launch_one(const KParams& kp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_tile<TS, WS, DW, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    k_tile<TS, WS, DW, MAXT><<<grid, threads, smem, st>>>(kp);
+    return cudaGetLastError();
+}
+
+template <int TS>
+static cudaError_t launch_ts(const Plan& pl, const KParams& kp, dim3 grid, cudaStream_t st) {
+    constexpr int MT = (TS <= 6 ? 512 : 256);
+    if (pl.ws) {
+        if (pl.densew) return launch_one<TS, true, true, 128>(kp, grid, pl.threads, pl.smem, st);
+        return launch_one<TS, true, false, 128>(kp, grid, pl.threads, pl.smem, st);
+    }
+    if (pl.densew) return launch_one<TS, false, true, MT>(kp, grid, pl.threads, pl.smem, st);
+    return launch_one<TS, false, false, MT>(kp, grid, pl.threads, pl.smem, st);
+}
+
+static cudaError_t launch_tile(const Plan& pl, const KParams& kp, dim3 grid, cudaStream_t st) {
+    switch (pl.TS) {
+        case 4: return launch_ts<4>(pl, kp, grid, st);
+        case 5: return launch_ts<5>(pl, kp, grid, st);
+        case 6: return launch_ts<6>(pl, kp, grid, st);
+        case 8: return launch_ts<8>(pl, kp, grid, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+static std::string plan_string(const bildk_model* m, const Plan& pl) {
+    char buf[256];
+    if (!pl.tile)
+        snprintf(buf, sizeof buf, "generic N=%d (covariance in L2 workspace)", m->N);
+    else
+        snprintf(buf, sizeof buf, "tile TS=%d G=%d %s-scope %s-w B=%s FPC=%d threads=%d smem=%zu", pl.TS, m->G,
+                 pl.ws ? "warp" : "cta", pl.densew ? "dense" : "sparse", pl.b_all ? "all" : "one", pl.FPC, pl.threads, pl.smem);
+    return buf;
+}
+
+extern "C" const char* bildk_describe_plan(bildk_traj_t t, int P) {
+    if (!t) return "";
+    Plan pl = make_plan(t->m, P);
+    t->plan = plan_string(t->m, pl);
+    return t->plan.c_str();
+}
+
+// Core launcher on device-resident profile arrays.  Trajectory metadata arrays are device pointers.
+static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const double* const* d_x,
+                         const uint8_t* const* d_valid, const int* d_T, const int* d_first,
+                         const std::vector<int>& h_first, int P, int K1, const int32_t* d_starts,
+                         const uint8_t* d_states, double* d_out, cudaStream_t st) {
+    if (P == 0) return BILDK_OK;
+    const int dstar = t0->dstar;
+    int max_per_traj = 0;
+    for (int i = 0; i < n_traj; ++i) max_per_traj = std::max(max_per_traj, h_first[i + 1] - h_first[i]);
+    Plan pl = make_plan(m, n_traj == 1 ? P : P);
+    double* d_part = d_out;
+    if (dstar > 1) {
+        int rc = m->part.reserve(static_cast<size_t>(dstar) * P);
+        if (rc) return rc;
+        d_part = m->part.p;
+    }
+    if (pl.tile) {
+        KParams kp{};
+        kp.N = m->N; kp.D = m->D; kp.S = m->S; kp.G = m->G; kp.LD = m->LD; kp.NP = m->NP;
+        kp.Bpad = m->dBpad; kp.Sigpad = m->dSigpad; kp.C0pad = m->dC0pad; kp.Gm = m->dG; kp.M0 = m->dM0; kp.w = m->dw;
+        kp.hasG = m->hasG; kp.nnz = m->nnz;
+        for (int z = 0; z < NZMAX; ++z) { kp.wz_idx[z] = m->wz_idx[z]; kp.wz_val[z] = m->wz_val[z]; }
+        kp.n_traj = n_traj; kp.x = d_x; kp.valid = d_valid; kp.T = d_T; kp.traj_first = d_first;
+        kp.dstar = dstar;
+        for (int e = 0; e < DMAX; ++e) {
+            kp.s2[e] = t0->s2[e]; kp.ncols[e] = t0->ncols[e];
+            for (int c = 0; c < DMAX; ++c) kp.cols[e][c] = t0->cols[e][c];
+        }
+        kp.P = P; kp.K1 = K1; kp.run_starts = d_starts; kp.run_states = d_states; kp.out = d_part;
+        kp.FPC = pl.FPC; kp.TPFS = pl.TPFS; kp.b_all = pl.b_all; kp.fstride = pl.fstride;
+        int n_cta = 0;
+        if (n_traj == 1) {
+            n_cta = (P + pl.FPC - 1) / pl.FPC;
+            kp.cta_traj = nullptr; kp.cta_first = nullptr;
+        } else {
+            std::vector<int> map;   // [cta_traj..., cta_first...]
+            std::vector<int> ct, cf;
+            for (int i = 0; i < n_traj; ++i)
+                for (int f = h_first[i]; f < h_first[i + 1]; f += pl.FPC) { ct.push_back(i); cf.push_back(f); }
+            n_cta = static_cast<int>(ct.size());
+            int rc = m->meta.reserve(static_cast<size_t>(2) * n_cta + 64);
+            if (rc) return rc;
+            CU(cudaMemcpyAsync(m->meta.p, ct.data(), n_cta * sizeof(int), cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(m->meta.p + n_cta, cf.data(), n_cta * sizeof(int), cudaMemcpyHostToDevice, st));
+            CU(cudaStreamSynchronize(st));   // ct/cf are stack vectors
+            kp.cta_traj = m->meta.p; kp.cta_first = m->meta.p + n_cta;
+        }
+        dim3 grid(n_cta, dstar);
+        CU(launch_tile(pl, kp, grid, st));
+        g_launches++;
+    } else {
+        GParams gp{};
+        gp.N = m->N; gp.D = m->D; gp.S = m->S;
+        gp.B = m->dB; gp.Sig = m->dSig; gp.C0 = m->dC0; gp.Gm = m->dG; gp.M0 = m->dM0; gp.w = m->dw;
+        gp.n_traj = n_traj; gp.x = d_x; gp.valid = d_valid; gp.T = d_T; gp.traj_first = d_first;
+        gp.dstar = dstar;
+        for (int e = 0; e < DMAX; ++e) {
+            gp.s2[e] = t0->s2[e]; gp.ncols[e] = t0->ncols[e];
+            for (int c = 0; c < DMAX; ++c) gp.cols[e][c] = t0->cols[e][c];
+        }
+        gp.P = P; gp.K1 = K1; gp.run_starts = d_starts; gp.run_states = d_states; gp.out = d_part;
+        gp.prof_traj = nullptr;
+        if (n_traj > 1) {
+            std::vector<int> pt(P);
+            for (int i = 0; i < n_traj; ++i) for (int f = h_first[i]; f < h_first[i + 1]; ++f) pt[f] = i;
+            int rc = m->meta.reserve(P + 64);
+            if (rc) return rc;
+            CU(cudaMemcpy(m->meta.p, pt.data(), P * sizeof(int), cudaMemcpyHostToDevice));
+            gp.prof_traj = m->meta.p;
+        }
+        const int n_cta = std::min(P, 4 * m->n_sm);
+        const size_t wsz = 2 * static_cast<size_t>(m->N) * m->N + 3 * static_cast<size_t>(m->N) * m->D + 2 * m->N;
+        int rc = m->work.reserve(wsz * n_cta * dstar);
+        if (rc) return rc;
+        gp.work = m->work.p;
+        k_generic<<<dim3(n_cta, dstar), 256, 0, st>>>(gp);
+        CU(cudaGetLastError());
+        g_launches++;
+    }
+    if (dstar > 1) {
+        k_sum_parts<<<(P + 255) / 256, 256, 0, st>>>(d_part, d_out, P, dstar);
+        CU(cudaGetLastError());
+        g_launches++;
+    }
+    return BILDK_OK;
+}
+
+static int validate_runs(const bildk_model* m, int T, int P, int K1, const int32_t* starts, const uint8_t* states, int pbase) {
+    for (int p = 0; p < P; ++p) {
+        const int32_t* rs = starts + static_cast<size_t>(p) * K1;
+        const uint8_t* rt = states + static_cast<size_t>(p) * K1;
+        if (rs[0] != 0) return fail(BILDK_EINVAL, "profile %d: first run must start at frame 0 (got %d)", pbase + p, rs[0]);
+        for (int r = 0; r < K1; ++r) {
+            if (rt[r] >= m->S) return fail(BILDK_EINVAL, "profile %d: state %d out of range [0,%d)", pbase + p, rt[r], m->S);
+            if (r && rs[r] < rs[r - 1]) return fail(BILDK_EINVAL, "profile %d: run starts must be non-decreasing", pbase + p);
+            if (rs[r] < 0 || rs[r] > T) return fail(BILDK_EINVAL, "profile %d: run start %d outside [0,%d]", pbase + p, rs[r], T);
+        }
+    }
+    return BILDK_OK;
+}
+
+extern "C" int bildk_logl_runs_device(bildk_traj_t t, int P, int K1, const int32_t* d_starts,
+                                      const uint8_t* d_states, double* d_out, void* stream) {
+    if (!t) return fail(BILDK_EINVAL, "NULL trajectory");
+    if (P < 0 || K1 < 1) return fail(BILDK_EINVAL, "need P >= 0 and K1 >= 1");
+    if (P == 0) return BILDK_OK;
+    if (!d_starts || !d_states || !d_out) return fail(BILDK_EINVAL, "NULL device pointer");
+    bildk_model* m = t->m;
+    CU(cudaSetDevice(m->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int first[2] = {0, P};
+    CU(cudaMemcpyAsync(t->d_first, first, sizeof first, cudaMemcpyHostToDevice, st));
+    std::vector<int> hf = {0, P};
+    return launch_device(m, t, 1, t->d_xptr, t->d_vptr, t->d_T, t->d_first, hf, P, K1, d_starts, d_states, d_out, st);
+}
+
+extern "C" int bildk_logl_runs_multi(int n_traj, const bildk_traj_t* trajs, const int32_t* offsets, int K1,
+                                     const int32_t* starts, const uint8_t* states, double* out) {
+    if (n_traj < 1 || !trajs || !offsets) return fail(BILDK_EINVAL, "need at least one trajectory");
+    if (K1 < 1) return fail(BILDK_EINVAL, "K1 must be >= 1");
+    bildk_model* m = trajs[0] ? trajs[0]->m : nullptr;
+    if (!m) return fail(BILDK_EINVAL, "NULL trajectory");
+    const int P = offsets[n_traj];
+    if (offsets[0] != 0 || P < 0) return fail(BILDK_EINVAL, "offsets must start at 0");
+    if (P == 0) return BILDK_OK;
+    if (!starts || !states || !out) return fail(BILDK_EINVAL, "NULL array argument");
+    std::vector<int> hf(offsets, offsets + n_traj + 1);
+    for (int i = 0; i < n_traj; ++i) {
+        bildk_traj* t = trajs[i];
+        if (!t || t->m != m) return fail(BILDK_EINVAL, "all trajectories must belong to one model");
+        if (hf[i + 1] < hf[i]) return fail(BILDK_EINVAL, "offsets must be non-decreasing");
+        if (t->dstar != trajs[0]->dstar) return fail(BILDK_EINVAL, "trajectories in one batch must share the localisation-error structure");
+        for (int e = 0; e < t->dstar; ++e) {
+            if (t->s2[e] != trajs[0]->s2[e] || t->ncols[e] != trajs[0]->ncols[e]) return fail(BILDK_EINVAL, "trajectories in one batch must share the localisation error");
+            for (int c = 0; c < t->ncols[e]; ++c) if (t->cols[e][c] != trajs[0]->cols[e][c]) return fail(BILDK_EINVAL, "trajectories in one batch must share the localisation error");
+        }
+        int rc = validate_runs(m, t->T, hf[i + 1] - hf[i], K1, starts + static_cast<size_t>(hf[i]) * K1, states + static_cast<size_t>(hf[i]) * K1, hf[i]);
+        if (rc) return rc;
+    }
+    CU(cudaSetDevice(m->device));
+    int rc;
+    const size_t nrun = static_cast<size_t>(P) * K1;
+    if ((rc = m->starts.reserve(nrun)) || (rc = m->states.reserve(nrun)) || (rc = m->out.reserve(P))) return rc;
+    CU(cudaMemcpy(m->starts.p, starts, nrun * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(m->states.p, states, nrun, cudaMemcpyHostToDevice));
+    const double* const* d_x;
+    const uint8_t* const* d_v;
+    const int* d_T;
+    const int* d_first;
+    DevBuf<int> tmeta;   // T + first, freed at the end (kept separate from m->meta used for the CTA map)
+    if (n_traj == 1) {
+        bildk_traj* t = trajs[0];
+        int first[2] = {0, P};
+        CU(cudaMemcpy(t->d_first, first, sizeof first, cudaMemcpyHostToDevice));
+        d_x = t->d_xptr; d_v = t->d_vptr; d_T = t->d_T; d_first = t->d_first;
+    } else {
+        std::vector<const double*> xs(n_traj);
+        std::vector<const uint8_t*> vs(n_traj);
+        std::vector<int> Ts(n_traj);
+        for (int i = 0; i < n_traj; ++i) { xs[i] = trajs[i]->dx; vs[i] = trajs[i]->dvalid; Ts[i] = trajs[i]->T; }
+        if ((rc = m->xptrs.reserve(n_traj)) || (rc = m->vptrs.reserve(n_traj)) || (rc = tmeta.reserve(2 * static_cast<size_t>(n_traj) + 1))) return rc;
+        CU(cudaMemcpy(m->xptrs.p, xs.data(), n_traj * sizeof(double*), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(m->vptrs.p, vs.data(), n_traj * sizeof(uint8_t*), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(tmeta.p, Ts.data(), n_traj * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(tmeta.p + n_traj, hf.data(), (n_traj + 1) * sizeof(int), cudaMemcpyHostToDevice));
+        d_x = m->xptrs.p; d_v = m->vptrs.p; d_T = tmeta.p; d_first = tmeta.p + n_traj;
+    }
+    rc = launch_device(m, trajs[0], n_traj, d_x, d_v, d_T, d_first, hf, P, K1, m->starts.p, m->states.p, m->out.p, nullptr);
+    if (rc == BILDK_OK) {
+        cudaError_t e = cudaMemcpy(out, m->out.p, P * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(BILDK_ECUDA, "kernel or copy-back failed: %s", cudaGetErrorString(e));
+    }
+    tmeta.release();
+    return rc;
+}
+
+extern "C" int bildk_logl_runs(bildk_traj_t t, int P, int K1, const int32_t* starts, const uint8_t* states, double* out) {
+    if (!t) return fail(BILDK_EINVAL, "NULL trajectory");
+    if (P < 0) return fail(BILDK_EINVAL, "P must be >= 0");
+    int32_t off[2] = {0, P};
+    bildk_traj_t arr[1] = {t};
+    return bildk_logl_runs_multi(1, arr, off, K1, starts, states, out);
+}
+
+extern "C" int bildk_logl_states(bildk_traj_t t, int P, const int32_t* states, double* out) {
+    if (!t) return fail(BILDK_EINVAL, "NULL trajectory");
+    if (P < 0) return fail(BILDK_EINVAL, "P must be >= 0");
+    if (P == 0) return BILDK_OK;
+    if (!states || !out) return fail(BILDK_EINVAL, "NULL array argument");
+    const int T = t->T, S = t->m->S;
+    // run-length code every profile; K1 = longest
+    std::vector<int> nruns(P);
+    int K1 = 1;
+    for (int p = 0; p < P; ++p) {
+        const int32_t* s = states + static_cast<size_t>(p) * T;
+        int n = 1;
+        for (int i = 0; i < T; ++i) {
+            if (s[i] < 0 || s[i] >= S) return fail(BILDK_EINVAL, "profile %d frame %d: state %d out of range [0,%d)", p, i, s[i], S);
+            if (i && s[i] != s[i - 1]) ++n;
+        }
+        nruns[p] = n;
+        K1 = std::max(K1, n);
+    }
+    std::vector<int32_t> rs(static_cast<size_t>(P) * K1, T);
+    std::vector<uint8_t> rt(static_cast<size_t>(P) * K1, 0);
+    for (int p = 0; p < P; ++p) {
+        const int32_t* s = states + static_cast<size_t>(p) * T;
+        int r = 0;
+        rs[static_cast<size_t>(p) * K1] = 0;
+        rt[static_cast<size_t>(p) * K1] = static_cast<uint8_t>(s[0]);
+        for (int i = 1; i < T; ++i)
+            if (s[i] != s[i - 1]) {
+                ++r;
+                rs[static_cast<size_t>(p) * K1 + r] = i;
+                rt[static_cast<size_t>(p) * K1 + r] = static_cast<uint8_t>(s[i]);
+            }
+        for (++r; r < K1; ++r) rt[static_cast<size_t>(p) * K1 + r] = rt[static_cast<size_t>(p) * K1 + r - 1];
+    }
+    return bildk_logl_runs(t, P, K1, rs.data(), rt.data(), out);
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int bildk_amis_weights(int n, const double* logL, const double* logdelta, const double* curlp,
+                                  double log_nsteps, double* log_w, double stats[4], int device) {
+    if (n < 1 || !logL || !logdelta || !curlp || !stats) return fail(BILDK_EINVAL, "bad argument");
+    int ndev = bildk_device_count();
+    if (ndev == 0) return fail(BILDK_ECUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(BILDK_EINVAL, "device %d out of range", device);
+    CU(cudaSetDevice(device));
+    double* d = nullptr;
+    const size_t nn = static_cast<size_t>(n);
+    CU(cudaMalloc(&d, (4 * nn + 4) * sizeof(double)));
+    int rc = BILDK_OK;
+    cudaError_t e;
+    if ((e = cudaMemcpy(d, logL, nn * 8, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(d + nn, logdelta, nn * 8, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(d + 2 * nn, curlp, nn * 8, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        rc = fail(BILDK_ECUDA, "copy failed: %s", cudaGetErrorString(e));
+    } else {
+        k_amis_weights<<<1, 1024>>>(n, d, d + nn, d + 2 * nn, log_nsteps, log_w ? d + 3 * nn : nullptr, d + 4 * nn);
+        g_launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaMemcpy(stats, d + 4 * nn, 4 * 8, cudaMemcpyDeviceToHost)) != cudaSuccess ||
+            (log_w && (e = cudaMemcpy(log_w, d + 3 * nn, nn * 8, cudaMemcpyDeviceToHost)) != cudaSuccess))
+            rc = fail(BILDK_ECUDA, "weights kernel failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d);
+    return rc;
+}

@@ -1,0 +1,182 @@
+"""
+Host-side engine: owns the GPU-resident model and trajectory handles and turns profile batches into
+one kernel launch through the C ABI (include/bild_b200.h).
+
+What the reference does per likelihood call (/root/reference/bild/src/MSRouse_logL.pyx:143-199:
+``np.unique`` of the noise, restacking B/G/Sig of every state, ``steady_state()``, NaN mask) happens
+here ONCE per model / trajectory; what it does per profile in a Python loop
+(/root/reference/bild/amis.py:735-739) happens here once per batch.
+"""
+import ctypes
+import weakref
+
+import numpy as np
+
+from . import _lib
+from ._lib import c_double_p, c_int32_p, c_uint8_p, c_uint32_p, as_f64, ptr
+
+__all__ = ["RouseEngine", "TrajectoryHandle", "st_to_runs", "states_to_runs"]
+
+
+def st_to_runs(ss, thetas, T):
+    """
+    Run-length form of ``FixedkSampler.st2profile`` for a whole batch.
+
+    Uses the identical numpy expression as /root/reference/bild/amis.py:687-688
+    (``floor(cumsum(s)[:-1] * (T-1)).astype(int) + 1``) so that the discrete profiles are the very
+    same ones; run ``r`` of profile ``p`` covers frames ``[starts[p, r], starts[p, r+1])`` with state
+    ``thetas[p, r]`` (last run to ``T``); empty runs vanish like the empty numpy slices do.
+    """
+    ss = np.asarray(ss, dtype=float)
+    thetas = np.asarray(thetas)
+    if ss.ndim == 1:
+        ss, thetas = ss[None, :], thetas[None, :]
+    P, K1 = ss.shape
+    starts = np.zeros((P, K1), dtype=np.int32)
+    if K1 > 1:
+        switchpos = np.cumsum(ss, axis=1)[:, :-1]
+        starts[:, 1:] = np.floor(switchpos * (T - 1)).astype(int) + 1
+    return starts, np.ascontiguousarray(thetas, dtype=np.uint8)
+
+
+def states_to_runs(states):
+    """Run-length code per-frame state arrays (P, T) -> (starts (P, K1) int32, run_states (P, K1) uint8)."""
+    states = np.asarray(states)
+    if states.ndim == 1:
+        states = states[None, :]
+    P, T = states.shape
+    change = np.ones((P, T), dtype=bool)
+    change[:, 1:] = states[:, 1:] != states[:, :-1]
+    nruns = change.sum(axis=1)
+    K1 = int(nruns.max())
+    starts = np.full((P, K1), T, dtype=np.int32)
+    rstates = np.zeros((P, K1), dtype=np.uint8)
+    pi, ti = np.nonzero(change)
+    ri = (np.cumsum(change, axis=1) - 1)[pi, ti]
+    starts[pi, ri] = ti
+    rstates[pi, ri] = states[pi, ti]
+    return starts, rstates
+
+
+class TrajectoryHandle:
+    """A trajectory resident on the GPU: data, missing-frame mask and localisation-error structure."""
+
+    def __init__(self, engine, x, localization_error):
+        x = as_f64(x)
+        if x.ndim == 1:
+            x = x[:, None]
+        if x.ndim != 2 or x.shape[1] != engine.d:
+            raise ValueError(f"trajectory must have shape (T, {engine.d}), got {x.shape}")
+        err = np.asarray(localization_error, dtype=float)
+        if err.shape != (engine.d,):
+            raise ValueError(f"localization_error must have shape ({engine.d},), got {err.shape}")
+        # MSRouse_logL.pyx:145-147
+        uniq, cind = np.unique(err, return_inverse=True)
+        self.s2 = as_f64(uniq * uniq)
+        self.Cind = np.ascontiguousarray(cind, dtype=np.uint32)
+        self.T = x.shape[0]
+        self.engine = engine
+        lib = _lib.load()
+        h = ctypes.c_void_p()
+        _lib.check(lib.bildk_traj_create(engine._h, self.T, ptr(x, c_double_p), len(self.s2), ptr(self.s2, c_double_p),
+                                         ptr(self.Cind, c_uint32_p), ctypes.byref(h)))
+        self._h = h
+        self._fin = weakref.finalize(self, lib.bildk_traj_destroy, h)
+
+    def describe_plan(self, P):
+        return _lib.load().bildk_describe_plan(self._h, int(P)).decode()
+
+
+class RouseEngine:
+    """
+    GPU-resident multi-state Rouse model.
+
+    Parameters
+    ----------
+    Bs, Gs, Sigs : (S, N, N), (S, N, d), (S, N, N)
+        per-state propagators (``m._dynamics['B'|'G'|'Sig']``)
+    M0, C0 : (S, N, d), (S, N, N)
+        per-state steady states
+    w : (N,)
+        measurement vector
+    device : int
+        CUDA device ordinal
+    """
+
+    def __init__(self, Bs, Gs, Sigs, M0, C0, w, device=0):
+        Bs, Gs, Sigs, M0, C0, w = (as_f64(a) for a in (Bs, Gs, Sigs, M0, C0, w))
+        S, N, d = Gs.shape
+        if Bs.shape != (S, N, N) or Sigs.shape != (S, N, N) or C0.shape != (S, N, N) or M0.shape != (S, N, d) or w.shape != (N,):
+            raise ValueError("inconsistent model array shapes")
+        self.S, self.N, self.d, self.device = S, N, d, int(device)
+        lib = _lib.load()
+        h = ctypes.c_void_p()
+        _lib.check(lib.bildk_model_create(N, d, S, *(ptr(a, c_double_p) for a in (Bs, Gs, Sigs, M0, C0, w)),
+                                          self.device, ctypes.byref(h)))
+        self._h = h
+        self._fin = weakref.finalize(self, lib.bildk_model_destroy, h)
+
+    @classmethod
+    def from_models(cls, models, measurement, device=0):
+        """Build from ``rouse.Model``-like objects (what MSRouse_logL.pyx:152-160 reads on every call)."""
+        for m in models:
+            m.check_dynamics()
+        ss = [m.steady_state() for m in models]
+        return cls([m._dynamics["B"] for m in models], [m._dynamics["G"] for m in models],
+                   [m._dynamics["Sig"] for m in models], [s[0] for s in ss], [s[1] for s in ss],
+                   measurement, device=device)
+
+    def trajectory(self, x, localization_error):
+        return TrajectoryHandle(self, x, localization_error)
+
+    # ------------------------------------------------------------------ batched likelihood
+    def logl_runs(self, traj, starts, run_states):
+        starts = np.ascontiguousarray(starts, dtype=np.int32)
+        run_states = np.ascontiguousarray(run_states, dtype=np.uint8)
+        if starts.ndim != 2 or starts.shape != run_states.shape:
+            raise ValueError("starts and run_states must both have shape (P, K1)")
+        P, K1 = starts.shape
+        out = np.empty(P, dtype=np.float64)
+        if P:
+            _lib.check(_lib.load().bildk_logl_runs(traj._h, P, K1, ptr(starts, c_int32_p), ptr(run_states, c_uint8_p),
+                                                   ptr(out, c_double_p)))
+        return out
+
+    def logl_st(self, traj, ss, thetas):
+        """Batched ``logL(st2profile(s, theta), traj)`` (amis.py:717-739)."""
+        thetas = np.asarray(thetas)
+        if thetas.size and (thetas.min() < 0 or thetas.max() >= self.S):
+            raise ValueError(f"state index out of range [0, {self.S})")
+        starts, rstates = st_to_runs(ss, thetas, traj.T)
+        return self.logl_runs(traj, starts, rstates)
+
+    def logl_states(self, traj, states):
+        """Per-frame state arrays (P, T) or (T,) -> (P,) log-likelihoods."""
+        states = np.ascontiguousarray(states, dtype=np.int32)
+        if states.ndim == 1:
+            states = states[None, :]
+        if states.shape[1] != traj.T:
+            raise ValueError(f"profile length {states.shape[1]} does not match trajectory length {traj.T}")
+        out = np.empty(states.shape[0], dtype=np.float64)
+        if len(out):
+            _lib.check(_lib.load().bildk_logl_states(traj._h, states.shape[0], ptr(states, c_int32_p), ptr(out, c_double_p)))
+        return out
+
+    def logl_runs_multi(self, trajs, offsets, starts, run_states):
+        """Profiles [offsets[i], offsets[i+1]) belong to trajs[i]; one launch for the whole dataset."""
+        starts = np.ascontiguousarray(starts, dtype=np.int32)
+        run_states = np.ascontiguousarray(run_states, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+        if len(offsets) != len(trajs) + 1 or starts.shape != run_states.shape or starts.shape[0] != offsets[-1]:
+            raise ValueError("inconsistent multi-trajectory batch")
+        out = np.empty(starts.shape[0], dtype=np.float64)
+        if len(out):
+            arr = (ctypes.c_void_p * len(trajs))(*[t._h for t in trajs])
+            _lib.check(_lib.load().bildk_logl_runs_multi(len(trajs), arr, ptr(offsets, c_int32_p), starts.shape[1],
+                                                         ptr(starts, c_int32_p), ptr(run_states, c_uint8_p), ptr(out, c_double_p)))
+        return out
+
+    def logl_runs_device(self, traj, P, K1, d_starts, d_states, d_out, stream=0):
+        """Device pointers (ints); asynchronous on ``stream``."""
+        _lib.check(_lib.load().bildk_logl_runs_device(traj._h, int(P), int(K1), ctypes.c_void_p(d_starts), ctypes.c_void_p(d_states),
+                                                      ctypes.c_void_p(d_out), ctypes.c_void_p(stream)))

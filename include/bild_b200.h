@@ -1,0 +1,119 @@
+/*
+ * bild_b200 - C ABI of the B200-native BILD likelihood engine (libbild_b200.so).
+ *
+ * The reference has exactly one native plugin slot for this path: the CPython extension
+ * ``bild.bin.MSRouse_logL`` exporting ``MSRouse_logL(model, profile, traj) -> float``
+ * (/root/reference/bild/cython_imports.py:3-7, built by /root/reference/setup.py:41-46, source
+ * /root/reference/bild/src/MSRouse_logL.pyx:95-256), called once per profile from the serial map in
+ * ``FixedkSampler.logL`` (/root/reference/bild/amis.py:717-739).  This header is what a binding for
+ * that slot would call instead (see INTEGRATION.md for the ctypes / Cython stub): the per-call
+ * Python->C setup of the .pyx (pyx:143-199) is hoisted into a model handle and a trajectory handle,
+ * and the per-profile call becomes one batched call.
+ *
+ * Conventions: plain C, no torch / CUDA types in any signature.  All matrices are C-ordered
+ * (row-major) float64 exactly as the .pyx declares them (``FLOAT_t[:, :, ::1]``, pyx:114-122).
+ * Every function returns 0 on success or a negative BILDK_E* code; bildk_last_error() gives the
+ * message for the calling thread.  There is NO CPU fallback: without a CUDA device every compute
+ * entry point fails with BILDK_ECUDA.
+ */
+#ifndef BILD_B200_H
+#define BILD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BILDK_OK        0
+#define BILDK_EINVAL   -1   /* bad argument (shape, state index out of range, non-finite error, ...) */
+#define BILDK_ECUDA    -2   /* CUDA runtime error or no device */
+#define BILDK_ENOMEM   -3
+#define BILDK_EUNSUP   -4   /* configuration not supported by any kernel */
+
+typedef struct bildk_model *bildk_model_t;
+typedef struct bildk_traj  *bildk_traj_t;
+
+/* ABI version (major*1000 + minor) and the last error message of the calling thread. */
+int         bildk_version(void);
+const char *bildk_last_error(void);
+
+/* Number of CUDA devices visible (0 if none / no driver); never fails. */
+int bildk_device_count(void);
+
+/*
+ * Model handle = what pyx:150-160 gathers on EVERY call, done once:
+ *   w    (N)       model.measurement                       pyx:150
+ *   B    (S,N,N)   [m._dynamics['B']   for m in models]    pyx:155   (symmetric; lower triangle is read,
+ *   G    (S,N,d)   [m._dynamics['G']   ...]                pyx:156    as dsymv("u") on C-order does)
+ *   Sig  (S,N,N)   [m._dynamics['Sig'] ...]                pyx:157
+ *   M0   (S,N,d), C0 (S,N,N)   m.steady_state() of every state; profile[0] selects one   pyx:160
+ * The arrays are copied to `device` (padded into the kernels' tile layout); the caller keeps
+ * ownership of the host arrays.
+ */
+int bildk_model_create(int N, int d, int S,
+                       const double *B, const double *G, const double *Sig,
+                       const double *M0, const double *C0, const double *w,
+                       int device, bildk_model_t *out);
+int bildk_model_destroy(bildk_model_t model);
+
+/*
+ * Trajectory handle = pyx:144-147 and pyx:174-178, done once per trajectory:
+ *   x     (T,d)   traj[:]; a frame is missing iff ANY component is NaN        pyx:178
+ *   s2    (dstar) squared distinct localisation errors  (np.unique(noise)**2) pyx:145-146
+ *   Cind  (d)     index into s2 for every spatial dimension                   pyx:147
+ */
+int bildk_traj_create(bildk_model_t model, int T, const double *x,
+                      int dstar, const double *s2, const uint32_t *Cind,
+                      bildk_traj_t *out);
+int bildk_traj_destroy(bildk_traj_t traj);
+
+/*
+ * Batched replacement of the serial map amis.py:735-739 -> models.py:278 -> pyx:95.
+ * Profiles are run-length coded the way FixedkSampler.st2profile builds them (amis.py:685-693):
+ * profile p consists of K1 runs; run r has state run_states[p*K1+r] and covers frames
+ * [run_starts[p*K1+r], run_starts[p*K1+r+1])  (the last run extends to T; run_starts[p*K1] must be 0;
+ * empty runs are allowed and vanish, as the empty numpy slices do).  out[p] = logL.
+ * HOST pointers; the call copies in, launches, copies out and returns when out[] is valid.
+ */
+int bildk_logl_runs(bildk_traj_t traj, int P, int K1,
+                    const int32_t *run_starts, const uint8_t *run_states, double *out);
+
+/* Same, from per-frame state arrays states[p*T + t] (the Loopingprofile format, util.py:15-23). */
+int bildk_logl_states(bildk_traj_t traj, int P, const int32_t *states, double *out);
+
+/*
+ * Device-resident variant: all three pointers are DEVICE pointers on the model's device, the launch
+ * is asynchronous on `stream` (a cudaStream_t passed as void*, NULL = default stream).
+ */
+int bildk_logl_runs_device(bildk_traj_t traj, int P, int K1,
+                           const int32_t *d_run_starts, const uint8_t *d_run_states,
+                           double *d_out, void *stream);
+
+/*
+ * Many trajectories in one launch (dataset runs): profiles [offsets[i], offsets[i+1]) belong to
+ * trajs[i]; all trajectories must share one model.  Host pointers, synchronous.
+ */
+int bildk_logl_runs_multi(int n_traj, const bildk_traj_t *trajs, const int32_t *offsets, int K1,
+                          const int32_t *run_starts, const uint8_t *run_states, double *out);
+
+/*
+ * AMIS weight normalisation (amis.py:843-845, 878-900), deterministic fixed-order reduction:
+ *   log_w[i] = logL[i] - logdelta[i] + log_nsteps
+ *   stats[0] = max_i log_w        stats[1] = sum_i exp(log_w - max)      stats[2] = sum_i exp(..)^2
+ *   stats[3] = sum_i exp(log_w - max) * (logL[i] - cur_log_proposal[i])   (NaN terms skipped, as nansum)
+ * Host pointers; log_w may be NULL.  n >= 1.
+ */
+int bildk_amis_weights(int n, const double *logL, const double *logdelta,
+                       const double *cur_log_proposal, double log_nsteps,
+                       double *log_w, double stats[4], int device);
+
+/* Diagnostics: kernels launched by this library since load; description of the kernel variant the
+ * next bildk_logl_* call on this trajectory would use for a batch of P ("tile TS=5 G=4 warp ..."). */
+long long   bildk_launch_count(void);
+const char *bildk_describe_plan(bildk_traj_t traj, int P);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BILD_B200_H */

@@ -1,0 +1,175 @@
+"""
+GPU parity tests: the CUDA path, called through the C ABI (bild_b200.engine -> libbild_b200.so),
+against (i) the golden vectors produced by the unmodified reference and (ii) the C oracle on seeded
+synthetic inputs.  Gate: 1e-9 relative on logL (BASELINE.json north_star); observed ~1e-13.
+"""
+import numpy as np
+import pytest
+
+import kalman_oracle as ko
+from helpers import MODEL_KEYS, golden_cases, load_golden, oracle_model, random_profiles, rel_err, synth_traj
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9   # relative, FP64 (north_star: "within 1e-9 relative on logL")
+
+
+def engine_for(mod, device=0):
+    from bild_b200.engine import RouseEngine
+    return RouseEngine(*(mod[k] for k in MODEL_KEYS), device=device)
+
+
+@pytest.mark.parametrize("path", golden_cases(), ids=lambda p: p.split("logl_")[-1][:-4])
+def test_golden_vectors(path):
+    g = load_golden(path)
+    eng = engine_for(g)
+    err = np.sqrt(g["s2"])[g["Cind"]]
+    traj = eng.trajectory(g["x"], err)
+    out = eng.logl_states(traj, g["states"])
+    assert rel_err(out, g["logL_cy"]) < TOL
+    assert rel_err(out, g["logL_py"]) < TOL
+
+
+CASES = [
+    # N, d, T, P, p_nan, noise, loops, kmax
+    (20, 3, 100, 64, 0.1, 0.3, (None, [(0, -1)]), 10),          # config 1/2 shape: warp-scope, 2 filters per warp
+    (10, 3, 60, 33, 0.0, 0.2, (None, [(0, -1)]), 4),            # N=10
+    (25, 3, 80, 20, 0.2, 0.3, (None, [(0, -1)]), 6),            # G=5: CTA-scope packing
+    (50, 3, 120, 19, 0.1, 0.3, (None, [(0, -1)]), 8),           # config 4 shape
+    (100, 3, 40, 5, 0.1, 0.3, (None, [(0, -1)]), 3),            # config 3 shape: single resident propagator
+    (23, 2, 50, 17, 0.3, [0.1, 0.4], (None, [(0, -1)], [(2, 9), (5, 20, 0.5)]), 5),  # odd N, 3 states, d*=2
+    (7, 1, 30, 9, 0.0, 0.5, (None, [(0, -1)]), 2),              # tiny
+    (3, 3, 25, 6, 0.0, 0.5, (None, [(0, -1)]), 2),              # N == d
+    (2, 3, 25, 6, 0.1, 0.5, (None, [(0, -1, 0.5)]), 2),         # N < d: catch-all kernel
+    (130, 2, 12, 3, 0.0, 0.3, (None, [(0, -1)]), 2),            # beyond the on-chip limit: catch-all kernel
+]
+
+
+@pytest.mark.parametrize("N,d,T,P,p_nan,noise,loops,kmax", CASES)
+def test_against_c_oracle(N, d, T, P, p_nan, noise, loops, kmax):
+    rng = np.random.default_rng(1000 + N * 7 + T)
+    mod = oracle_model(N, d=d, loops=loops)
+    x, _ = synth_traj(mod, T, rng, noise, p_nan=p_nan)
+    ss, thetas = random_profiles(rng, P, T, len(loops), kmax)
+    err = np.broadcast_to(np.asarray(noise, dtype=float), (d,))
+    s2, Cind = ko.noise_to_s2_cind(err)
+    states = np.array([ko.st2states(s, th, T) for s, th in zip(ss, thetas)])
+    want = ko.logl_c(*(mod[k] for k in MODEL_KEYS), x, s2, Cind, states)
+
+    eng = engine_for(mod)
+    traj = eng.trajectory(x, err)
+    got_st = eng.logl_st(traj, ss, thetas)            # run-length path (amis.py:717-739 replacement)
+    got_states = eng.logl_states(traj, states)        # per-frame path (models.py:265-278 replacement)
+    assert rel_err(got_st, want) < TOL
+    assert rel_err(got_states, want) < TOL
+    assert np.array_equal(got_st, got_states)          # same filters, same arithmetic
+
+
+def test_dense_measurement_vector():
+    rng = np.random.default_rng(5)
+    N, d, T, P = 20, 3, 60, 21
+    w = rng.normal(size=N)
+    w -= w.mean()
+    mod = oracle_model(N, d=d, w=w)
+    x, _ = synth_traj(mod, T, rng, 0.2, p_nan=0.1)
+    ss, thetas = random_profiles(rng, P, T, 2, 5)
+    s2, Cind = ko.noise_to_s2_cind([0.2] * d)
+    states = np.array([ko.st2states(s, th, T) for s, th in zip(ss, thetas)])
+    want = ko.logl_c(*(mod[k] for k in MODEL_KEYS), x, s2, Cind, states)
+    eng = engine_for(mod)
+    got = eng.logl_st(eng.trajectory(x, [0.2] * d), ss, thetas)
+    assert rel_err(got, want) < TOL
+
+
+def test_external_force_mean_offset():
+    """G != 0 (pyx:209): constant force on the chain ends."""
+    rng = np.random.default_rng(6)
+    N, d, T, P = 15, 2, 40, 10
+    F = np.zeros((N, d))
+    F[0, 0], F[-1, 0] = -0.7, 0.7
+    mod = oracle_model(N, d=d, F=F)
+    assert np.any(mod["Gs"] != 0)
+    x, _ = synth_traj(mod, T, rng, 0.2)
+    ss, thetas = random_profiles(rng, P, T, 2, 4)
+    s2, Cind = ko.noise_to_s2_cind([0.2] * d)
+    states = np.array([ko.st2states(s, th, T) for s, th in zip(ss, thetas)])
+    want = ko.logl_c(*(mod[k] for k in MODEL_KEYS), x, s2, Cind, states)
+    eng = engine_for(mod)
+    got = eng.logl_st(eng.trajectory(x, [0.2] * d), ss, thetas)
+    assert rel_err(got, want) < TOL
+
+
+def test_no_valid_frames_and_single_frame():
+    mod = oracle_model(12, d=2)
+    eng = engine_for(mod)
+    x = np.full((9, 2), np.nan)
+    traj = eng.trajectory(x, [0.3, 0.3])
+    assert np.array_equal(eng.logl_states(traj, np.zeros((3, 9), dtype=int)), np.zeros(3))   # _py.py:121: sum of nothing
+    x1 = np.array([[0.4, -0.1]])
+    traj1 = eng.trajectory(x1, [0.3, 0.3])
+    s2, Cind = ko.noise_to_s2_cind([0.3, 0.3])
+    want = ko.logl_c(*(mod[k] for k in MODEL_KEYS), x1, s2, Cind, np.array([[1]]))
+    assert rel_err(eng.logl_states(traj1, np.array([[1]])), want) < TOL
+
+
+def test_multi_trajectory_batch():
+    rng = np.random.default_rng(11)
+    N, d = 20, 3
+    mod = oracle_model(N, d=d)
+    eng = engine_for(mod)
+    s2, Cind = ko.noise_to_s2_cind([0.3] * d)
+    trajs, wants, starts_all, states_all, offsets = [], [], [], [], [0]
+    from bild_b200.engine import st_to_runs
+    for i, (T, P) in enumerate([(40, 7), (75, 1), (40, 12), (90, 5)]):
+        x, _ = synth_traj(mod, T, rng, 0.3, p_nan=0.1 * i)
+        ss, thetas = random_profiles(rng, P, T, 2, 6)
+        st = np.array([ko.st2states(s, th, T) for s, th in zip(ss, thetas)])
+        wants.append(ko.logl_c(*(mod[k] for k in MODEL_KEYS), x, s2, Cind, st))
+        trajs.append(eng.trajectory(x, [0.3] * d))
+        a, b = st_to_runs(ss, thetas, T)
+        starts_all.append(a); states_all.append(b); offsets.append(offsets[-1] + P)
+    got = eng.logl_runs_multi(trajs, offsets, np.concatenate(starts_all), np.concatenate(states_all))
+    assert rel_err(got, np.concatenate(wants)) < TOL
+
+
+def test_error_behaviour():
+    mod = oracle_model(8, d=1)
+    eng = engine_for(mod)
+    traj = eng.trajectory(np.arange(5.0), [0.5])
+    with pytest.raises(ValueError):
+        eng.logl_states(traj, np.array([[0, 1, 2, 0, 0]]))          # state out of range
+    with pytest.raises(ValueError):
+        eng.logl_states(traj, np.zeros((1, 4), dtype=int))           # length mismatch
+    with pytest.raises(ValueError):
+        eng.trajectory(np.arange(5.0), [np.nan])
+    assert eng.logl_states(traj, np.zeros((0, 5), dtype=int)).shape == (0,)
+
+
+def test_round_trip_properties_full_size():
+    """BASELINE config 2 size (N=20, T=500, P=4096): properties that need no oracle."""
+    rng = np.random.default_rng(2)
+    N, d, T, P = 20, 3, 500, 4096
+    mod = oracle_model(N, d=d)
+    x, _ = synth_traj(mod, T, rng, 0.3, p_nan=0.0)
+    ss, thetas = random_profiles(rng, P, T, 2, 10)
+    eng = engine_for(mod)
+    traj = eng.trajectory(x, [0.3] * d)
+    a = eng.logl_st(traj, ss, thetas)
+    assert np.all(np.isfinite(a))
+    # (1) permutation equivariance + run-to-run determinism (bitwise)
+    perm = rng.permutation(P)
+    b = eng.logl_st(traj, ss[perm], thetas[perm])
+    assert np.array_equal(a[perm], b)
+    # (2) batch-split invariance (bitwise)
+    c = np.concatenate([eng.logl_st(traj, ss[:1000], thetas[:1000]), eng.logl_st(traj, ss[1000:], thetas[1000:])])
+    assert np.array_equal(a, c)
+    # (3) a sample of the batch against the oracle
+    idx = rng.choice(P, 24, replace=False)
+    s2, Cind = ko.noise_to_s2_cind([0.3] * d)
+    st = np.array([ko.st2states(ss[i], thetas[i], T) for i in idx])
+    want = ko.logl_c(*(mod[k] for k in MODEL_KEYS), x, s2, Cind, st)
+    assert rel_err(a[idx], want) < TOL
+    # (4) spatial dimensions with equal error are exchangeable: permuting columns leaves logL unchanged up to summation order
+    traj_p = eng.trajectory(x[:, [2, 0, 1]], [0.3] * d)
+    e = eng.logl_st(traj_p, ss[:256], thetas[:256])
+    assert rel_err(e, a[:256]) < 1e-12
