@@ -646,3 +646,46 @@ extern "C" int bildk_amis_weights(int n, const double* logL, const double* logde
     cudaFree(d);
     return rc;
 }
+
+extern "C" int bildk_amis_weights_device(int n, const double* d_logL, const double* d_logdelta, const double* d_curlp,
+                                         double log_nsteps, double* d_log_w, double* d_stats, void* stream) {
+    if (n < 1 || !d_logL || !d_logdelta || !d_curlp || !d_stats) return fail(BILDK_EINVAL, "bad argument");
+    k_amis_weights<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(n, d_logL, d_logdelta, d_curlp, log_nsteps, d_log_w, d_stats);
+    CU(cudaGetLastError());
+    g_launches++;
+    return BILDK_OK;
+}
+
+extern "C" int bildk_measure_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops) {
+    int ndev = bildk_device_count();
+    if (ndev == 0) return fail(BILDK_ECUDA, "no CUDA device available");
+    if (device < 0 || device >= ndev || !dfma_tflops || !dmma_tflops) return fail(BILDK_EINVAL, "bad argument");
+    CU(cudaSetDevice(device));
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    double* d = nullptr;
+    CU(cudaMalloc(&d, 8));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const int iters = 4096, blocks = sms * 4;   // 32 warps per SM
+    double best[2] = {1e30, 1e30};
+    for (int which = 0; which < 2; ++which)
+        for (int rep = 0; rep < 7; ++rep) {
+            CU(cudaEventRecord(e0));
+            if (which == 0) k_peak_dfma<<<blocks, 256>>>(d, iters, 1.0000001, 1e-9);
+            else k_peak_dmma<<<blocks, 256>>>(d, iters, 1.0000001, 1e-9);
+            CU(cudaEventRecord(e1));
+            CU(cudaEventSynchronize(e1));
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep >= 2 && ms < best[which]) best[which] = ms;
+        }
+    CU(cudaGetLastError());
+    *dfma_tflops = 2.0 * 16 * iters * 256.0 * blocks / best[0] * 1e-9;
+    *dmma_tflops = 2.0 * 256 * 8 * iters * 8.0 * blocks / best[1] * 1e-9;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    return BILDK_OK;
+}

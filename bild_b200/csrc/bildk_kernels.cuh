@@ -628,4 +628,36 @@ __global__ void __launch_bounds__(1024) k_amis_weights(int n, const double* __re
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// FP64 peak probes (roofline denominators; MEASURED_PEAKS.json has no FP64 entry): independent
+// register-resident DFMA chains, and DMMA m8n8k4 chains.  Same kernels as tools/fp64_peak.cu.
+__global__ void __launch_bounds__(256) k_peak_dfma(double* out, int iters, double a, double b) {
+    double acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = threadIdx.x * 1e-9 + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = fma(acc[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    if (s == 123.456) out[0] = s;
+}
+__global__ void __launch_bounds__(256) k_peak_dmma(double* out, int iters, double a, double b) {
+    double c0[8], c1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c0[i] = threadIdx.x * 1e-9; c1[i] = i; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c0[i] + c1[i];
+    if (s == 123.456) out[0] = s;
+}
+
 }  // namespace bildk

@@ -108,6 +108,15 @@ int bildk_amis_weights(int n, const double *logL, const double *logdelta,
                        const double *cur_log_proposal, double log_nsteps,
                        double *log_w, double stats[4], int device);
 
+/* Device-resident variant of bildk_amis_weights: device pointers (d_log_w may be NULL, d_stats has
+ * room for 4 doubles), asynchronous on `stream`. */
+int bildk_amis_weights_device(int n, const double *d_logL, const double *d_logdelta,
+                              const double *d_cur_log_proposal, double log_nsteps,
+                              double *d_log_w, double *d_stats, void *stream);
+
+/* Roofline denominators measured on the spot: FP64 FMA and FP64 MMA (m8n8k4) peak, TFLOP/s. */
+int bildk_measure_fp64_peak(int device, double *dfma_tflops, double *dmma_tflops);
+
 /* Diagnostics: kernels launched by this library since load; description of the kernel variant the
  * next bildk_logl_* call on this trajectory would use for a batch of P ("tile TS=5 G=4 warp ..."). */
 long long   bildk_launch_count(void);
