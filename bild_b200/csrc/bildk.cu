@@ -5,6 +5,7 @@
 // /root/reference/bild/amis.py:735-739 by one batched kernel launch.
 #include "../../include/bild_b200.h"
 #include "bildk_kernels.cuh"
+#include "bildk_mma.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -78,6 +79,11 @@ struct bildk_model {
     double *dB = nullptr, *dSig = nullptr, *dC0 = nullptr;            // unpadded [S][N][N]
     double *dBpad = nullptr, *dSigpad = nullptr, *dC0pad = nullptr;   // padded   [S][NP][LD]
     double *dG = nullptr, *dM0 = nullptr, *dw = nullptr;
+    uint16_t* d_lane_ab = nullptr;   // [G*G] lane -> tile map (2x2 tile blocks per lane quad)
+    // tensor-core (DMMA) layout: 8x8 tiles, row strides == 4 (mod 8)
+    bool mma_ok = false, mma_mx = false;
+    int GT = 0, NPm = 0, LDBm = 0, LDCm = 0, MC0 = 0, NK = 0;
+    double *dBm = nullptr, *dSigm = nullptr, *dC0m = nullptr;
     // per-model scratch for the host-pointer entry points
     DevBuf<int32_t> starts;
     DevBuf<uint8_t> states;
@@ -118,8 +124,11 @@ static double ts_penalty(int TS) {   // relative cost per FMA, from tools/fp64_p
 }
 static int maxt_for(int TS, bool ws) { return ws ? 128 : (TS <= 6 ? 512 : 256); }
 
+// shared memory per filter, in doubles; == 8 (mod 16) so that the two filters sharing a warp (and the
+// propagators of two states) sit 64 bytes apart modulo the 128-byte bank row
+static size_t stride_8mod16(size_t n) { return (n + 15) / 16 * 16 + 8; }
 static size_t filter_doubles(int NP, int LD, bool densew) {
-    return static_cast<size_t>(NP) * LD + 2 * static_cast<size_t>(NP) * MSTRIDE + (densew ? 2 : NZMAX) * static_cast<size_t>(NP) + DMAX;
+    return stride_8mod16(static_cast<size_t>(NP) * LD + 2 * static_cast<size_t>(NP) * MSTRIDE + (densew ? 2 : NZMAX) * static_cast<size_t>(NP) + DMAX);
 }
 
 // Pick the register-tile edge for a model: least padded arithmetic among the variants that fit.
@@ -172,8 +181,9 @@ extern "C" int bildk_device_count(void) {
 extern "C" int bildk_model_destroy(bildk_model_t m) {
     if (!m) return BILDK_OK;
     cudaSetDevice(m->device);
-    for (double* p : {m->dB, m->dSig, m->dC0, m->dBpad, m->dSigpad, m->dC0pad, m->dG, m->dM0, m->dw})
+    for (double* p : {m->dB, m->dSig, m->dC0, m->dBpad, m->dSigpad, m->dC0pad, m->dG, m->dM0, m->dw, m->dBm, m->dSigm, m->dC0m})
         if (p) cudaFree(p);
+    if (m->d_lane_ab) cudaFree(m->d_lane_ab);
     m->starts.release(); m->states.release(); m->out.release(); m->part.release(); m->work.release();
     m->meta.release(); m->xptrs.release(); m->vptrs.release();
     delete m;
@@ -239,6 +249,46 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
         if ((rc = upload(&m->dSigpad, pad.data(), S * matd))) { bildk_model_destroy(m); return rc; }
         for (int s = 0; s < S; ++s) pad_matrix(C0 + s * NN, N, m->TS, m->BS, m->LD, m->NP, pad.data() + s * matd, false);
         if ((rc = upload(&m->dC0pad, pad.data(), S * matd))) { bildk_model_destroy(m); return rc; }
+        // lane -> (a, b): walk the tile grid in 2x2 blocks so that an aligned quad of lanes owns one block
+        std::vector<uint16_t> lab;
+        const int Gt = m->G;
+        for (int ba = 0; ba < Gt; ba += 2)
+            for (int bb = 0; bb < Gt; bb += 2)
+                for (int ia = 0; ia < 2; ++ia)
+                    for (int ib = 0; ib < 2; ++ib)
+                        if (ba + ia < Gt && bb + ib < Gt) lab.push_back(static_cast<uint16_t>(((ba + ia) << 8) | (bb + ib)));
+        CU(cudaMalloc(&m->d_lane_ab, lab.size() * sizeof(uint16_t)));
+        CU(cudaMemcpy(m->d_lane_ab, lab.data(), lab.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
+    // tensor-core layout (one warp per filter): N <= 56, sparse measurement vector
+    {
+        const int GT = (N + 7) / 8;
+        if (GT <= 7 && m->nnz == 2) {
+            m->GT = GT; m->NPm = 8 * GT;
+            m->mma_mx = (m->NPm - N) < d;
+            m->MC0 = m->mma_mx ? m->NPm : N;
+            m->LDBm = m->NPm + 4;
+            m->LDCm = 8 * (GT + (m->mma_mx ? 1 : 0)) + 4;
+            m->NK = (N + 3) / 4 * 4;
+            const size_t matb = static_cast<size_t>(m->NPm) * m->LDBm;
+            std::vector<double> pad(S * matb);
+            auto fill = [&](const double* src, bool sym) {
+                std::fill(pad.begin(), pad.end(), 0.0);
+                for (int s = 0; s < S; ++s)
+                    for (int i = 0; i < N; ++i)
+                        for (int j = 0; j < N; ++j)
+                            pad[s * matb + static_cast<size_t>(i) * m->LDBm + j] =
+                                sym ? src[s * NN + static_cast<size_t>(std::max(i, j)) * N + std::min(i, j)] : src[s * NN + static_cast<size_t>(i) * N + j];
+            };
+            fill(B, true);
+            if ((rc = upload(&m->dBm, pad.data(), S * matb))) { bildk_model_destroy(m); return rc; }
+            fill(Sig, false);
+            if ((rc = upload(&m->dSigm, pad.data(), S * matb))) { bildk_model_destroy(m); return rc; }
+            fill(C0, false);
+            if ((rc = upload(&m->dC0m, pad.data(), S * matb))) { bildk_model_destroy(m); return rc; }
+            const size_t fbytes = (static_cast<size_t>(m->NPm) * m->LDCm + static_cast<size_t>(2) * m->NPm) * 8;
+            m->mma_ok = 16 + matb * 8 * S + fbytes <= static_cast<size_t>(m->max_smem_optin);
+        }
     }
     *out = m;
     return BILDK_OK;
@@ -302,15 +352,98 @@ extern "C" int bildk_traj_create(bildk_model_t m, int T, const double* x, int ds
 
 // ------------------------------------------------------------------------------------------------
 struct Plan {
+    bool mma = false;      // tensor-core kernel, one warp per filter
+    int WPC = 0;
     bool tile;
     bool ws, densew, b_all;
     int TS, FPC, TPFS, threads, maxt;
     size_t smem;
-    int fstride;
+    int fstride, bstride;
 };
+
+template <int GT, bool MX>
+static cudaError_t mma_launch(const MParams& mp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_mma<GT, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    k_mma<GT, MX><<<grid, threads, smem, st>>>(mp);
+    return cudaGetLastError();
+}
+template <int GT, bool MX>
+static int mma_regs() {
+    cudaFuncAttributes a{};
+    if (cudaFuncGetAttributes(&a, k_mma<GT, MX>) != cudaSuccess) { cudaGetLastError(); return 255; }
+    return a.numRegs;
+}
+#define MMA_DISPATCH(GTV, MXV, CALL)                                          \
+    switch ((GTV) * 2 + ((MXV) ? 1 : 0)) {                                     \
+        case 2: return CALL(1, false); case 3: return CALL(1, true);           \
+        case 4: return CALL(2, false); case 5: return CALL(2, true);           \
+        case 6: return CALL(3, false); case 7: return CALL(3, true);           \
+        case 8: return CALL(4, false); case 9: return CALL(4, true);           \
+        case 10: return CALL(5, false); case 11: return CALL(5, true);         \
+        case 12: return CALL(6, false); case 13: return CALL(6, true);         \
+        case 14: return CALL(7, false); case 15: return CALL(7, true);         \
+    }
+static int mma_regs_for(int GT, bool MX) {
+#define CALL_REGS(G_, M_) mma_regs<G_, M_>()
+    MMA_DISPATCH(GT, MX, CALL_REGS)
+#undef CALL_REGS
+    return 255;
+}
+static cudaError_t mma_launch_for(int GT, bool MX, const MParams& mp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+#define CALL_LAUNCH(G_, M_) mma_launch<G_, M_>(mp, grid, threads, smem, st)
+    MMA_DISPATCH(GT, MX, CALL_LAUNCH)
+#undef CALL_LAUNCH
+    return cudaErrorInvalidValue;
+}
 
 static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
     Plan pl{};
+    {
+        const char* force = getenv("BILDK_KERNEL");
+        const bool want_mma = m->mma_ok && !(force && !strcmp(force, "tile")) && !env_int("BILDK_FORCE_GENERIC", 0);
+        if (want_mma) {
+            const size_t matb = static_cast<size_t>(m->NPm) * m->LDBm * 8;
+            const size_t fbytes = (static_cast<size_t>(m->NPm) * m->LDCm + static_cast<size_t>(2) * m->NPm) * 8;
+            const size_t cap = static_cast<size_t>(m->max_smem_optin);
+            const size_t sm_total = 228 * 1024;
+            const int regs = mma_regs_for(m->GT, m->mma_mx);
+            const int P = std::max(1, P_per_traj_hint);
+            double best = -1;
+            int best_w = 1;
+            const int forced = env_int("BILDK_WPC", 0);
+            for (int w = 1; w <= 8; ++w) {
+                if (forced && w != forced) continue;
+                const size_t smem = 16 + matb * m->S + fbytes * w;
+                if (smem > cap) break;
+                int per_sm = static_cast<int>(sm_total / (smem + 1024));
+                per_sm = std::min(per_sm, 65536 / (regs * 32 * w));
+                per_sm = std::min(per_sm, 64 / w);
+                if (per_sm < 1) continue;
+                const long long slots = static_cast<long long>(m->n_sm) * per_sm * w;
+                const long long waves = (P + slots - 1) / slots;
+                // efficiency of the last wave plus a mild preference for more resident warps (latency hiding)
+                // tail efficiency of the last wave x how well the resident warps can keep the FP64 pipe fed
+                // (>= 2 warps per scheduler hide the store / update / barrier phases of each other)
+                const double eff = static_cast<double>(P) / (waves * slots) * std::min(1.0, per_sm * w / 8.0) + 1e-4 * per_sm * w;
+                if (eff > best) { best = eff; best_w = w; }
+            }
+            if (best > 0) {
+                pl.mma = true;
+                pl.WPC = best_w;
+                pl.threads = 32 * best_w;
+                pl.smem = 16 + matb * m->S + fbytes * best_w;
+                pl.fstride = static_cast<int>(fbytes / 8);
+                pl.bstride = static_cast<int>(matb / 8);
+                pl.tile = false;
+                return pl;
+            }
+        }
+    }
     pl.tile = m->tile_ok && !env_int("BILDK_FORCE_GENERIC", 0);
     if (!pl.tile) return pl;
     const int G = m->G, TPF = G * G;
@@ -322,8 +455,9 @@ static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
     const size_t fbytes = filter_doubles(m->NP, m->LD, pl.densew) * 8;
     pl.fstride = static_cast<int>(fbytes / 8);
     const size_t cap = static_cast<size_t>(m->max_smem_optin);
-    pl.b_all = 16 + matb * m->S + fbytes <= cap;
-    const size_t bbytes = matb * (pl.b_all ? m->S : 1);
+    pl.bstride = static_cast<int>(stride_8mod16(matb / 8));
+    pl.b_all = 16 + static_cast<size_t>(pl.bstride) * 8 * m->S + fbytes <= cap;
+    const size_t bbytes = pl.b_all ? static_cast<size_t>(pl.bstride) * 8 * m->S : matb;
     int fpc_smem = static_cast<int>((cap - 16 - bbytes) / fbytes);
     if (!pl.b_all) fpc_smem = 1;
     if (pl.ws) {
@@ -383,7 +517,10 @@ static cudaError_t launch_tile(const Plan& pl, const KParams& kp, dim3 grid, cud
 
 static std::string plan_string(const bildk_model* m, const Plan& pl) {
     char buf[256];
-    if (!pl.tile)
+    if (pl.mma)
+        snprintf(buf, sizeof buf, "mma (DMMA m8n8k4) GT=%d %s warp-per-filter WPC=%d threads=%d smem=%zu", m->GT,
+                 m->mma_mx ? "mean-in-extra-tile" : "mean-in-padding", pl.WPC, pl.threads, pl.smem);
+    else if (!pl.tile)
         snprintf(buf, sizeof buf, "generic N=%d (covariance in L2 workspace)", m->N);
     else
         snprintf(buf, sizeof buf, "tile TS=%d G=%d %s-scope %s-w B=%s FPC=%d threads=%d smem=%zu", pl.TS, m->G,
@@ -414,7 +551,7 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
         if (rc) return rc;
         d_part = m->part.p;
     }
-    if (pl.tile) {
+    if (pl.mma || pl.tile) {
         KParams kp{};
         kp.N = m->N; kp.D = m->D; kp.S = m->S; kp.G = m->G; kp.LD = m->LD; kp.NP = m->NP;
         kp.Bpad = m->dBpad; kp.Sigpad = m->dSigpad; kp.C0pad = m->dC0pad; kp.Gm = m->dG; kp.M0 = m->dM0; kp.w = m->dw;
@@ -427,7 +564,8 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
             for (int c = 0; c < DMAX; ++c) kp.cols[e][c] = t0->cols[e][c];
         }
         kp.P = P; kp.K1 = K1; kp.run_starts = d_starts; kp.run_states = d_states; kp.out = d_part;
-        kp.FPC = pl.FPC; kp.TPFS = pl.TPFS; kp.b_all = pl.b_all; kp.fstride = pl.fstride;
+        if (pl.mma) pl.FPC = pl.WPC;   // CTA -> first filter maps use FPC
+        kp.FPC = pl.FPC; kp.TPFS = pl.TPFS; kp.b_all = pl.b_all; kp.fstride = pl.fstride; kp.bstride = pl.bstride; kp.lane_ab = m->d_lane_ab;
         int n_cta = 0;
         if (n_traj == 1) {
             n_cta = (P + pl.FPC - 1) / pl.FPC;
@@ -446,7 +584,16 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
             kp.cta_traj = m->meta.p; kp.cta_first = m->meta.p + n_cta;
         }
         dim3 grid(n_cta, dstar);
-        CU(launch_tile(pl, kp, grid, st));
+        if (pl.mma) {
+            MParams mp{};
+            mp.k = kp;
+            mp.NPm = m->NPm; mp.LDB = m->LDBm; mp.LDC = m->LDCm; mp.MC0 = m->MC0; mp.NK = m->NK;
+            mp.Bm = m->dBm; mp.Sigm = m->dSigm; mp.C0m = m->dC0m;
+            mp.WPC = pl.WPC; mp.fstride_m = pl.fstride; mp.bstride_m = pl.bstride;
+            CU(mma_launch_for(m->GT, m->mma_mx, mp, grid, pl.threads, pl.smem, st));
+        } else {
+            CU(launch_tile(pl, kp, grid, st));
+        }
         g_launches++;
     } else {
         GParams gp{};

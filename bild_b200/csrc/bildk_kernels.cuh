@@ -66,7 +66,9 @@ struct KParams {
     int FPC;        // filters per CTA
     int TPFS;       // thread stride between filters of a CTA (>= G*G)
     int b_all;      // 1: all S propagators resident in smem; 0: only the current one (FPC == 1)
-    int fstride;    // doubles of shared memory per filter
+    int fstride;    // doubles of shared memory per filter (== 8 mod 16: neighbouring filters use disjoint banks)
+    int bstride;    // doubles between the propagators of consecutive states in shared memory (== 8 mod 16)
+    const uint16_t* lane_ab;   // [G*G] thread-in-filter -> (a << 8 | b); aligned lane quads own 2x2 tile blocks
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -164,8 +166,12 @@ __global__ void __launch_bounds__(MAXT, (WS && TS <= 5) ? 4 : 1) k_tile(const __
     const int pend = p.traj_first[tj + 1];
     const int pidx = first + fl;
     const bool alive = (fl < p.FPC) && (pidx < pend) && (l < TPF);
-    const int a = alive ? l / G : 0;
-    const int b = alive ? l - a * G : 0;
+    // Lane -> tile map: an aligned quad of lanes owns a 2x2 block of tiles, so every operand load sees at
+    // most 2 distinct addresses per quad (measured with tools/lds_patterns.cu: 4 distinct per quad doubles
+    // the shared-memory wavefronts of a warp-wide LDS.64/LDS.128)
+    const int ab = alive ? p.lane_ab[l] : 0;
+    const int a = ab >> 8;
+    const int b = ab & 0xff;
 
     // ---- stage propagators with TMA
     int s_loaded = -1;
@@ -173,11 +179,21 @@ __global__ void __launch_bounds__(MAXT, (WS && TS <= 5) ? 4 : 1) k_tile(const __
     if (tid == 0) mbar_init(mbar, 1);
     __syncthreads();
     if (p.b_all) {
-        if (tid == 0) tma_stage(Bsm, p.Bpad, matd * p.S * sizeof(double), mbar);
+        if (tid == 0) {
+            mbar_expect_tx(mbar, static_cast<uint32_t>(matd * p.S * sizeof(double)));
+            for (int st = 0; st < p.S; ++st) {
+                constexpr uint32_t CH = 32768;
+                const size_t bytes = matd * sizeof(double);
+                for (size_t off = 0; off < bytes; off += CH)
+                    tma_load_1d(reinterpret_cast<char*>(Bsm + static_cast<size_t>(st) * p.bstride) + off,
+                                reinterpret_cast<const char*>(p.Bpad + matd * st) + off,
+                                static_cast<uint32_t>(bytes - off < CH ? bytes - off : CH), mbar);
+            }
+        }
     }
 
     // ---- per-filter shared buffers
-    double* fbase = Bsm + matd * (p.b_all ? p.S : 1) + static_cast<size_t>(fl < p.FPC ? fl : 0) * p.fstride;
+    double* fbase = Bsm + (p.b_all ? static_cast<size_t>(p.bstride) * p.S : matd) + static_cast<size_t>(fl < p.FPC ? fl : 0) * p.fstride;
     double* Cb = fbase;                              // [NP][LD]   covariance / transposed intermediate
     double* Mb0 = Cb + matd;                         // [NP][MSTRIDE] mean used by the next propagation
     double* Mb1 = Mb0 + NP * MSTRIDE;                // [NP][MSTRIDE] prior mean of a valid frame
@@ -243,7 +259,7 @@ __global__ void __launch_bounds__(MAXT, (WS && TS <= 5) ? 4 : 1) k_tile(const __
                 bphase ^= 1;
                 s_loaded = s;
             }
-            const double* Bs = Bsm + (p.b_all ? matd * s : 0);
+            const double* Bs = Bsm + (p.b_all ? static_cast<size_t>(p.bstride) * s : 0);
             // ---------------- P1: T = B C (and M' = B M), operands: row k of B / C / M
             if (alive) {
 #pragma unroll
@@ -301,7 +317,7 @@ __global__ void __launch_bounds__(MAXT, (WS && TS <= 5) ? 4 : 1) k_tile(const __
                 const double* Sg = p.Sigpad + matd * s + static_cast<size_t>(a * TS) * LD + b * BS;
 #pragma unroll
                 for (int r = 0; r < TS; ++r) ldg_frag<TS>(acc[r], Sg + r * LD);
-                const double* Bs = Bsm + (p.b_all ? matd * s : 0);
+                const double* Bs = Bsm + (p.b_all ? static_cast<size_t>(p.bstride) * s : 0);
                 const double* Tp = Cb + a * BS;
                 const double* Bp = Bs + b * BS;
 #pragma unroll 2

@@ -1,0 +1,330 @@
+// FP64 tensor-core (DMMA m8n8k4) variant of the filter kernel: ONE WARP PER FILTER.
+//
+// Why: tools/lds_patterns.cu + the ncu capture of the DFMA tile kernel (profiles/) show that kernel bound
+// by shared-memory operand delivery (0.4 doubles loaded per FMA with 5x5 register tiles).  A DMMA
+// consumes 2 doubles per lane for 8 FMAs per lane and fragments are reused across the warp's tile
+// block, so a 3x3-tile filter (N <= 24) needs 0.083 doubles per FMA; the FP64 pipe becomes the limit.
+//
+// Per frame (MSRouse_logL.pyx:203-248), with the covariance as GT x GT tiles of 8 x 8 in registers
+// (lane l holds D[l>>2][2*(l&3) + {0,1}] of every tile):
+//   P1   T    = B_s [C | M]      A-fragments from B_s (row-major), B-fragments from the C buffer; the mean
+//                                columns ride in the padding columns N..N+d-1 of the last tile column
+//                                (or in one extra tile column when 8*GT - N < d), so M' = B_s M is free
+//   ---- T (and with it M') overwrites the C buffer, same row-major layout
+//   P2   C'   = T B_s + Sig      A-fragments from the buffer, B-fragments from B_s, accumulators start at Sig
+//   upd  rank-1 measurement update in the fragment layout (pyx:19-90); sparse w only
+//   ---- C+ (with M+ merged into its columns) overwrites the buffer
+// Row strides are == 4 (mod 8) doubles: tools/lds_patterns.cu shows 2 cycles per fragment load then
+// (the minimum for 256 distinct bytes) versus 4 for strides == 0 (mod 8).
+#pragma once
+#include "bildk_kernels.cuh"
+
+namespace bildk {
+
+struct MParams {
+    KParams k;                 // shared fields (model sizes, trajectories, batch); tile-layout fields unused
+    int NPm;                   // 8*GT
+    int LDB;                   // row stride of B / Sig / C0 (global and shared), == 4 mod 8
+    int LDC;                   // row stride of the per-filter buffer, == 4 mod 8, >= 8*GTC
+    int MC0;                   // first mean column inside the buffer
+    int NK;                    // 4*ceil(N/4): contraction length
+    const double* Bm;          // [S][NPm][LDB] zero padded
+    const double* Sigm;        // [S][NPm][LDB]
+    const double* C0m;         // [S][NPm][LDB]
+    int WPC;                   // warps (= filters) per CTA
+    int fstride_m;             // doubles of shared memory per filter
+    int bstride_m;             // doubles per state of B in shared memory
+};
+
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// GT: tiles per edge; MX: mean columns live in an extra tile column.  The measurement vector has exactly
+// two non-zeros (BILD's end-to-end distance, models.py:230-233); other vectors use the tile kernel.
+// Strides are compile-time (NPm = 8 GT, LDB = NPm + 4, LDC = 8 GTC + 4) so that all fragment addressing
+// folds into immediates.
+// register budget: GT <= 3 must keep 28 warps per SM resident (BASELINE config 2 is 27.7 filters per SM)
+template <int GT, bool MX>
+__global__ void __launch_bounds__(GT <= 3 ? 224 : 256, GT <= 3 ? 4 : (GT == 4 ? 2 : 1)) k_mma(const __grid_constant__ MParams mp) {
+    constexpr int GTC = GT + (MX ? 1 : 0);
+    constexpr int TJM = MX ? GT : GT - 1;   // tile column that contains the mean columns
+    constexpr int NPm = 8 * GT, LDB = NPm + 4, LDC = 8 * GTC + 4;
+    constexpr int MATB = NPm * LDB;
+    const KParams& p = mp.k;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
+    double* Bsm = reinterpret_cast<double*>(smem_raw + 16);
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int g = lane >> 2, c4 = lane & 3;
+    const int e_sub = blockIdx.y;
+    const int N = p.N, D = p.D, NK = mp.NK;
+
+    const int tj = p.cta_traj ? p.cta_traj[blockIdx.x] : 0;
+    const int first = p.cta_first ? p.cta_first[blockIdx.x] : blockIdx.x * mp.WPC;
+    const int pend = p.traj_first[tj + 1];
+    const int pidx = first + wid;
+    const bool alive = (wid < mp.WPC) && (pidx < pend);
+
+    if (tid == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(mbar, static_cast<uint32_t>(MATB * p.S * sizeof(double)));
+        for (int st = 0; st < p.S; ++st) {
+            constexpr uint32_t CH = 32768;
+            constexpr uint32_t bytes = MATB * sizeof(double);
+            for (uint32_t off = 0; off < bytes; off += CH)
+                tma_load_1d(reinterpret_cast<char*>(Bsm + st * MATB) + off, reinterpret_cast<const char*>(mp.Bm + static_cast<size_t>(MATB) * st) + off,
+                            bytes - off < CH ? bytes - off : CH, mbar);
+        }
+    }
+    if (!alive) return;   // warps are independent after this point (warp-scope barriers only)
+
+    double* Cb = Bsm + MATB * p.S + wid * mp.fstride_m;   // [NPm][LDC]
+    double* colb = Cb + NPm * LDC;                         // [2][NPm]
+
+    const int T = p.T[tj];
+    const double* __restrict__ xg = p.x[tj];
+    const uint8_t* __restrict__ vg = p.valid[tj];
+    const int ncols = p.ncols[e_sub];
+    const double s2 = p.s2[e_sub];
+
+    // the two non-zeros of w
+    const int j0 = p.wz_idx[0], j1 = p.wz_idx[1];
+    const double w0 = p.wz_val[0], w1 = p.wz_val[1];
+
+    // mean columns owned by this lane: buffer column MC0 + q  <->  tile TJM, local column 2*c4 + e
+    const int c0 = mp.MC0 - 8 * TJM;
+    const int q0 = 2 * c4 - c0, q1 = q0 + 1;
+    const bool qv0 = q0 >= 0 && q0 < ncols, qv1 = q1 >= 0 && q1 < ncols;
+    const int xc0 = qv0 ? p.cols[e_sub][q0] : 0, xc1 = qv1 ? p.cols[e_sub][q1] : 0;
+
+    // log-likelihood pieces (pyx:88), summed at the end: quad = sum xmm^2 Sinv over this lane's dimensions;
+    // sum_t log Sinv_t is kept as log(mantissa product) + exponent sum (one log per filter instead of per frame)
+    double quad = 0.0, lmant = 1.0;
+    int lexp = 0, nvalid = 0;
+
+    const int32_t* rs = p.run_starts + static_cast<size_t>(pidx) * p.K1;
+    const uint8_t* rt = p.run_states + static_cast<size_t>(pidx) * p.K1;
+    int r_cur = 0;
+    int s = rt[0];
+    int next_sw = (p.K1 > 1) ? rs[1] : 0x7fffffff;
+
+    double acc[GT][GTC][2];
+    double* const myC = Cb + g * LDC + 2 * c4;   // this lane's pair in tile (0,0); tile (ti,tj) at + 8*ti*LDC + 8*tj
+
+    mbar_wait(mbar, 0);
+
+    for (int t = 0; t < T; ++t) {
+        while (t >= next_sw) {
+            ++r_cur;
+            s = rt[r_cur];
+            next_sw = (r_cur + 1 < p.K1) ? rs[r_cur + 1] : 0x7fffffff;
+        }
+        const bool is_valid = vg[t] != 0;
+        double x0 = 0.0, x1 = 0.0;   // fetched early: consumed only after both products
+        if (is_valid) {
+            if (qv0) x0 = __ldg(xg + t * D + xc0);
+            if (qv1) x1 = __ldg(xg + t * D + xc1);
+        }
+        const double* Bs = Bsm + s * MATB;
+
+        if (t == 0) {
+            const double* C0 = mp.C0m + static_cast<size_t>(MATB) * s + g * LDB + 2 * c4;
+#pragma unroll
+            for (int ti = 0; ti < GT; ++ti)
+#pragma unroll
+                for (int tjj = 0; tjj < GT; ++tjj) {
+                    const double2 v = __ldg(reinterpret_cast<const double2*>(C0 + 8 * ti * LDB + 8 * tjj));
+                    acc[ti][tjj][0] = v.x;
+                    acc[ti][tjj][1] = v.y;
+                }
+        } else {
+            // ---------------- P1: T = B_s [C | M]
+#pragma unroll
+            for (int ti = 0; ti < GT; ++ti)
+#pragma unroll
+                for (int tjj = 0; tjj < GTC; ++tjj) acc[ti][tjj][0] = acc[ti][tjj][1] = 0.0;
+            {
+                const double* Ap = Bs + g * LDB + c4;
+                const double* Bp = Cb + c4 * LDC + g;
+#pragma unroll 1
+                for (int k0 = 0; k0 < NK; k0 += 4) {
+                    double a[GT], b[GTC];
+#pragma unroll
+                    for (int ti = 0; ti < GT; ++ti) a[ti] = Ap[8 * ti * LDB];
+#pragma unroll
+                    for (int tjj = 0; tjj < GTC; ++tjj) b[tjj] = Bp[8 * tjj];
+                    Ap += 4;
+                    Bp += 4 * LDC;
+#pragma unroll
+                    for (int ti = 0; ti < GT; ++ti)
+#pragma unroll
+                        for (int tjj = 0; tjj < GTC; ++tjj) dmma884(acc[ti][tjj], a[ti], b[tjj]);
+                }
+            }
+            __syncwarp();   // A: everybody finished reading C and M
+            // T (with M' in its mean columns) overwrites the buffer; each accumulator pair is refilled with
+            // its Sig entries right after it is stored, so the global-load latency hides behind the stores
+            {
+                const double* Sg = mp.Sigm + static_cast<size_t>(MATB) * s + g * LDB + 2 * c4;
+#pragma unroll
+                for (int ti = 0; ti < GT; ++ti)
+#pragma unroll
+                    for (int tjj = 0; tjj < GTC; ++tjj) {
+                        *reinterpret_cast<double2*>(myC + 8 * ti * LDC + 8 * tjj) = make_double2(acc[ti][tjj][0], acc[ti][tjj][1]);
+                        if (tjj < GT) {
+                            const double2 v = __ldg(reinterpret_cast<const double2*>(Sg + 8 * ti * LDB + 8 * tjj));
+                            acc[ti][tjj][0] = v.x;
+                            acc[ti][tjj][1] = v.y;
+                        }
+                    }
+            }
+            __syncwarp();   // B: T complete
+            // ---------------- P2: C' = T B_s + Sig
+            {
+                const double* Ap = Cb + g * LDC + c4;
+                const double* Bp = Bs + c4 * LDB + g;
+#pragma unroll 1
+                for (int k0 = 0; k0 < NK; k0 += 4) {
+                    double a[GT], b[GT];
+#pragma unroll
+                    for (int ti = 0; ti < GT; ++ti) a[ti] = Ap[8 * ti * LDC];
+#pragma unroll
+                    for (int tjj = 0; tjj < GT; ++tjj) b[tjj] = Bp[8 * tjj];
+                    Ap += 4;
+                    Bp += 4 * LDB;
+#pragma unroll
+                    for (int ti = 0; ti < GT; ++ti)
+#pragma unroll
+                        for (int tjj = 0; tjj < GT; ++tjj) dmma884(acc[ti][tjj], a[ti], b[tjj]);
+                }
+            }
+        }
+
+        // prior mean pair owned by this lane in tile row ti (rows 8*ti + g, mean columns q0, q1):
+        // M0 at t = 0, afterwards M' sits in the buffer's mean columns (it was written with T)
+        auto mean_prior = [&](int ti, double& m0, double& m1) {
+            const int row = 8 * ti + g;
+            if (t == 0) {
+                m0 = (qv0 && row < N) ? __ldg(p.M0 + (s * N + row) * D + xc0) : 0.0;
+                m1 = (qv1 && row < N) ? __ldg(p.M0 + (s * N + row) * D + xc1) : 0.0;
+            } else {
+                const double2 v = *reinterpret_cast<const double2*>(myC + 8 * ti * LDC + 8 * TJM);
+                m0 = qv0 ? v.x : 0.0;
+                m1 = qv1 ? v.y : 0.0;
+                if (p.hasG && row < N) {
+                    if (qv0) m0 += __ldg(p.Gm + (s * N + row) * D + xc0);
+                    if (qv1) m1 += __ldg(p.Gm + (s * N + row) * D + xc1);
+                }
+            }
+        };
+
+        if (is_valid) {
+            // publish the two columns of C' that w touches: column j lives in tile column j>>3, lanes with
+            // c4 == (j&7)>>1, element j&1
+#pragma unroll
+            for (int z = 0; z < 2; ++z) {
+                const int jz = z ? j1 : j0;
+                if (c4 == ((jz & 7) >> 1)) {
+                    const int tjz = jz >> 3;
+                    const bool hi = jz & 1;
+#pragma unroll
+                    for (int tjj = 0; tjj < GT; ++tjj)
+                        if (tjj == tjz) {
+#pragma unroll
+                            for (int ti = 0; ti < GT; ++ti) colb[z * NPm + 8 * ti + g] = hi ? acc[ti][tjj][1] : acc[ti][tjj][0];
+                        }
+                }
+            }
+            if (t == 0) {   // at t = 0 the mean is not in the buffer yet: put it where w . M' reads it
+#pragma unroll
+                for (int ti = 0; ti < GT; ++ti) {
+                    double m0, m1;
+                    mean_prior(ti, m0, m1);
+                    if (qv0) Cb[(8 * ti + g) * LDC + mp.MC0 + q0] = m0;
+                    if (qv1) Cb[(8 * ti + g) * LDC + mp.MC0 + q1] = m1;
+                }
+            }
+        }
+        __syncwarp();   // C: T no longer needed; published columns (and M') visible
+        double kr[GT];
+        double xm0 = 0.0, xm1 = 0.0;
+        if (is_valid) {
+            // S = s2 + w^T C' w, from the 2x2 block of C' at the non-zeros (pyx:55-63)
+            const double cw_j0 = fma(w1, colb[NPm + j0], w0 * colb[j0]);   // (C' w)[j0]
+            const double cw_j1 = fma(w1, colb[NPm + j1], w0 * colb[j1]);   // (C' w)[j1]
+            const double S = fma(w1, cw_j1, fma(w0, cw_j0, s2));
+            const double Sinv = __drcp_rn(S);                               // 1/S, correctly rounded (pyx:63)
+#pragma unroll
+            for (int ti = 0; ti < GT; ++ti)
+                kr[ti] = fma(w1, colb[NPm + 8 * ti + g], w0 * colb[8 * ti + g]) * Sinv;   // K = C' w / S (pyx:66-67)
+#pragma unroll
+            for (int tjj = 0; tjj < GT; ++tjj) {
+                const double2 u = *reinterpret_cast<const double2*>(colb + 8 * tjj + 2 * c4);
+                const double2 v = *reinterpret_cast<const double2*>(colb + NPm + 8 * tjj + 2 * c4);
+                const double c0v = fma(w1, v.x, w0 * u.x), c1v = fma(w1, v.y, w0 * u.y);   // (C' w)[column pair]
+#pragma unroll
+                for (int ti = 0; ti < GT; ++ti) {
+                    acc[ti][tjj][0] = fma(-kr[ti], c0v, acc[ti][tjj][0]);   // pyx:71-75
+                    acc[ti][tjj][1] = fma(-kr[ti], c1v, acc[ti][tjj][1]);
+                }
+            }
+            // innovation (pyx:79): x - w . M'  (G, if any, is not in the buffer: add w . G)
+            if (qv0) {
+                double ma = Cb[j0 * LDC + mp.MC0 + q0], mb = Cb[j1 * LDC + mp.MC0 + q0];
+                if (p.hasG && t > 0) { ma += __ldg(p.Gm + (s * N + j0) * D + xc0); mb += __ldg(p.Gm + (s * N + j1) * D + xc0); }
+                xm0 = x0 - fma(w1, mb, w0 * ma);
+                if (g == 0) quad = fma(xm0 * xm0, Sinv, quad);
+            }
+            if (qv1) {
+                double ma = Cb[j0 * LDC + mp.MC0 + q1], mb = Cb[j1 * LDC + mp.MC0 + q1];
+                if (p.hasG && t > 0) { ma += __ldg(p.Gm + (s * N + j0) * D + xc1); mb += __ldg(p.Gm + (s * N + j1) * D + xc1); }
+                xm1 = x1 - fma(w1, mb, w0 * ma);
+                if (g == 0) quad = fma(xm1 * xm1, Sinv, quad);
+            }
+            // running product of Sinv with the exponent split off (no overflow over thousands of frames)
+            lmant *= Sinv;
+            const int ex = ((__double2hiint(lmant) >> 20) & 0x7ff) - 1023;
+            lmant = __hiloint2double(__double2hiint(lmant) - (ex << 20), __double2loint(lmant));
+            lexp += ex;
+            ++nvalid;
+            __syncwarp();   // everybody has read w . M' before M+ lands in the buffer
+        }
+        // ---------------- C+ (and M+ in its columns) becomes the operand of the next propagation
+        if (t + 1 < T) {
+#pragma unroll
+            for (int ti = 0; ti < GT; ++ti) {
+                double m0, m1;
+                mean_prior(ti, m0, m1);
+                if (is_valid) {
+                    m0 = fma(kr[ti], xm0, m0);   // pyx:82-85
+                    m1 = fma(kr[ti], xm1, m1);
+                }
+#pragma unroll
+                for (int tjj = 0; tjj < GT; ++tjj) {
+                    double v0 = acc[ti][tjj][0], v1 = acc[ti][tjj][1];
+                    if (!MX && tjj == TJM) {
+                        if (qv0) v0 = m0;
+                        if (qv1) v1 = m1;
+                    }
+                    *reinterpret_cast<double2*>(myC + 8 * ti * LDC + 8 * tjj) = make_double2(v0, v1);
+                }
+                if (MX) *reinterpret_cast<double2*>(myC + 8 * ti * LDC + 8 * TJM) = make_double2(m0, m1);
+            }
+        }
+        __syncwarp();   // D
+    }
+
+    // logL = -1/2 [ sum xmm^2 Sinv - ncols * sum_t log Sinv_t + nvalid * ncols * log 2 pi ]   (pyx:88, 251-256)
+    quad += __shfl_xor_sync(0xffffffffu, quad, 1);   // lanes 0..3 (g == 0) hold the per-dimension sums
+    quad += __shfl_xor_sync(0xffffffffu, quad, 2);
+    if (lane == 0) {
+        const double logdet = log(lmant) + lexp * 0.6931471805599453;
+        p.out[static_cast<size_t>(e_sub) * p.P + pidx] = -0.5 * (quad - ncols * logdet + static_cast<double>(nvalid) * ncols * LOG_2PI);
+    }
+}
+
+}  // namespace bildk
