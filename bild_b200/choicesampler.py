@@ -1,0 +1,76 @@
+"""
+Which k to sample next?  Information-based sample selection for the iterative AMIS scheme.
+
+Behavioural mirror of /root/reference/bild/choicesampler.py (`ChoiceSampler`); host-side numpy, tiny
+(``samplesize x kmax`` normals), but it draws from the global numpy RNG (choicesampler.py:106), so the
+call order is part of the seed-parity contract and is kept.
+"""
+import numpy as np
+
+__all__ = ["ChoiceSampler"]
+
+
+class ChoiceSampler:
+    """
+    Monte-Carlo "choice distribution" p(k): how often is k the smallest k whose evidence lies within ``dE``
+    of the maximum, when the evidence curve is resampled within its error bars?
+
+    Parameters
+    ----------
+    muhat, shat : (k,) arrays
+        evidence estimates and the variances of these estimates
+    N : (k,) array (float, ``inf`` allowed)
+        number of AMIS steps behind each estimate
+    dE : float
+        evidence margin
+    samplesize : int
+        Monte-Carlo sample size
+    """
+
+    def __init__(self, muhat, shat, N, dE, samplesize=10000):
+        self.dE, self.muhat, self.shat, self.N, self.samplesize = dE, muhat, shat, N, samplesize
+        self.kmax = len(muhat)
+        self.EDmu2 = self.shat / (self.N + 1)       # expected squared move of the estimate after one more step
+        self.Dmu = np.sqrt(self.EDmu2)
+        self.init_sample()
+
+    def init_sample(self):
+        """(Re)draw the common random numbers all evaluations share, and the point estimate of p(k)."""
+        self._scaled_rvs = np.sqrt(self.shat[None, ...]) * np.random.normal(size=(self.samplesize, self.kmax))
+        self.bestk = self.evaluate()
+        self.best_is_k = self.bestk[:, None] == np.arange(self.kmax)[None, :]
+        self.n0 = np.sum(self.best_is_k, axis=0)
+
+    def evaluate(self, k_change=None, n_step=0, omit_k=None):
+        """Chosen k per Monte-Carlo draw, optionally with ``muhat[k_change]`` shifted by ``n_step * Dmu`` or
+        with some k ignored (``omit_k``)."""
+        mu = self.muhat.copy()
+        if k_change is not None:
+            mu[k_change] += n_step * self.Dmu[k_change]
+        if omit_k is not None:
+            mu[omit_k] = np.nan
+        draws = self._scaled_rvs + mu
+        top = np.nanmax(draws, axis=1, keepdims=True)
+        return np.nanargmax(top - self.dE - draws <= 0, axis=1)      # first k within dE of the maximum
+
+    def Dn(self):
+        """``[k1, k2]``: expected change of the count for k2 caused by one more sample at k1."""
+        counts = []
+        for step in (-0.5, 0.5):
+            picks = np.array([self.evaluate(k, step) for k in range(self.kmax)])              # (k_change, samp)
+            counts.append(np.sum(picks[..., None] == np.arange(self.kmax), axis=-2))          # (k_change, k)
+        return counts[1] - counts[0]
+
+    def KLD_moreSamples(self):
+        """Expected Kullback-Leibler gain of one more AMIS step at each k."""
+        Dn = self.Dn()
+        return 0.5 / self.samplesize * np.sum(Dn ** 2 / (self.n0 + 1)[None, :], axis=-1)
+
+    def KLD_omitK(self, omit_k=None):
+        """Information contributed by the positions ``omit_k``: KL(full choice distribution || without them)."""
+        without = self.evaluate(omit_k=omit_k)
+        old_n = np.sum(without[:, None] == np.arange(self.kmax)[None, :], axis=0)
+        old_n = old_n / np.sum(old_n) * self.samplesize
+        Dn = self.n0 - old_n
+        Dn[omit_k] = 0          # would contribute infinite KLD (old_n is 0 there); not of interest
+        return 0.5 / self.samplesize * np.sum(Dn ** 2 / (old_n + 1))

@@ -609,8 +609,10 @@ __global__ void __launch_bounds__(1024) k_amis_weights(int n, const double* __re
                                                        const double* __restrict__ logdelta,
                                                        const double* __restrict__ curlp, double log_nsteps,
                                                        double* __restrict__ log_w, double* __restrict__ stats) {
-    __shared__ double red[32][4];
+    __shared__ double red[32][2];
+    __shared__ double bc;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    // pass 1: log weights and their maximum
     double mx = -INFINITY;
     for (int i = tid; i < n; i += blockDim.x) {
         const double lw = logL[i] - logdelta[i] + log_nsteps;
@@ -620,27 +622,38 @@ __global__ void __launch_bounds__(1024) k_amis_weights(int n, const double* __re
     mx = warp_max(mx);
     if (lane == 0) red[wid][0] = mx;
     __syncthreads();
-    mx = (lane < nw) ? red[lane][0] : -INFINITY;
-    mx = warp_max(mx);
+    mx = warp_max((lane < nw) ? red[lane][0] : -INFINITY);
     __syncthreads();
-    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    for (int i = tid; i < n; i += blockDim.x) {
-        const double lw = logL[i] - logdelta[i] + log_nsteps;
-        const double wo = exp(lw - mx);
-        s1 += wo;
-        s2 = fma(wo, wo, s2);
-        const double term = wo * (logL[i] - curlp[i]);
-        if (term == term) s3 += term;   // nansum
-    }
-    s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
-    if (lane == 0) { red[wid][1] = s1; red[wid][2] = s2; red[wid][3] = s3; }
+    // pass 2: sum of the shifted weights
+    double s1 = 0.0;
+    for (int i = tid; i < n; i += blockDim.x) s1 += exp(logL[i] - logdelta[i] + log_nsteps - mx);
+    s1 = warp_sum(s1);
+    if (lane == 0) red[wid][0] = s1;
     __syncthreads();
     if (wid == 0) {
-        s1 = (lane < nw) ? red[lane][1] : 0.0;
-        s2 = (lane < nw) ? red[lane][2] : 0.0;
-        s3 = (lane < nw) ? red[lane][3] : 0.0;
-        s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
-        if (lane == 0) { stats[0] = mx; stats[1] = s1; stats[2] = s2; stats[3] = s3; }
+        s1 = warp_sum((lane < nw) ? red[lane][0] : 0.0);
+        if (lane == 0) bc = s1;
+    }
+    __syncthreads();
+    s1 = bc;
+    const double mean = s1 / n;
+    // pass 3: centred second moment (what scipy.stats.sem needs) and the KL numerator
+    double ssd = 0.0, s3 = 0.0;
+    for (int i = tid; i < n; i += blockDim.x) {
+        const double wo = exp(logL[i] - logdelta[i] + log_nsteps - mx);
+        const double dv = wo - mean;
+        ssd = fma(dv, dv, ssd);
+        const double term = wo * (logL[i] - curlp[i]);
+        if (term == term) s3 += term;   // nansum (amis.py:885-895)
+    }
+    ssd = warp_sum(ssd);
+    s3 = warp_sum(s3);
+    if (lane == 0) { red[wid][0] = ssd; red[wid][1] = s3; }
+    __syncthreads();
+    if (wid == 0) {
+        ssd = warp_sum((lane < nw) ? red[lane][0] : 0.0);
+        s3 = warp_sum((lane < nw) ? red[lane][1] : 0.0);
+        if (lane == 0) { stats[0] = mx; stats[1] = s1; stats[2] = ssd; stats[3] = s3; }
     }
 }
 

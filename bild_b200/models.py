@@ -195,6 +195,23 @@ class MultiStateRouse(MultiStateModel):
         """Batched ``logL(st2profile(s, theta), traj)`` for AMIS samples (replaces the loop at amis.py:735-739)."""
         return self.engine.logl_st(self._handle(traj), ss, thetas)
 
+    def amis_weights(self, logLs, logdeltas, cur_log_proposal, log_nsteps):
+        """
+        AMIS weight normalisation on the device (amis.py:843-845, 878-900): returns ``log_weights`` and
+        ``(max, sum w, sum (w - mean)^2, nansum w (logL - log q))`` with ``w = exp(log_weights - max)``,
+        reduced in a fixed order (identical bits on every rank).
+        """
+        import ctypes
+        from . import _lib
+        a, b, c = (_lib.as_f64(v) for v in (logLs, logdeltas, cur_log_proposal))
+        n = len(a)
+        log_w = np.empty(n)
+        st = np.empty(4)
+        dp = _lib.c_double_p
+        _lib.check(_lib.load().bildk_amis_weights(n, _lib.ptr(a, dp), _lib.ptr(b, dp), _lib.ptr(c, dp), float(log_nsteps),
+                                                  _lib.ptr(log_w, dp), _lib.ptr(st, dp), self.engine.device))
+        return log_w, tuple(st)
+
     # ------------------------------------------------------------------ helpers shared with the reference API
     def initial_loopingprofile(self, traj):
         return self.toFactorized().initial_loopingprofile(traj)

@@ -100,7 +100,8 @@ int bildk_logl_runs_multi(int n_traj, const bildk_traj_t *trajs, const int32_t *
 /*
  * AMIS weight normalisation (amis.py:843-845, 878-900), deterministic fixed-order reduction:
  *   log_w[i] = logL[i] - logdelta[i] + log_nsteps
- *   stats[0] = max_i log_w        stats[1] = sum_i exp(log_w - max)      stats[2] = sum_i exp(..)^2
+ *   stats[0] = max_i log_w        stats[1] = sum_i wo_i, wo_i = exp(log_w_i - max)
+ *   stats[2] = sum_i (wo_i - mean(wo))^2   (the centred second moment scipy.stats.sem needs, amis.py:884)
  *   stats[3] = sum_i exp(log_w - max) * (logL[i] - cur_log_proposal[i])   (NaN terms skipped, as nansum)
  * Host pointers; log_w may be NULL.  n >= 1.
  */

@@ -160,5 +160,48 @@ def main():
     print("st2profile cases:", len(hand))
 
 
+def sample_goldens():
+    """Full ``bild.sample`` runs of the unmodified reference under fixed seeds (host AMIS parity)."""
+    import scipy.stats
+    out = {}
+    # (a) FactorizedModel - the model the reference's own TestCore uses (tests/test_bild.py:224-283)
+    for seed in (1, 2, 3):
+        np.random.seed(seed)
+        model = bild.models.FactorizedModel([scipy.stats.maxwell(scale=1), scipy.stats.maxwell(scale=4)], d=1)
+        traj = nl.Trajectory(np.array([0.5, 0.7, 3.0, 5.0, 4.0, 0.8, 0.9, 6.0, 5.5, 0.3, 0.2, 4.0]))
+        res = bild.sample(traj, model, sampler_kw={"N": 50}, dE=1.0)
+        out[f"fact{seed}_k"] = res.k
+        out[f"fact{seed}_evidence"] = res.evidence
+        out[f"fact{seed}_evidence_se"] = res.evidence_se
+        out[f"fact{seed}_logk"] = res.log["k"]
+        out[f"fact{seed}_best"] = res.best_profile()[:]
+        out[f"fact{seed}_post"] = res.log_marginal_posterior()
+        out[f"fact{seed}_post_avg"] = res.log_marginal_posterior(dE="average")
+    out["fact_data"] = np.array([0.5, 0.7, 3.0, 5.0, 4.0, 0.8, 0.9, 6.0, 5.5, 0.3, 0.2, 4.0])
+
+    # (b) BASELINE.json configs[0]: MultiStateRouse N=20, d=3, T=100, localisation error, defaults
+    import bild.models as bm
+    bm.MSRouse_logL = ref_logL_cy                       # the reference's own compiled .pyx (its plugin slot)
+    np.random.seed(685441950)
+    model = bild.models.MultiStateRouse(20, 1, 5, d=3, localization_error=0.3)
+    truth = (np.arange(100) // 20) % 2
+    traj = model.trajectory_from_loopingprofile(bild.Loopingprofile(truth))
+    np.random.seed(1234)
+    res = bild.sample(traj, model)
+    out["c1_x"] = traj[:]
+    out["c1_truth"] = truth
+    out["c1_k"] = res.k
+    out["c1_evidence"] = res.evidence
+    out["c1_evidence_se"] = res.evidence_se
+    out["c1_logk"] = res.log["k"]
+    out["c1_best"] = res.best_profile()[:]
+    out["c1_post"] = res.log_marginal_posterior()
+    out["c1_n_logl_batches"] = np.array(sum(len(smp.samples) for smp in res.samplers))
+    print("C1: k", res.k, "best k", res.best_k(), "steps", len(res.log["k"]),
+          "profile recovered:", bool(np.all(res.best_profile()[:] == truth)))
+    np.savez_compressed(os.path.join(OUT, "sample_runs.npz"), **out)
+
+
 if __name__ == "__main__":
     main()
+    sample_goldens()

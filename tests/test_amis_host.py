@@ -1,0 +1,238 @@
+"""
+CPU tests of the host AMIS layer (bild_b200.amis / choicesampler / core / postproc): the known-answer
+values the reference's own tests hold (/root/reference/tests/test_amis.py, test_bild.py) and full
+``bild.sample`` runs recorded from the unmodified reference under fixed seeds (tests/golden/sample_runs.npz,
+produced by oracle/make_golden.py).
+"""
+import os
+
+import numpy as np
+import pytest
+import scipy.stats
+from scipy.special import logsumexp
+
+import kalman_oracle as ko
+import bild_b200 as bild
+from bild_b200 import amis
+
+
+@pytest.fixture(scope="module")
+def runs(golden_dir):
+    return np.load(os.path.join(golden_dir, "sample_runs.npz"))
+
+
+# ------------------------------------------------------------------ known answers from the reference's tests
+def test_dirichlet_kat():
+    d = amis.Dirichlet()
+    # test_amis.py:51-54: a < 1 with s == 0 -> +inf
+    assert d.logpdf(np.array([0.5, 1.0]), np.array([[0.0, 1.0]]))[0] == np.inf
+    assert np.isfinite(d.logpdf(np.array([1.0, 1.0]), np.array([[0.0, 1.0]]))[0])
+    # test_amis.py:56-63: method of moments
+    ss = np.array([[0.0, 1.0], [0.5, 0.5], [1.0, 0.0]])
+    assert np.array_equal(d.estimate(ss, np.zeros(3)), [0.25, 0.25])
+    assert np.array_equal(d.estimate(ss, np.array([1, 1, -np.inf])), [0.5, 1.5])
+    # density against scipy on random points
+    rng = np.random.default_rng(0)
+    a = rng.uniform(0.3, 4, size=5)
+    ss = rng.dirichlet(np.ones(5), size=50)
+    np.testing.assert_allclose(d.logpdf(a, ss), scipy.stats.dirichlet(a).logpdf(ss.T), rtol=1e-12)
+    np.random.seed(3)
+    x = d.sample(a, 7)
+    np.random.seed(3)
+    assert np.array_equal(x, scipy.stats.dirichlet(a).rvs(7))          # same RNG stream as the reference call
+
+
+def test_cfc_kat():
+    cfc = amis.CFC(~np.eye(3, dtype=bool))
+    for k in range(5):
+        assert cfc.N_total(k) == 3 * 2 ** k                                # test_amis.py: N_total = 3*2^k
+        full = cfc.full_sample(k)
+        assert full.shape == (3 * 2 ** k, k + 1)
+        assert len({tuple(r) for r in full}) == len(full)
+        assert np.all(full[:, 1:] != full[:, :-1])
+    assert np.array_equal(cfc.full_sample(1), [[0, 1], [0, 2], [1, 0], [1, 2], [2, 0], [2, 1]])
+    with pytest.raises(ValueError):
+        cfc.full_sample(10, Nmax=100)
+    # uniform proposal is uniform over traces
+    logp = cfc.logp_uniform(3)
+    np.testing.assert_allclose(cfc.logpmf(logp, cfc.full_sample(3)), -np.log(24), atol=1e-10)
+    np.testing.assert_allclose(logsumexp(cfc.logpmf(logp, cfc.full_sample(3))), 0, atol=1e-10)
+    # estimate: Kronecker-delta marginals survive
+    thetas = np.array([[0, 1, 0]] * 5)
+    est = cfc.estimate(thetas, np.zeros(5))
+    assert np.all(np.exp(est[[0, 1, 0], [0, 1, 2]]) > 1 - 1e-12)
+    # pathological transition matrix (test_amis.py: state 2 is absorbing-free): counts stay exact integers
+    tr = np.array([[0, 1, 0], [1, 0, 1], [0, 1, 0]], dtype=bool)
+    c2 = amis.CFC(tr)
+    assert c2.N_total(2) == int(np.sum(np.linalg.matrix_power(tr.astype(int), 2)))
+    m = c2.uniform_marginals(4)
+    np.testing.assert_allclose(logsumexp(m, axis=0), 0, atol=1e-12)
+    assert c2.N_total(300) > 10 ** 40                                       # python ints: no overflow
+    np.random.seed(0)
+    th = c2.sample(c2.logp_uniform(6), 200)
+    assert np.all(tr[th[:, :-1], th[:, 1:]])
+
+
+def test_cfc_pathological_transitions():
+    """/root/reference/tests/test_amis.py:66-97."""
+    cfc = amis.CFC([[0, 1, 1], [0, 0, 0], [1, 1, 0]])          # impossible to leave state 1
+    lm = cfc.uniform_marginals(4)
+    assert np.all(lm[1, :-1] == -np.inf) and lm[1, -1] != -np.inf
+    lp = cfc.logp_uniform(4)
+    assert np.all(lp[1, :-1] == -np.inf) and lp[1, -1] != -np.inf
+    cfc = amis.CFC([[0, 0, 1], [1, 0, 1], [1, 0, 0]])          # impossible to enter state 1
+    lm = cfc.uniform_marginals(4)
+    assert np.all(lm[1, 1:] == -np.inf) and lm[1, 0] != -np.inf
+    lp = cfc.logp_uniform(4)
+    assert np.all(lp[1, 1:] == -np.inf) and lp[1, 0] != -np.inf
+    logf = -np.log(2) * np.ones(3)
+    logf[1] = -np.inf
+    assert np.array_equal(cfc.solve_marginals_single(logf, np.array([-np.inf, 0., -np.inf])), logf)
+
+
+def test_cfc_matches_scipy_formulation():
+    """logpmf / estimate against the straightforward scipy.logsumexp(b=...) formulation."""
+    rng = np.random.default_rng(1)
+    tr = ~np.eye(3, dtype=bool)
+    cfc = amis.CFC(tr)
+    logp = np.log(rng.dirichlet(np.ones(3), size=5).T)
+    np.random.seed(5)
+    thetas = cfc.sample(logp, 300)
+    picked = np.take_along_axis(logp[None], thetas[:, None, :], axis=1)[:, 0, :]
+    norm = logsumexp(logp.T[None, 1:, :], b=tr[thetas[:, :-1]], axis=-1)
+    want = picked.sum(1) - norm.sum(1) - logsumexp(logp[:, 0])
+    np.testing.assert_allclose(cfc.logpmf(logp, thetas), want, rtol=1e-12, atol=1e-12)
+    lw = rng.normal(size=300)
+    ind = thetas[None] == np.arange(3)[:, None, None]
+    lm = logsumexp(lw[None, :, None], b=ind, axis=1)
+    lm -= logsumexp(lm, axis=0, keepdims=True)
+    np.testing.assert_allclose(cfc.estimate(thetas, lw), cfc.logp_from_marginals(lm), rtol=1e-10, atol=1e-12)
+
+
+def test_fixedk_sampler_basics():
+    model = bild.models.FactorizedModel([scipy.stats.maxwell(scale=1), scipy.stats.maxwell(scale=4)], d=1)
+    traj = bild.Trajectory(np.array([0.5, 0.7, 3.0, 5.0, 4.0, 0.8]))
+    s = amis.FixedkSampler(traj, model, k=2, N=10)
+    assert np.array_equal(s.st2profile(np.array([.25, .5, .25]), np.array([0, 1, 0])).state, [0, 0, 1, 1, 0, 0])   # test_amis.py:199-202
+    # k=2 on 6 frames: C(5,2)*2 = 20 profiles <= 1000 -> exhaustive, exact evidence
+    assert s.exhausted and len(s.samples) == 1 and len(s.samples[0]["logLs"]) == 20
+    assert s.step() is False
+    post = s.log_marginal_posterior()
+    np.testing.assert_allclose(logsumexp(post, axis=0), 0, atol=1e-10)      # test_amis.py:238-242
+    # exact evidence = log mean likelihood over all profiles
+    np.testing.assert_allclose(s.evidences[-1][0], logsumexp(s.samples[0]["logLs"]) - np.log(20), rtol=1e-12)
+    # k >= T: unidentifiable
+    s = amis.FixedkSampler(traj, model, k=6)
+    assert s.exhausted and s.evidences[-1][0] == -np.inf
+    # forced AMIS
+    np.random.seed(1)
+    s = amis.FixedkSampler(traj, model, k=2, N=10, max_fcomplete=1, max_fev=45)
+    assert not s.exhausted
+    assert s.step() and s.step() and s.step() and not s.exhausted            # (3+1)*10 < 45
+    assert s.step() and s.exhausted and s.step() is False                     # (4+1)*10 >= 45 (amis.py:903-904)
+    assert len(s.evidences) == 4 and all(np.isfinite(e[0]) and e[1] > 0 for e in s.evidences)
+    assert len(s.MAP_profile()) == 6
+
+
+def test_ensemble_states_match_st2profile():
+    model = bild.models.FactorizedModel([scipy.stats.maxwell(scale=1), scipy.stats.maxwell(scale=4)], d=1)
+    traj = bild.Trajectory(np.random.default_rng(0).uniform(0.2, 6.0, size=40))
+    np.random.seed(2)
+    s = amis.FixedkSampler(traj, model, k=4, N=30)
+    s.step()
+    s.step()
+    states = s._ensemble_states()
+    i = 0
+    for smp in s.samples:
+        for a, b in zip(smp["ss"], smp["thetas"]):
+            assert np.array_equal(states[i], s.st2profile(a, b).state)
+            i += 1
+
+
+# ------------------------------------------------------------------ recorded reference runs
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_sample_matches_reference_run_factorized(runs, seed):
+    np.random.seed(seed)
+    model = bild.models.FactorizedModel([scipy.stats.maxwell(scale=1), scipy.stats.maxwell(scale=4)], d=1)
+    traj = bild.Trajectory(runs["fact_data"])
+    res = bild.sample(traj, model, sampler_kw={"N": 50}, dE=1.0)
+    assert np.array_equal(res.k, runs[f"fact{seed}_k"])
+    assert np.array_equal(res.log["k"], runs[f"fact{seed}_logk"])
+    np.testing.assert_allclose(res.evidence, runs[f"fact{seed}_evidence"], rtol=1e-9)
+    np.testing.assert_allclose(res.evidence_se, runs[f"fact{seed}_evidence_se"], rtol=1e-7)
+    assert np.array_equal(res.best_profile()[:], runs[f"fact{seed}_best"])
+    np.testing.assert_allclose(np.exp(res.log_marginal_posterior()), np.exp(runs[f"fact{seed}_post"]), atol=1e-9)
+    np.testing.assert_allclose(np.exp(res.log_marginal_posterior(dE="average")), np.exp(runs[f"fact{seed}_post_avg"]), atol=1e-9)
+    # properties the reference's TestCore asserts (test_bild.py:237-248)
+    assert len(res.k) > 4 and np.all(res.evidence_se > 0)
+    assert res.best_profile() == res.best_profile(dE=res.dE)
+
+
+class OracleBackedRouse(bild.models.MultiStateRouse):
+    """Test double: the product's host model with the likelihood answered by the C ORACLE (CPU)."""
+
+    def logL_st_batch(self, ss, thetas, traj):
+        arrs = ko.model_arrays(self.models)
+        s2, cind = ko.noise_to_s2_cind(self._get_noise(traj))
+        st = np.array([ko.st2states(s, t, len(traj)) for s, t in zip(ss, thetas)])
+        return ko.logl_c(*arrs, self.measurement, traj[:], s2, cind, st)
+
+    def logL_batch(self, profiles, traj):
+        arrs = ko.model_arrays(self.models)
+        s2, cind = ko.noise_to_s2_cind(self._get_noise(traj))
+        return ko.logl_c(*arrs, self.measurement, traj[:], s2, cind, np.asarray(profiles))
+
+    def logL(self, profile, traj):
+        return float(self.logL_batch(np.asarray(profile[:])[None, :], traj)[0])
+
+    amis_weights = None    # host numpy weights
+
+    def __getattribute__(self, name):
+        if name == "amis_weights":
+            raise AttributeError(name)
+        return super().__getattribute__(name)
+
+
+def test_sample_matches_reference_run_rouse_config1(runs):
+    """BASELINE.json configs[0] with the host layer of the product and the oracle as likelihood."""
+    model = OracleBackedRouse(20, 1, 5, d=3, localization_error=0.3)
+    traj = bild.Trajectory(runs["c1_x"], localization_error=[0.3] * 3)
+    np.random.seed(1234)
+    res = bild.sample(traj, model)
+    assert np.array_equal(res.k, runs["c1_k"])
+    assert np.array_equal(res.log["k"], runs["c1_logk"])            # identical sequence of 140 AMIS steps
+    check_c1_evidence(res, runs)
+
+
+def check_c1_evidence(res, runs):
+    """
+    Evidences agree to 1e-9 relative - except where the reference's own profile discretisation is
+    ill-conditioned: a concentrated Dirichlet proposal emits interval lengths at rounding level
+    (s_last ~ 1e-16), so ``floor(cumsum(s) * (T-1))`` (amis.py:688) sits exactly on a frame boundary and a
+    1e-15 perturbation of the proposal (from a 1e-13 difference in logL) moves a switch by one frame.
+    Observed: 1 of 9 samplers, |d logE| ~ 2e-5, no effect on any decision.  Tolerate at most one such
+    sampler and only at that magnitude.
+    """
+    rel = np.abs(res.evidence - runs["c1_evidence"]) / np.abs(runs["c1_evidence"])
+    assert np.sum(rel > 1e-9) <= 1 and np.max(rel) < 1e-6
+    assert np.array_equal(res.best_profile()[:], runs["c1_best"])
+    np.testing.assert_allclose(np.exp(res.log_marginal_posterior()), np.exp(runs["c1_post"]), atol=1e-4)
+
+
+def test_postproc_with_batched_model():
+    """test_bild.py:302-321 analogue: greedy boundary optimisation, batch path == per-profile path."""
+    from bild_b200 import postproc
+    model = OracleBackedRouse(10, 1, 5, d=2, localization_error=0.2)
+    np.random.seed(4)
+    truth = bild.Loopingprofile([0] * 12 + [1] * 14 + [0] * 10)
+    traj = model.trajectory_from_loopingprofile(truth)
+    start = bild.Loopingprofile([0] * 10 + [1] * 18 + [0] * 8)
+    lr = postproc.logLR_boundaries(start, traj, model)
+    assert lr.shape == (2, 2)
+    base = model.logL(start, traj)
+    moved = start.copy(); moved[9] = 1
+    assert abs(lr[0, 0] - (model.logL(moved, traj) - base)) < 1e-9
+    opt = postproc.optimize_boundary(start, traj, model)
+    assert model.logL(opt, traj) >= base
+    assert opt.count_switches() == 2
+    assert len(postproc.logLR_boundaries(bild.Loopingprofile([1] * 36), traj, model)) == 0

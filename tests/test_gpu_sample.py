@@ -1,0 +1,89 @@
+"""
+GPU tests of the drop-in API: ``bild_b200.sample`` with the real engine against the run recorded from the
+unmodified reference (BASELINE.json configs[0]), the device AMIS-weight reduction against the oracle's
+restatement of amis.py:843-900, and the batched postproc caller.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import kalman_oracle as ko
+import bild_b200 as bild
+from test_amis_host import check_c1_evidence
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def runs(golden_dir):
+    return np.load(os.path.join(golden_dir, "sample_runs.npz"))
+
+
+def test_models_logL_reference_fixture():
+    """tests/test_bild.py:135-148 through the GPU: range, error-source equivalence, ValueError."""
+    traj = bild.Trajectory(np.array([1, 2, np.nan, 4]), localization_error=[0.5])
+    profile = bild.Loopingprofile([1, 1, 0, 0])
+    model = bild.models.MultiStateRouse(20, 1, 5, d=1)
+    v = model.logL(profile, traj)
+    assert -100 < v < 0
+    assert abs(v - (-10.2226225359098)) < 1e-9 * 10.3
+    model2 = bild.models.MultiStateRouse(20, 1, 5, d=1, localization_error=0.5)
+    assert model2.logL(profile, traj) == v
+    traj.localization_error = None
+    with pytest.raises(ValueError):
+        model.logL(profile, traj)
+    assert np.array_equal(model2.initial_loopingprofile(traj).state, [1, 0, 0, 0])
+
+
+def test_sample_config1_matches_reference_run(runs):
+    model = bild.models.MultiStateRouse(20, 1, 5, d=3, localization_error=0.3)
+    traj = bild.Trajectory(runs["c1_x"], localization_error=[0.3] * 3)
+    np.random.seed(1234)
+    res = bild.sample(traj, model)
+    assert np.array_equal(res.k, runs["c1_k"])
+    assert np.array_equal(res.log["k"], runs["c1_logk"])
+    check_c1_evidence(res, runs)
+    # every likelihood batch went through the CUDA library
+    from bild_b200 import _lib
+    assert _lib.load().bildk_launch_count() >= int(runs["c1_n_logl_batches"])
+
+
+def test_amis_weights_kernel():
+    rng = np.random.default_rng(0)
+    model = bild.models.MultiStateRouse(8, 1, 5, d=1, localization_error=0.5)
+    for n in (1, 2, 31, 1000, 20000):
+        logL = rng.normal(-400, 30, size=n)
+        logd = rng.normal(-30, 5, size=n)
+        cur = rng.normal(-30, 5, size=n)
+        if n > 10:
+            cur[3] = -np.inf            # weight-zero sample re-evaluated under the new proposal -> NaN term skipped
+            logd[5] = np.inf
+        want_lw, logev, dlogev, KL = ko.amis_evidence(logL, logd, cur, 7, -3.3) if n > 1 else (logL - logd + np.log(7), None, None, None)
+        lw, (mx, s1, ssd, s3) = model.amis_weights(logL, logd, cur, np.log(7))
+        assert np.array_equal(lw, want_lw)
+        if n > 1:
+            ev = s1 / n
+            assert abs(np.log(ev) + mx - 3.3 - logev) < 1e-12 * abs(logev)
+            sem = np.sqrt(ssd / (n - 1)) / np.sqrt(n)
+            assert abs(sem / ev - dlogev) < 1e-9 * dlogev
+            assert abs(s3 / n / ev - (np.log(ev) + mx - 3.3) - 3.3 - KL) < 1e-9 * max(1, abs(KL))
+    a = model.amis_weights(logL, logd, cur, np.log(7))
+    b = model.amis_weights(logL, logd, cur, np.log(7))
+    assert a[1] == b[1]                 # fixed-order reduction: bitwise reproducible
+
+
+def test_postproc_batched_on_gpu():
+    from bild_b200 import postproc
+    model = bild.models.MultiStateRouse(10, 1, 5, d=2, localization_error=0.2)
+    np.random.seed(4)
+    truth = bild.Loopingprofile([0] * 12 + [1] * 14 + [0] * 10)
+    traj = model.trajectory_from_loopingprofile(truth)
+    start = bild.Loopingprofile([0] * 10 + [1] * 18 + [0] * 8)
+    lr = postproc.logLR_boundaries(start, traj, model)
+    base = model.logL(start, traj)
+    moved = start.copy()
+    moved[28] = 1
+    assert abs(lr[1, 1] - (model.logL(moved, traj) - base)) < 1e-9
+    opt = postproc.optimize_boundary(start, traj, model)
+    assert model.logL(opt, traj) >= base and opt.count_switches() == 2
