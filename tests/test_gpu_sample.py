@@ -57,7 +57,8 @@ def test_amis_weights_kernel():
         logd = rng.normal(-30, 5, size=n)
         cur = rng.normal(-30, 5, size=n)
         if n > 10:
-            cur[3] = -np.inf            # weight-zero sample re-evaluated under the new proposal -> NaN term skipped
+            cur[3] = -np.inf            # weight-zero sample, impossible under the new proposal: 0 * inf = NaN, skipped
+            logd[3] = np.inf
             logd[5] = np.inf
         want_lw, logev, dlogev, KL = ko.amis_evidence(logL, logd, cur, 7, -3.3) if n > 1 else (logL - logd + np.log(7), None, None, None)
         lw, (mx, s1, ssd, s3) = model.amis_weights(logL, logd, cur, np.log(7))
