@@ -347,7 +347,7 @@ def run_gpu_arm(args, wl, rank, world, local_rank):
         "wall_s_timed_region": wall,
         "clocks": clocks,
         "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-                     "traffic": None, "kernel": "k_tile (Kalman filter over frames)", "kernel_ms": kavg_ms,
+                     "traffic": None, "kernel": th.describe_plan(P).split(" FPC")[0].split(" WPC")[0], "kernel_ms": kavg_ms,
                      "flop_per_launch": fl, "flop_model": "4N^3 d* per frame-step + lower-order terms (SURVEY.md 8d)",
                      "peak_source": f"measured in this run: DFMA {dfma.value:.2f}, DMMA {dmma.value:.2f} TFLOP/s (bildk_measure_fp64_peak)",
                      "hbm_streaming_model": {"bytes_per_frame_step": 16 * N * N,

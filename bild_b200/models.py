@@ -128,6 +128,7 @@ class MultiStateRouse(MultiStateModel):
         self.init_transitions(len(self.models))
 
         self.device = device
+        self._sharder = None
         self._engine = None
         self._handles = OrderedDict()   # id(traj) -> (fingerprint, TrajectoryHandle)
         self._max_handles = 8192
@@ -192,8 +193,22 @@ class MultiStateRouse(MultiStateModel):
         return self.engine.logl_states(self._handle(traj), states)
 
     def logL_st_batch(self, ss, thetas, traj):
-        """Batched ``logL(st2profile(s, theta), traj)`` for AMIS samples (replaces the loop at amis.py:735-739)."""
+        """Batched ``logL(st2profile(s, theta), traj)`` for AMIS samples (replaces the loop at amis.py:735-739).
+        With `shard_over` set, the batch is split across the ranks of a process group (bild_b200/dist.py)."""
+        if self._sharder is not None:
+            return self._sharder(lambda a, b: self._logL_st_local(a, b, traj), np.asarray(ss), np.asarray(thetas))
+        return self._logL_st_local(ss, thetas, traj)
+
+    def _logL_st_local(self, ss, thetas, traj):
         return self.engine.logl_st(self._handle(traj), ss, thetas)
+
+    def shard_over(self, group=None, device=None):
+        """Evaluate every AMIS batch sharded over the ranks of ``group`` (one all-gather of logL per batch)."""
+        from .dist import ShardedEvaluator
+        if device is None:
+            device = f"cuda:{self.engine.device}"
+        self._sharder = ShardedEvaluator(group, device)
+        return self
 
     def amis_weights(self, logLs, logdeltas, cur_log_proposal, log_nsteps):
         """
