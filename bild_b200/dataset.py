@@ -1,0 +1,155 @@
+"""
+Dataset runs: many trajectories through the full `sample` scheme with their likelihood batches fused.
+
+The reference analyses a dataset by calling ``bild.sample`` once per trajectory, one after the other
+(/root/reference/bild/core.py:22 has no dataset entry point); each call is a data-dependent sequential state
+machine (core.py:202-229) that needs a likelihood batch of only ``sampler_kw['N']`` (default 100) profiles
+per step - far too few to fill a B200.  `sample_many` runs all state machines concurrently and fuses the
+pending batches of all trajectories into ONE multi-trajectory launch per round (C ABI
+``bildk_logl_runs_multi``): SURVEY.md section 8(f) rank 2, BASELINE.json configs[3].
+
+Determinism: every trajectory owns its numpy RNG stream.  The state machines are cooperative (exactly one
+runs at a time, fixed round-robin order) and the global ``np.random`` state is swapped at every hand-over,
+so trajectory ``i`` consumes exactly the random numbers it would consume in
+``np.random.seed(seeds[i]); sample(trajs[i], model, ...)`` run on its own - the results are identical to
+the sequential runs, independent of how many trajectories share a launch or a GPU.
+
+Multi-GPU: trajectories are partitioned across ranks (`rank`, `world`); no communication during sampling.
+"""
+import threading
+
+import numpy as np
+
+from .core import sample
+from .engine import st_to_runs
+from .trajectory import make_Trajectory
+
+__all__ = ["sample_many"]
+
+
+class _Lane:
+    """One trajectory's state machine, running `sample` in its own thread, one step at a time."""
+
+    def __init__(self, idx, traj, seed):
+        self.idx, self.traj, self.seed = idx, traj, seed
+        self.go = threading.Semaphore(0)        # scheduler -> lane: run until your next likelihood request
+        self.request = None                      # (ss, thetas) waiting for evaluation
+        self.answer = None
+        self.result = None
+        self.error = None
+        self.done = False
+        self.rng_state = None
+
+
+class _FusingModel:
+    """
+    Per-lane proxy of the shared model: everything is forwarded, except that ``logL_st_batch`` parks the
+    request, hands control back to the scheduler and returns the answer it is given.
+    """
+
+    def __init__(self, model, lane, sched):
+        object.__setattr__(self, "_m", model)
+        object.__setattr__(self, "_lane", lane)
+        object.__setattr__(self, "_sched", sched)
+
+    def __getattr__(self, name):
+        return getattr(self._m, name)
+
+    def logL_st_batch(self, ss, thetas, traj):
+        lane = self._lane
+        lane.request = (np.asarray(ss, dtype=float), np.asarray(thetas))
+        lane.rng_state = np.random.get_state()
+        self._sched.release()                    # back to the scheduler
+        lane.go.acquire()                        # ... until the fused batch has been evaluated
+        np.random.set_state(lane.rng_state)
+        ans, lane.answer = lane.answer, None
+        return ans
+
+
+def sample_many(trajs, model, seeds=None, rank=0, world=1, max_active=None, **sample_kw):
+    """
+    Run `sample` on every trajectory, fusing the likelihood batches of all concurrently active trajectories.
+
+    Parameters
+    ----------
+    trajs : sequence of trajectories (anything `make_Trajectory` accepts)
+    model : bild_b200.models.MultiStateRouse
+    seeds : sequence of int, optional
+        numpy seed of each trajectory's private RNG stream (default: ``range(len(trajs))``)
+    rank, world : int
+        this process handles trajectories ``rank, rank + world, ...`` (one process per GPU)
+    max_active : int, optional
+        upper bound on concurrently running state machines (default: all of this rank's)
+    **sample_kw : forwarded to `sample` (dE, init_runs, sampler_kw, ...)
+
+    Returns
+    -------
+    dict  trajectory index -> SamplingResults   (this rank's trajectories)
+    stats : dict  launches, profiles and frame-steps evaluated
+    """
+    trajs = [make_Trajectory(t) for t in trajs]
+    if seeds is None:
+        seeds = list(range(len(trajs)))
+    mine = list(range(rank, len(trajs), world))
+    sched = threading.Semaphore(0)
+    outer_rng = np.random.get_state()
+    stats = {"launches": 0, "profiles": 0, "frame_steps": 0, "rounds": 0}
+
+    def body(lane):
+        lane.go.acquire()
+        try:
+            np.random.seed(lane.seed)
+            lane.result = sample(lane.traj, _FusingModel(model, lane, sched), **sample_kw)
+        except BaseException as err:  # noqa: BLE001 - reported by the scheduler thread
+            lane.error = err
+        lane.done = True
+        lane.rng_state = np.random.get_state()
+        sched.release()
+
+    pending = [_Lane(i, trajs[i], seeds[i]) for i in mine]
+    limit = max_active or len(pending) or 1
+    active, results = [], {}
+    while pending or active:
+        while pending and len(active) < limit:
+            lane = pending.pop(0)
+            threading.Thread(target=body, args=(lane,), daemon=True).start()
+            active.append(lane)
+        # let every active lane run (one at a time, fixed order) until it asks for likelihoods or finishes
+        for lane in active:
+            if lane.request is None and not lane.done:
+                lane.go.release()
+                sched.acquire()
+        for lane in [ln for ln in active if ln.done]:
+            if lane.error is not None:
+                raise lane.error
+            results[lane.idx] = lane.result
+            active.remove(lane)
+        waiting = [ln for ln in active if ln.request is not None]
+        if not waiting:
+            continue
+        # ---- fuse: one launch for all waiting trajectories; profiles with fewer runs are padded with
+        #      empty runs (start = T), which vanish exactly like the empty slices of st2profile
+        stats["rounds"] += 1
+        K1 = max(ln.request[0].shape[1] for ln in waiting)
+        starts, states, offsets = [], [], [0]
+        for ln in waiting:
+            ss, thetas = ln.request
+            if thetas.size and (thetas.min() < 0 or thetas.max() >= model.nStates):
+                raise ValueError("state index out of range")
+            a, b = st_to_runs(ss, thetas, len(ln.traj))
+            if a.shape[1] < K1:
+                extra = K1 - a.shape[1]
+                a = np.concatenate([a, np.full((len(a), extra), len(ln.traj), dtype=a.dtype)], axis=1)
+                b = np.concatenate([b, np.repeat(b[:, -1:], extra, axis=1)], axis=1)
+            starts.append(a)
+            states.append(b)
+            offsets.append(offsets[-1] + len(a))
+            stats["frame_steps"] += len(a) * (len(ln.traj) - 1)
+        out = model.logL_runs_multi([ln.traj for ln in waiting], offsets, np.concatenate(starts), np.concatenate(states))
+        stats["launches"] += 1
+        stats["profiles"] += offsets[-1]
+        for ln, lo, hi in zip(waiting, offsets[:-1], offsets[1:]):
+            ln.answer = out[lo:hi]
+            ln.request = None
+    np.random.set_state(outer_rng)
+    return results, stats

@@ -199,6 +199,11 @@ class MultiStateRouse(MultiStateModel):
             return self._sharder(lambda a, b: self._logL_st_local(a, b, traj), np.asarray(ss), np.asarray(thetas))
         return self._logL_st_local(ss, thetas, traj)
 
+    def logL_runs_multi(self, trajs, offsets, starts, run_states):
+        """Run-length profiles of MANY trajectories in one launch: profiles [offsets[i], offsets[i+1]) belong
+        to ``trajs[i]`` (used by `bild_b200.dataset.sample_many`)."""
+        return self.engine.logl_runs_multi([self._handle(t) for t in trajs], offsets, starts, run_states)
+
     def _logL_st_local(self, ss, thetas, traj):
         return self.engine.logl_st(self._handle(traj), ss, thetas)
 

@@ -185,6 +185,20 @@ class OracleBackedRouse(bild.models.MultiStateRouse):
     def logL(self, profile, traj):
         return float(self.logL_batch(np.asarray(profile[:])[None, :], traj)[0])
 
+    def logL_runs_multi(self, trajs, offsets, starts, run_states):
+        out = np.empty(offsets[-1])
+        arrs = ko.model_arrays(self.models)
+        for tr, lo, hi in zip(trajs, offsets[:-1], offsets[1:]):
+            T = len(tr)
+            st = np.empty((hi - lo, T), dtype=np.int32)
+            for p in range(lo, hi):
+                b = list(starts[p]) + [T]
+                for r in range(starts.shape[1]):
+                    st[p - lo, b[r]:max(b[r], b[r + 1])] = run_states[p, r]
+            s2, cind = ko.noise_to_s2_cind(self._get_noise(tr))
+            out[lo:hi] = ko.logl_c(*arrs, self.measurement, tr[:], s2, cind, st)
+        return out
+
     amis_weights = None    # host numpy weights
 
     def __getattribute__(self, name):
@@ -236,3 +250,29 @@ def test_postproc_with_batched_model():
     assert model.logL(opt, traj) >= base
     assert opt.count_switches() == 2
     assert len(postproc.logLR_boundaries(bild.Loopingprofile([1] * 36), traj, model)) == 0
+
+
+def test_sample_many_equals_sequential_runs():
+    """Dataset driver: fused multi-trajectory batches, per-trajectory RNG streams -> identical to one-by-one runs."""
+    from bild_b200.dataset import sample_many
+    model = OracleBackedRouse(8, 1, 5, d=2, localization_error=0.3)
+    np.random.seed(21)
+    trajs = [model.trajectory_from_loopingprofile(bild.Loopingprofile([0] * a + [1] * b + [0] * c))
+             for a, b, c in [(8, 9, 7), (12, 10, 0), (5, 5, 9), (20, 0, 0)]]
+    kw = dict(init_runs=4, sampler_kw={"N": 20, "max_fcomplete": 50}, k_max=4, certainty_in_k=0.9)
+    seeds = [101, 102, 103, 104]
+    res, stats = sample_many(trajs, model, seeds=seeds, **kw)
+    assert sorted(res) == [0, 1, 2, 3] and stats["launches"] == stats["rounds"] and stats["profiles"] > 0
+    for i, tr in enumerate(trajs):
+        np.random.seed(seeds[i])
+        solo = bild.sample(tr, model, **kw)
+        assert np.array_equal(solo.k, res[i].k)
+        assert np.array_equal(solo.log["k"], res[i].log["k"])
+        assert np.array_equal(solo.evidence, res[i].evidence)          # bitwise: same arithmetic, same random numbers
+        assert solo.best_profile() == res[i].best_profile()
+    # sharding by trajectory: rank r of 2 handles trajectories r, r+2
+    r1, _ = sample_many(trajs, model, seeds=seeds, rank=1, world=2, **kw)
+    assert sorted(r1) == [1, 3] and np.array_equal(r1[3].evidence, res[3].evidence)
+    # bounded concurrency gives the same answers
+    r2, _ = sample_many(trajs, model, seeds=seeds, max_active=2, **kw)
+    assert all(np.array_equal(r2[i].evidence, res[i].evidence) for i in range(4))
