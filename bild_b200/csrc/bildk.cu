@@ -267,26 +267,35 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
             m->GT = GT; m->NPm = 8 * GT;
             m->mma_mx = (m->NPm - N) < d;
             m->MC0 = m->mma_mx ? m->NPm : N;
-            m->LDBm = m->NPm + 4;
-            m->LDCm = 8 * (GT + (m->mma_mx ? 1 : 0)) + 4;
+            m->LDBm = (m->NPm + 15) / 16 * 16;
+            m->LDCm = (8 * (GT + (m->mma_mx ? 1 : 0)) + 15) / 16 * 16;
             m->NK = (N + 3) / 4 * 4;
             const size_t matb = static_cast<size_t>(m->NPm) * m->LDBm;
-            std::vector<double> pad(S * matb);
-            auto fill = [&](const double* src, bool sym) {
+            const size_t matg = static_cast<size_t>(m->NPm) * m->NPm;
+            // B: the shared-memory image (32-byte column groups XOR-swizzled by the row), TMA-copied verbatim
+            {
+                std::vector<double> pad(S * matb, 0.0);
+                for (int s = 0; s < S; ++s)
+                    for (int i = 0; i < N; ++i) {
+                        const int sw = ((i & 1) << 1) | ((i >> 1) & 1);
+                        for (int j = 0; j < N; ++j)
+                            pad[s * matb + static_cast<size_t>(i) * m->LDBm + ((((j >> 2) ^ sw) << 2) | (j & 3))] =
+                                B[s * NN + static_cast<size_t>(std::max(i, j)) * N + std::min(i, j)];
+                    }
+                if ((rc = upload(&m->dBm, pad.data(), S * matb))) { bildk_model_destroy(m); return rc; }
+            }
+            auto fill = [&](const double* src, std::vector<double>& pad) {
                 std::fill(pad.begin(), pad.end(), 0.0);
                 for (int s = 0; s < S; ++s)
                     for (int i = 0; i < N; ++i)
-                        for (int j = 0; j < N; ++j)
-                            pad[s * matb + static_cast<size_t>(i) * m->LDBm + j] =
-                                sym ? src[s * NN + static_cast<size_t>(std::max(i, j)) * N + std::min(i, j)] : src[s * NN + static_cast<size_t>(i) * N + j];
+                        for (int j = 0; j < N; ++j) pad[s * matg + static_cast<size_t>(i) * m->NPm + j] = src[s * NN + static_cast<size_t>(i) * N + j];
             };
-            fill(B, true);
-            if ((rc = upload(&m->dBm, pad.data(), S * matb))) { bildk_model_destroy(m); return rc; }
-            fill(Sig, false);
-            if ((rc = upload(&m->dSigm, pad.data(), S * matb))) { bildk_model_destroy(m); return rc; }
-            fill(C0, false);
-            if ((rc = upload(&m->dC0m, pad.data(), S * matb))) { bildk_model_destroy(m); return rc; }
-            const size_t fbytes = (static_cast<size_t>(m->NPm) * m->LDCm + static_cast<size_t>(2) * m->NPm) * 8;
+            std::vector<double> padg(S * matg);
+            fill(Sig, padg);
+            if ((rc = upload(&m->dSigm, padg.data(), S * matg))) { bildk_model_destroy(m); return rc; }
+            fill(C0, padg);
+            if ((rc = upload(&m->dC0m, padg.data(), S * matg))) { bildk_model_destroy(m); return rc; }
+            const size_t fbytes = (static_cast<size_t>(m->NPm) * m->LDCm + static_cast<size_t>(2) * m->NPm + 2) * 8;
             m->mma_ok = 16 + matb * 8 * S + fbytes <= static_cast<size_t>(m->max_smem_optin);
         }
     }
@@ -335,8 +344,17 @@ extern "C" int bildk_traj_create(bildk_model_t m, int T, const double* x, int ds
     const size_t nx = static_cast<size_t>(T) * m->D;
     CU(cudaMalloc(&t->dx, nx * sizeof(double)));
     CU(cudaMemcpy(t->dx, x, nx * sizeof(double), cudaMemcpyHostToDevice));
-    CU(cudaMalloc(&t->dvalid, T));
-    CU(cudaMemcpy(t->dvalid, valid.data(), T, cudaMemcpyHostToDevice));
+    // layout: T byte flags | pad to 4 bytes | ceil(T/32) packed words (bit i of word w = frame 32 w + i)
+    {
+        const size_t boff = (static_cast<size_t>(T) + 3) / 4 * 4;
+        const size_t nwords = (static_cast<size_t>(T) + 31) / 32;
+        std::vector<uint8_t> buf(boff + 4 * nwords, 0);
+        std::memcpy(buf.data(), valid.data(), T);
+        for (int i = 0; i < T; ++i)
+            if (valid[i]) buf[boff + 4 * (i / 32) + (i % 32) / 8] |= static_cast<uint8_t>(1u << (i % 8));   // little endian
+        CU(cudaMalloc(&t->dvalid, buf.size()));
+        CU(cudaMemcpy(t->dvalid, buf.data(), buf.size(), cudaMemcpyHostToDevice));
+    }
     CU(cudaMalloc(&t->d_xptr, sizeof(double*)));
     CU(cudaMalloc(&t->d_vptr, sizeof(uint8_t*)));
     CU(cudaMalloc(&t->d_T, sizeof(int)));
@@ -408,7 +426,7 @@ static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
         const bool want_mma = m->mma_ok && !(force && !strcmp(force, "tile")) && !env_int("BILDK_FORCE_GENERIC", 0);
         if (want_mma) {
             const size_t matb = static_cast<size_t>(m->NPm) * m->LDBm * 8;
-            const size_t fbytes = (static_cast<size_t>(m->NPm) * m->LDCm + static_cast<size_t>(2) * m->NPm) * 8;
+            const size_t fbytes = (static_cast<size_t>(m->NPm) * m->LDCm + static_cast<size_t>(2) * m->NPm + 2) * 8;
             const size_t cap = static_cast<size_t>(m->max_smem_optin);
             const size_t sm_total = 228 * 1024;
             const int regs = mma_regs_for(m->GT, m->mma_mx);
@@ -416,7 +434,8 @@ static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
             double best = -1;
             int best_w = 1;
             const int forced = env_int("BILDK_WPC", 0);
-            for (int w = 1; w <= 8; ++w) {
+            const int wmax = m->GT <= 3 ? 14 : 8;   // __launch_bounds__ of k_mma
+            for (int w = 1; w <= wmax; ++w) {
                 if (forced && w != forced) continue;
                 const size_t smem = 16 + matb * m->S + fbytes * w;
                 if (smem > cap) break;

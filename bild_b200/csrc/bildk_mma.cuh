@@ -14,8 +14,11 @@
 //   P2   C'   = T B_s + Sig      A-fragments from the buffer, B-fragments from B_s, accumulators start at Sig
 //   upd  rank-1 measurement update in the fragment layout (pyx:19-90); sparse w only
 //   ---- C+ (with M+ merged into its columns) overwrites the buffer
-// Row strides are == 4 (mod 8) doubles: tools/lds_patterns.cu shows 2 cycles per fragment load then
-// (the minimum for 256 distinct bytes) versus 4 for strides == 0 (mod 8).
+// Shared-memory layout: row stride a multiple of 128 bytes, 32-byte column groups XOR-swizzled by the
+// row ( group' = group ^ swz(row), swz(r) = ((r&1)<<1) | ((r>>1)&1) ).  Fragment loads (8 rows x 32 B or
+// 4 rows x 64 B per half warp) and accumulator-pair stores (2 rows x 64 B per quarter warp) are then all
+// conflict-free; the first version (stride == 4 mod 8, no swizzle) had ideal loads but 2x the ideal
+// wavefronts on every store (ncu: profiles/r01_ncu_c2_mma_v2.txt, tools/lds_patterns.cu).
 #pragma once
 #include "bildk_kernels.cuh"
 
@@ -24,13 +27,13 @@ namespace bildk {
 struct MParams {
     KParams k;                 // shared fields (model sizes, trajectories, batch); tile-layout fields unused
     int NPm;                   // 8*GT
-    int LDB;                   // row stride of B / Sig / C0 (global and shared), == 4 mod 8
-    int LDC;                   // row stride of the per-filter buffer, == 4 mod 8, >= 8*GTC
+    int LDB;                   // row stride of B (global pre-swizzled copy and shared), multiple of 16
+    int LDC;                   // row stride of the per-filter buffer, multiple of 16, >= 8*GTC
     int MC0;                   // first mean column inside the buffer
     int NK;                    // 4*ceil(N/4): contraction length
-    const double* Bm;          // [S][NPm][LDB] zero padded
-    const double* Sigm;        // [S][NPm][LDB]
-    const double* C0m;         // [S][NPm][LDB]
+    const double* Bm;          // [S][NPm][LDB] zero padded, swizzled like the shared copy
+    const double* Sigm;        // [S][NPm][NPm] zero padded, plain row-major
+    const double* C0m;         // [S][NPm][NPm]
     int WPC;                   // warps (= filters) per CTA
     int fstride_m;             // doubles of shared memory per filter
     int bstride_m;             // doubles per state of B in shared memory
@@ -43,15 +46,14 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
 
 // GT: tiles per edge; MX: mean columns live in an extra tile column.  The measurement vector has exactly
 // two non-zeros (BILD's end-to-end distance, models.py:230-233); other vectors use the tile kernel.
-// Strides are compile-time (NPm = 8 GT, LDB = NPm + 4, LDC = 8 GTC + 4) so that all fragment addressing
-// folds into immediates.
+// Strides are compile-time so that all fragment addressing folds into immediates.
 // register budget: GT <= 3 must keep 28 warps per SM resident (BASELINE config 2 is 27.7 filters per SM)
 template <int GT, bool MX>
-__global__ void __launch_bounds__(GT <= 3 ? 224 : 256, GT <= 3 ? 4 : (GT == 4 ? 2 : 1)) k_mma(const __grid_constant__ MParams mp) {
+__global__ void __launch_bounds__(GT <= 3 ? 448 : 256, GT <= 4 ? 2 : 1) k_mma(const __grid_constant__ MParams mp) {
     constexpr int GTC = GT + (MX ? 1 : 0);
     constexpr int TJM = MX ? GT : GT - 1;   // tile column that contains the mean columns
-    constexpr int NPm = 8 * GT, LDB = NPm + 4, LDC = 8 * GTC + 4;
-    constexpr int MATB = NPm * LDB;
+    constexpr int NPm = 8 * GT, LDB = (NPm + 15) / 16 * 16, LDC = (8 * GTC + 15) / 16 * 16;
+    constexpr int MATB = NPm * LDB, MATG = NPm * NPm;
     const KParams& p = mp.k;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -87,43 +89,58 @@ __global__ void __launch_bounds__(GT <= 3 ? 224 : 256, GT <= 3 ? 4 : (GT == 4 ? 
 
     const int T = p.T[tj];
     const double* __restrict__ xg = p.x[tj];
-    const uint8_t* __restrict__ vg = p.valid[tj];
+    // packed valid-frame bits live behind the byte flags (bildk_traj_create); one word per 32 frames
+    const uint32_t* __restrict__ vbits = reinterpret_cast<const uint32_t*>(p.valid[tj] + (T + 3) / 4 * 4);
+    uint32_t vword = 0;
     const int ncols = p.ncols[e_sub];
     const double s2 = p.s2[e_sub];
 
     // the two non-zeros of w
     const int j0 = p.wz_idx[0], j1 = p.wz_idx[1];
     const double w0 = p.wz_val[0], w1 = p.wz_val[1];
+    const int sw0 = ((j0 & 1) << 1) | ((j0 >> 1) & 1), sw1 = ((j1 & 1) << 1) | ((j1 >> 1) & 1);   // swizzle of rows j0, j1
 
     // mean columns owned by this lane: buffer column MC0 + q  <->  tile TJM, local column 2*c4 + e
-    const int c0 = mp.MC0 - 8 * TJM;
-    const int q0 = 2 * c4 - c0, q1 = q0 + 1;
-    const bool qv0 = q0 >= 0 && q0 < ncols, qv1 = q1 >= 0 && q1 < ncols;
-    const int xc0 = qv0 ? p.cols[e_sub][q0] : 0, xc1 = qv1 ? p.cols[e_sub][q1] : 0;
+    const int q0 = 2 * c4 - (mp.MC0 - 8 * TJM), q1 = q0 + 1;
+#define qv0 (static_cast<unsigned>(q0) < static_cast<unsigned>(ncols))
+#define qv1 (static_cast<unsigned>(q1) < static_cast<unsigned>(ncols))
+#define xc0 (p.cols[e_sub][qv0 ? q0 : 0])
+#define xc1 (p.cols[e_sub][qv1 ? q1 : 0])
 
     // log-likelihood pieces (pyx:88), summed at the end: quad = sum xmm^2 Sinv over this lane's dimensions;
     // sum_t log Sinv_t is kept as log(mantissa product) + exponent sum (one log per filter instead of per frame)
-    double quad = 0.0, lmant = 1.0;
-    int lexp = 0, nvalid = 0;
+    double quad = 0.0;
+    // running product of Sinv (mantissa) and its exponent sum / frame count live in shared memory: they are
+    // warp-uniform, touched once per valid frame, and registers are the scarce resource here
+    double* const lst = colb + 2 * NPm;          // [0] mantissa  [1] (int2) exponent sum, valid frames
+    if (lane == 0) { lst[0] = 1.0; reinterpret_cast<int*>(lst + 1)[0] = 0; reinterpret_cast<int*>(lst + 1)[1] = 0; }
 
-    const int32_t* rs = p.run_starts + static_cast<size_t>(pidx) * p.K1;
-    const uint8_t* rt = p.run_states + static_cast<size_t>(pidx) * p.K1;
     int r_cur = 0;
-    int s = rt[0];
-    int next_sw = (p.K1 > 1) ? rs[1] : 0x7fffffff;
+    int s = p.run_states[static_cast<size_t>(pidx) * p.K1];
+    int next_sw = (p.K1 > 1) ? p.run_starts[static_cast<size_t>(pidx) * p.K1 + 1] : 0x7fffffff;
 
     double acc[GT][GTC][2];
-    double* const myC = Cb + g * LDC + 2 * c4;   // this lane's pair in tile (0,0); tile (ti,tj) at + 8*ti*LDC + 8*tj
+    // swizzle constants of this lane: rows 8*ti + g share swz(g); rows k0 + c4 share swz(c4)
+    const int sg = ((g & 1) << 1) | ((g >> 1) & 1);
+    const int sc = ((c4 & 1) << 1) | ((c4 >> 1) & 1);
+    // accumulator pair of tile (ti, tj): row 8 ti + g, logical columns 8 tj + 2 c4 + {0,1} -> physical tile
+    // column tj ^ (sg>>1), 32-byte group (c4>>1) ^ (sg&1).  tj ^ 1 is tj + 1 for even and tj - 1 for odd tj:
+    double* const dE = Cb + g * LDC + ((c4 >> 1) ^ (sg & 1)) * 4 + (c4 & 1) * 2 + (sg >> 1) * 8;   // even tj
+    double* const dO = dE - (sg >> 1) * 16;                                                         // odd tj
+#define DPAIR(ti, tjj) (((tjj) & 1 ? dO : dE) + 8 * (ti) * LDC + 8 * (tjj))
+    // physical column of logical column c in a row whose swizzle is sw
+    auto pcol = [](int c, int sw) { return (((c >> 2) ^ sw) << 2) | (c & 3); };
 
     mbar_wait(mbar, 0);
 
     for (int t = 0; t < T; ++t) {
-        while (t >= next_sw) {
+        while (t >= next_sw) {   // rare: at most K1 - 1 times per filter; pointers are recomputed, not kept
             ++r_cur;
-            s = rt[r_cur];
-            next_sw = (r_cur + 1 < p.K1) ? rs[r_cur + 1] : 0x7fffffff;
+            s = p.run_states[static_cast<size_t>(pidx) * p.K1 + r_cur];
+            next_sw = (r_cur + 1 < p.K1) ? p.run_starts[static_cast<size_t>(pidx) * p.K1 + r_cur + 1] : 0x7fffffff;
         }
-        const bool is_valid = vg[t] != 0;
+        if ((t & 31) == 0) vword = __ldg(vbits + (t >> 5));
+        const bool is_valid = (vword >> (t & 31)) & 1u;
         double x0 = 0.0, x1 = 0.0;   // fetched early: consumed only after both products
         if (is_valid) {
             if (qv0) x0 = __ldg(xg + t * D + xc0);
@@ -132,12 +149,12 @@ __global__ void __launch_bounds__(GT <= 3 ? 224 : 256, GT <= 3 ? 4 : (GT == 4 ? 
         const double* Bs = Bsm + s * MATB;
 
         if (t == 0) {
-            const double* C0 = mp.C0m + static_cast<size_t>(MATB) * s + g * LDB + 2 * c4;
+            const double* C0 = mp.C0m + static_cast<size_t>(MATG) * s + g * NPm + 2 * c4;
 #pragma unroll
             for (int ti = 0; ti < GT; ++ti)
 #pragma unroll
                 for (int tjj = 0; tjj < GT; ++tjj) {
-                    const double2 v = __ldg(reinterpret_cast<const double2*>(C0 + 8 * ti * LDB + 8 * tjj));
+                    const double2 v = __ldg(reinterpret_cast<const double2*>(C0 + 8 * ti * NPm + 8 * tjj));
                     acc[ti][tjj][0] = v.x;
                     acc[ti][tjj][1] = v.y;
                 }
@@ -149,16 +166,18 @@ __global__ void __launch_bounds__(GT <= 3 ? 224 : 256, GT <= 3 ? 4 : (GT == 4 ? 
                 for (int tjj = 0; tjj < GTC; ++tjj) acc[ti][tjj][0] = acc[ti][tjj][1] = 0.0;
             {
                 const double* Ap = Bs + g * LDB + c4;
-                const double* Bp = Cb + c4 * LDC + g;
+                const double* BpE = Cb + c4 * LDC + (g & 3) + ((g >> 2) ^ (sc & 1)) * 4 + (sc >> 1) * 8;
+                const double* BpO = BpE - (sc >> 1) * 16;
 #pragma unroll 1
                 for (int k0 = 0; k0 < NK; k0 += 4) {
                     double a[GT], b[GTC];
+                    const int ao = ((k0 >> 2) ^ sg) << 2;
 #pragma unroll
-                    for (int ti = 0; ti < GT; ++ti) a[ti] = Ap[8 * ti * LDB];
+                    for (int ti = 0; ti < GT; ++ti) a[ti] = Ap[8 * ti * LDB + ao];
 #pragma unroll
-                    for (int tjj = 0; tjj < GTC; ++tjj) b[tjj] = Bp[8 * tjj];
-                    Ap += 4;
-                    Bp += 4 * LDC;
+                    for (int tjj = 0; tjj < GTC; ++tjj) b[tjj] = (tjj & 1 ? BpO : BpE)[8 * tjj];
+                    BpE += 4 * LDC;
+                    BpO += 4 * LDC;
 #pragma unroll
                     for (int ti = 0; ti < GT; ++ti)
 #pragma unroll
@@ -169,14 +188,14 @@ __global__ void __launch_bounds__(GT <= 3 ? 224 : 256, GT <= 3 ? 4 : (GT == 4 ? 
             // T (with M' in its mean columns) overwrites the buffer; each accumulator pair is refilled with
             // its Sig entries right after it is stored, so the global-load latency hides behind the stores
             {
-                const double* Sg = mp.Sigm + static_cast<size_t>(MATB) * s + g * LDB + 2 * c4;
+                const double* Sg = mp.Sigm + static_cast<size_t>(MATG) * s + g * NPm + 2 * c4;
 #pragma unroll
                 for (int ti = 0; ti < GT; ++ti)
 #pragma unroll
                     for (int tjj = 0; tjj < GTC; ++tjj) {
-                        *reinterpret_cast<double2*>(myC + 8 * ti * LDC + 8 * tjj) = make_double2(acc[ti][tjj][0], acc[ti][tjj][1]);
+                        *reinterpret_cast<double2*>(DPAIR(ti, tjj)) = make_double2(acc[ti][tjj][0], acc[ti][tjj][1]);
                         if (tjj < GT) {
-                            const double2 v = __ldg(reinterpret_cast<const double2*>(Sg + 8 * ti * LDB + 8 * tjj));
+                            const double2 v = __ldg(reinterpret_cast<const double2*>(Sg + 8 * ti * NPm + 8 * tjj));
                             acc[ti][tjj][0] = v.x;
                             acc[ti][tjj][1] = v.y;
                         }
@@ -186,16 +205,18 @@ __global__ void __launch_bounds__(GT <= 3 ? 224 : 256, GT <= 3 ? 4 : (GT == 4 ? 
             // ---------------- P2: C' = T B_s + Sig
             {
                 const double* Ap = Cb + g * LDC + c4;
-                const double* Bp = Bs + c4 * LDB + g;
+                const double* BpE = Bs + c4 * LDB + (g & 3) + ((g >> 2) ^ (sc & 1)) * 4 + (sc >> 1) * 8;
+                const double* BpO = BpE - (sc >> 1) * 16;
 #pragma unroll 1
                 for (int k0 = 0; k0 < NK; k0 += 4) {
                     double a[GT], b[GT];
+                    const int ao = ((k0 >> 2) ^ sg) << 2;
 #pragma unroll
-                    for (int ti = 0; ti < GT; ++ti) a[ti] = Ap[8 * ti * LDC];
+                    for (int ti = 0; ti < GT; ++ti) a[ti] = Ap[8 * ti * LDC + ao];
 #pragma unroll
-                    for (int tjj = 0; tjj < GT; ++tjj) b[tjj] = Bp[8 * tjj];
-                    Ap += 4;
-                    Bp += 4 * LDB;
+                    for (int tjj = 0; tjj < GT; ++tjj) b[tjj] = (tjj & 1 ? BpO : BpE)[8 * tjj];
+                    BpE += 4 * LDB;
+                    BpO += 4 * LDB;
 #pragma unroll
                     for (int ti = 0; ti < GT; ++ti)
 #pragma unroll
@@ -212,7 +233,7 @@ __global__ void __launch_bounds__(GT <= 3 ? 224 : 256, GT <= 3 ? 4 : (GT == 4 ? 
                 m0 = (qv0 && row < N) ? __ldg(p.M0 + (s * N + row) * D + xc0) : 0.0;
                 m1 = (qv1 && row < N) ? __ldg(p.M0 + (s * N + row) * D + xc1) : 0.0;
             } else {
-                const double2 v = *reinterpret_cast<const double2*>(myC + 8 * ti * LDC + 8 * TJM);
+                const double2 v = *reinterpret_cast<const double2*>(DPAIR(ti, TJM));
                 m0 = qv0 ? v.x : 0.0;
                 m1 = qv1 ? v.y : 0.0;
                 if (p.hasG && row < N) {
@@ -244,8 +265,8 @@ __global__ void __launch_bounds__(GT <= 3 ? 224 : 256, GT <= 3 ? 4 : (GT == 4 ? 
                 for (int ti = 0; ti < GT; ++ti) {
                     double m0, m1;
                     mean_prior(ti, m0, m1);
-                    if (qv0) Cb[(8 * ti + g) * LDC + mp.MC0 + q0] = m0;
-                    if (qv1) Cb[(8 * ti + g) * LDC + mp.MC0 + q1] = m1;
+                    if (qv0) Cb[(8 * ti + g) * LDC + pcol(mp.MC0 + q0, sg)] = m0;
+                    if (qv1) Cb[(8 * ti + g) * LDC + pcol(mp.MC0 + q1, sg)] = m1;
                 }
             }
         }
@@ -274,23 +295,26 @@ __global__ void __launch_bounds__(GT <= 3 ? 224 : 256, GT <= 3 ? 4 : (GT == 4 ? 
             }
             // innovation (pyx:79): x - w . M'  (G, if any, is not in the buffer: add w . G)
             if (qv0) {
-                double ma = Cb[j0 * LDC + mp.MC0 + q0], mb = Cb[j1 * LDC + mp.MC0 + q0];
+                double ma = Cb[j0 * LDC + pcol(mp.MC0 + q0, sw0)], mb = Cb[j1 * LDC + pcol(mp.MC0 + q0, sw1)];
                 if (p.hasG && t > 0) { ma += __ldg(p.Gm + (s * N + j0) * D + xc0); mb += __ldg(p.Gm + (s * N + j1) * D + xc0); }
                 xm0 = x0 - fma(w1, mb, w0 * ma);
                 if (g == 0) quad = fma(xm0 * xm0, Sinv, quad);
             }
             if (qv1) {
-                double ma = Cb[j0 * LDC + mp.MC0 + q1], mb = Cb[j1 * LDC + mp.MC0 + q1];
+                double ma = Cb[j0 * LDC + pcol(mp.MC0 + q1, sw0)], mb = Cb[j1 * LDC + pcol(mp.MC0 + q1, sw1)];
                 if (p.hasG && t > 0) { ma += __ldg(p.Gm + (s * N + j0) * D + xc1); mb += __ldg(p.Gm + (s * N + j1) * D + xc1); }
                 xm1 = x1 - fma(w1, mb, w0 * ma);
                 if (g == 0) quad = fma(xm1 * xm1, Sinv, quad);
             }
             // running product of Sinv with the exponent split off (no overflow over thousands of frames)
-            lmant *= Sinv;
-            const int ex = ((__double2hiint(lmant) >> 20) & 0x7ff) - 1023;
-            lmant = __hiloint2double(__double2hiint(lmant) - (ex << 20), __double2loint(lmant));
-            lexp += ex;
-            ++nvalid;
+            if (lane == 0) {
+                double lmant = lst[0] * Sinv;
+                const int ex = ((__double2hiint(lmant) >> 20) & 0x7ff) - 1023;
+                lmant = __hiloint2double(__double2hiint(lmant) - (ex << 20), __double2loint(lmant));
+                lst[0] = lmant;
+                reinterpret_cast<int*>(lst + 1)[0] += ex;
+                reinterpret_cast<int*>(lst + 1)[1] += 1;
+            }
             __syncwarp();   // everybody has read w . M' before M+ lands in the buffer
         }
         // ---------------- C+ (and M+ in its columns) becomes the operand of the next propagation
@@ -310,9 +334,9 @@ __global__ void __launch_bounds__(GT <= 3 ? 224 : 256, GT <= 3 ? 4 : (GT == 4 ? 
                         if (qv0) v0 = m0;
                         if (qv1) v1 = m1;
                     }
-                    *reinterpret_cast<double2*>(myC + 8 * ti * LDC + 8 * tjj) = make_double2(v0, v1);
+                    *reinterpret_cast<double2*>(DPAIR(ti, tjj)) = make_double2(v0, v1);
                 }
-                if (MX) *reinterpret_cast<double2*>(myC + 8 * ti * LDC + 8 * TJM) = make_double2(m0, m1);
+                if (MX) *reinterpret_cast<double2*>(DPAIR(ti, TJM)) = make_double2(m0, m1);
             }
         }
         __syncwarp();   // D
@@ -322,9 +346,15 @@ __global__ void __launch_bounds__(GT <= 3 ? 224 : 256, GT <= 3 ? 4 : (GT == 4 ? 
     quad += __shfl_xor_sync(0xffffffffu, quad, 1);   // lanes 0..3 (g == 0) hold the per-dimension sums
     quad += __shfl_xor_sync(0xffffffffu, quad, 2);
     if (lane == 0) {
-        const double logdet = log(lmant) + lexp * 0.6931471805599453;
+        const int lexp = reinterpret_cast<const int*>(lst + 1)[0], nvalid = reinterpret_cast<const int*>(lst + 1)[1];
+        const double logdet = log(lst[0]) + lexp * 0.6931471805599453;
         p.out[static_cast<size_t>(e_sub) * p.P + pidx] = -0.5 * (quad - ncols * logdet + static_cast<double>(nvalid) * ncols * LOG_2PI);
     }
 }
 
+#undef DPAIR
+#undef qv0
+#undef qv1
+#undef xc0
+#undef xc1
 }  // namespace bildk
