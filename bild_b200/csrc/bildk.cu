@@ -267,8 +267,9 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
             m->GT = GT; m->NPm = 8 * GT;
             m->mma_mx = (m->NPm - N) < d;
             m->MC0 = m->mma_mx ? m->NPm : N;
-            m->LDBm = (m->NPm + 15) / 16 * 16;
-            m->LDCm = (8 * (GT + (m->mma_mx ? 1 : 0)) + 15) / 16 * 16;
+            const bool swz = GT <= 4;   // must match k_mma's SWZ
+            m->LDBm = swz ? (m->NPm + 15) / 16 * 16 : m->NPm + 4;
+            m->LDCm = swz ? (8 * (GT + (m->mma_mx ? 1 : 0)) + 15) / 16 * 16 : 8 * (GT + (m->mma_mx ? 1 : 0)) + 4;
             m->NK = (N + 3) / 4 * 4;
             const size_t matb = static_cast<size_t>(m->NPm) * m->LDBm;
             const size_t matg = static_cast<size_t>(m->NPm) * m->NPm;
@@ -277,7 +278,7 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
                 std::vector<double> pad(S * matb, 0.0);
                 for (int s = 0; s < S; ++s)
                     for (int i = 0; i < N; ++i) {
-                        const int sw = ((i & 1) << 1) | ((i >> 1) & 1);
+                        const int sw = swz ? (((i & 1) << 1) | ((i >> 1) & 1)) : 0;
                         for (int j = 0; j < N; ++j)
                             pad[s * matb + static_cast<size_t>(i) * m->LDBm + ((((j >> 2) ^ sw) << 2) | (j & 3))] =
                                 B[s * NN + static_cast<size_t>(std::max(i, j)) * N + std::min(i, j)];

@@ -46,14 +46,33 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
 
 // GT: tiles per edge; MX: mean columns live in an extra tile column.  The measurement vector has exactly
 // two non-zeros (BILD's end-to-end distance, models.py:230-233); other vectors use the tile kernel.
-// Strides are compile-time so that all fragment addressing folds into immediates.
-// register budget: GT <= 3 must keep 28 warps per SM resident (BASELINE config 2 is 27.7 filters per SM)
+//
+// Symmetry: C' = B C B + Sig is symmetric, so P2 computes only the NU = GT (GT+1)/2 upper tiles (ti <= tj)
+// and mirrors them when the posterior is written back: 3 N^3 instead of 4 N^3 executed flops, and a
+// third fewer accumulator registers.  T = B [C | M] is not symmetric; it is produced IN PLACE by column
+// blocks of CB = (GT+1)/2 tile columns (block J reads only C[:, J] and overwrites it with T[:, J]), which
+// needs GT * CB <= NU accumulators - the same registers.
+//
+// Strides are compile-time so that all fragment addressing folds into immediates.  For GT <= 4 the row
+// stride is a multiple of 128 bytes with XOR-swizzled 32-byte groups (all loads and stores conflict-free);
+// for larger GT the stride is == 4 (mod 8) doubles without swizzle (ideal fragment loads, 2x wavefronts on
+// the comparatively rare stores) because the padded stride would cost a resident filter per SM.
+// Register budget: GT <= 3 must keep 28 warps per SM resident (BASELINE config 2 is 27.7 filters per SM).
 template <int GT, bool MX>
 __global__ void __launch_bounds__(GT <= 3 ? 448 : 256, GT <= 4 ? 2 : 1) k_mma(const __grid_constant__ MParams mp) {
     constexpr int GTC = GT + (MX ? 1 : 0);
     constexpr int TJM = MX ? GT : GT - 1;   // tile column that contains the mean columns
-    constexpr int NPm = 8 * GT, LDB = (NPm + 15) / 16 * 16, LDC = (8 * GTC + 15) / 16 * 16;
+    constexpr bool SWZ = GT <= 4;
+    constexpr int NPm = 8 * GT;
+    constexpr int LDB = SWZ ? (NPm + 15) / 16 * 16 : NPm + 4;
+    constexpr int LDC = SWZ ? (8 * GTC + 15) / 16 * 16 : 8 * GTC + 4;
     constexpr int MATB = NPm * LDB, MATG = NPm * NPm;
+    constexpr int NU = GT * (GT + 1) / 2;          // upper tiles
+    constexpr int CB = (GT + 1) / 2;               // tile columns per P1 pass
+    constexpr int NPASS = (GTC + CB - 1) / CB;
+    static_assert(GT * CB <= NU || GT == 2, "P1 pass must fit the accumulator file");
+    constexpr int NACC = (GT * CB > NU) ? GT * CB : NU;
+#define UIDX(ti, tjj) ((ti) * GT - (ti) * ((ti) - 1) / 2 + ((tjj) - (ti)))
     const KParams& p = mp.k;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -98,7 +117,9 @@ __global__ void __launch_bounds__(GT <= 3 ? 448 : 256, GT <= 4 ? 2 : 1) k_mma(co
     // the two non-zeros of w
     const int j0 = p.wz_idx[0], j1 = p.wz_idx[1];
     const double w0 = p.wz_val[0], w1 = p.wz_val[1];
-    const int sw0 = ((j0 & 1) << 1) | ((j0 >> 1) & 1), sw1 = ((j1 & 1) << 1) | ((j1 >> 1) & 1);   // swizzle of rows j0, j1
+    auto swz = [](int r) { return SWZ ? (((r & 1) << 1) | ((r >> 1) & 1)) : 0; };
+    // physical column of logical column c in a row whose swizzle is sw
+    auto pcol = [](int c, int sw) { return (((c >> 2) ^ sw) << 2) | (c & 3); };
 
     // mean columns owned by this lane: buffer column MC0 + q  <->  tile TJM, local column 2*c4 + e
     const int q0 = 2 * c4 - (mp.MC0 - 8 * TJM), q1 = q0 + 1;
@@ -119,17 +140,14 @@ __global__ void __launch_bounds__(GT <= 3 ? 448 : 256, GT <= 4 ? 2 : 1) k_mma(co
     int s = p.run_states[static_cast<size_t>(pidx) * p.K1];
     int next_sw = (p.K1 > 1) ? p.run_starts[static_cast<size_t>(pidx) * p.K1 + 1] : 0x7fffffff;
 
-    double acc[GT][GTC][2];
+    double acc[NACC][2];
     // swizzle constants of this lane: rows 8*ti + g share swz(g); rows k0 + c4 share swz(c4)
-    const int sg = ((g & 1) << 1) | ((g >> 1) & 1);
-    const int sc = ((c4 & 1) << 1) | ((c4 >> 1) & 1);
+    const int sg = swz(g), sc = swz(c4);
     // accumulator pair of tile (ti, tj): row 8 ti + g, logical columns 8 tj + 2 c4 + {0,1} -> physical tile
     // column tj ^ (sg>>1), 32-byte group (c4>>1) ^ (sg&1).  tj ^ 1 is tj + 1 for even and tj - 1 for odd tj:
     double* const dE = Cb + g * LDC + ((c4 >> 1) ^ (sg & 1)) * 4 + (c4 & 1) * 2 + (sg >> 1) * 8;   // even tj
     double* const dO = dE - (sg >> 1) * 16;                                                         // odd tj
 #define DPAIR(ti, tjj) (((tjj) & 1 ? dO : dE) + 8 * (ti) * LDC + 8 * (tjj))
-    // physical column of logical column c in a row whose swizzle is sw
-    auto pcol = [](int c, int sw) { return (((c >> 2) ^ sw) << 2) | (c & 3); };
 
     mbar_wait(mbar, 0);
 
@@ -147,81 +165,82 @@ __global__ void __launch_bounds__(GT <= 3 ? 448 : 256, GT <= 4 ? 2 : 1) k_mma(co
             if (qv1) x1 = __ldg(xg + t * D + xc1);
         }
         const double* Bs = Bsm + s * MATB;
+        const double* Gsrc = (t == 0) ? mp.C0m + static_cast<size_t>(MATG) * s : mp.Sigm + static_cast<size_t>(MATG) * s;
+        Gsrc += g * NPm + 2 * c4;
 
-        if (t == 0) {
-            const double* C0 = mp.C0m + static_cast<size_t>(MATG) * s + g * NPm + 2 * c4;
+        if (t > 0) {
+            // ---------------- P1: T = B_s [C | M], in place, one block of CB tile columns at a time
 #pragma unroll
-            for (int ti = 0; ti < GT; ++ti)
-#pragma unroll
-                for (int tjj = 0; tjj < GT; ++tjj) {
-                    const double2 v = __ldg(reinterpret_cast<const double2*>(C0 + 8 * ti * NPm + 8 * tjj));
-                    acc[ti][tjj][0] = v.x;
-                    acc[ti][tjj][1] = v.y;
-                }
-        } else {
-            // ---------------- P1: T = B_s [C | M]
-#pragma unroll
-            for (int ti = 0; ti < GT; ++ti)
-#pragma unroll
-                for (int tjj = 0; tjj < GTC; ++tjj) acc[ti][tjj][0] = acc[ti][tjj][1] = 0.0;
-            {
-                const double* Ap = Bs + g * LDB + c4;
-                const double* BpE = Cb + c4 * LDC + (g & 3) + ((g >> 2) ^ (sc & 1)) * 4 + (sc >> 1) * 8;
-                const double* BpO = BpE - (sc >> 1) * 16;
-#pragma unroll 1
-                for (int k0 = 0; k0 < NK; k0 += 4) {
-                    double a[GT], b[GTC];
-                    const int ao = ((k0 >> 2) ^ sg) << 2;
-#pragma unroll
-                    for (int ti = 0; ti < GT; ++ti) a[ti] = Ap[8 * ti * LDB + ao];
-#pragma unroll
-                    for (int tjj = 0; tjj < GTC; ++tjj) b[tjj] = (tjj & 1 ? BpO : BpE)[8 * tjj];
-                    BpE += 4 * LDC;
-                    BpO += 4 * LDC;
-#pragma unroll
-                    for (int ti = 0; ti < GT; ++ti)
-#pragma unroll
-                        for (int tjj = 0; tjj < GTC; ++tjj) dmma884(acc[ti][tjj], a[ti], b[tjj]);
-                }
-            }
-            __syncwarp();   // A: everybody finished reading C and M
-            // T (with M' in its mean columns) overwrites the buffer; each accumulator pair is refilled with
-            // its Sig entries right after it is stored, so the global-load latency hides behind the stores
-            {
-                const double* Sg = mp.Sigm + static_cast<size_t>(MATG) * s + g * NPm + 2 * c4;
+            for (int pass = 0; pass < NPASS; ++pass) {
+                constexpr int dummy = 0; (void)dummy;
+                const int c_lo = pass * CB;
+                const int nc = (GTC - c_lo) < CB ? (GTC - c_lo) : CB;
 #pragma unroll
                 for (int ti = 0; ti < GT; ++ti)
 #pragma unroll
-                    for (int tjj = 0; tjj < GTC; ++tjj) {
-                        *reinterpret_cast<double2*>(DPAIR(ti, tjj)) = make_double2(acc[ti][tjj][0], acc[ti][tjj][1]);
-                        if (tjj < GT) {
-                            const double2 v = __ldg(reinterpret_cast<const double2*>(Sg + 8 * ti * NPm + 8 * tjj));
-                            acc[ti][tjj][0] = v.x;
-                            acc[ti][tjj][1] = v.y;
-                        }
-                    }
-            }
-            __syncwarp();   // B: T complete
-            // ---------------- P2: C' = T B_s + Sig
-            {
-                const double* Ap = Cb + g * LDC + c4;
-                const double* BpE = Bs + c4 * LDB + (g & 3) + ((g >> 2) ^ (sc & 1)) * 4 + (sc >> 1) * 8;
-                const double* BpO = BpE - (sc >> 1) * 16;
+                    for (int tc = 0; tc < CB; ++tc)
+                        if (tc < nc) acc[ti * CB + tc][0] = acc[ti * CB + tc][1] = 0.0;
+                {
+                    const double* Ap = Bs + g * LDB + c4;
+                    const double* BpE = Cb + c4 * LDC + (g & 3) + ((g >> 2) ^ (sc & 1)) * 4 + (sc >> 1) * 8;
+                    const double* BpO = BpE - (sc >> 1) * 16;
 #pragma unroll 1
-                for (int k0 = 0; k0 < NK; k0 += 4) {
-                    double a[GT], b[GT];
-                    const int ao = ((k0 >> 2) ^ sg) << 2;
+                    for (int k0 = 0; k0 < NK; k0 += 4) {
+                        double a[GT], b[CB];
+                        const int ao = ((k0 >> 2) ^ sg) << 2;
 #pragma unroll
-                    for (int ti = 0; ti < GT; ++ti) a[ti] = Ap[8 * ti * LDC + ao];
+                        for (int ti = 0; ti < GT; ++ti) a[ti] = Ap[8 * ti * LDB + ao];
 #pragma unroll
-                    for (int tjj = 0; tjj < GT; ++tjj) b[tjj] = (tjj & 1 ? BpO : BpE)[8 * tjj];
-                    BpE += 4 * LDB;
-                    BpO += 4 * LDB;
+                        for (int tc = 0; tc < CB; ++tc)
+                            if (tc < nc) b[tc] = ((c_lo + tc) & 1 ? BpO : BpE)[8 * (c_lo + tc)];
+                        BpE += 4 * LDC;
+                        BpO += 4 * LDC;
 #pragma unroll
-                    for (int ti = 0; ti < GT; ++ti)
+                        for (int ti = 0; ti < GT; ++ti)
 #pragma unroll
-                        for (int tjj = 0; tjj < GT; ++tjj) dmma884(acc[ti][tjj], a[ti], b[tjj]);
+                            for (int tc = 0; tc < CB; ++tc)
+                                if (tc < nc) dmma884(acc[ti * CB + tc], a[ti], b[tc]);
+                    }
                 }
+                __syncwarp();   // everybody finished reading C[:, J] (and M when J holds the mean columns)
+#pragma unroll
+                for (int ti = 0; ti < GT; ++ti)
+#pragma unroll
+                    for (int tc = 0; tc < CB; ++tc)
+                        if (tc < nc)
+                            *reinterpret_cast<double2*>(DPAIR(ti, c_lo + tc)) = make_double2(acc[ti * CB + tc][0], acc[ti * CB + tc][1]);
+            }
+        }
+        // accumulators of the upper tiles start at Sig (t > 0) / hold the steady state C0 (t = 0); the global
+        // loads are issued before the barrier so that their latency overlaps it
+#pragma unroll
+        for (int ti = 0; ti < GT; ++ti)
+#pragma unroll
+            for (int tjj = ti; tjj < GT; ++tjj) {
+                const double2 v = __ldg(reinterpret_cast<const double2*>(Gsrc + 8 * ti * NPm + 8 * tjj));
+                acc[UIDX(ti, tjj)][0] = v.x;
+                acc[UIDX(ti, tjj)][1] = v.y;
+            }
+        if (t > 0) {
+            __syncwarp();   // B: T (with M' in its mean columns) complete
+            // ---------------- P2: C' = T B_s + Sig, upper tiles only
+            const double* Ap = Cb + g * LDC + c4;
+            const double* BpE = Bs + c4 * LDB + (g & 3) + ((g >> 2) ^ (sc & 1)) * 4 + (sc >> 1) * 8;
+            const double* BpO = BpE - (sc >> 1) * 16;
+#pragma unroll 1
+            for (int k0 = 0; k0 < NK; k0 += 4) {
+                double a[GT], b[GT];
+                const int ao = ((k0 >> 2) ^ sg) << 2;
+#pragma unroll
+                for (int ti = 0; ti < GT; ++ti) a[ti] = Ap[8 * ti * LDC + ao];
+#pragma unroll
+                for (int tjj = 0; tjj < GT; ++tjj) b[tjj] = (tjj & 1 ? BpO : BpE)[8 * tjj];
+                BpE += 4 * LDB;
+                BpO += 4 * LDB;
+#pragma unroll
+                for (int ti = 0; ti < GT; ++ti)
+#pragma unroll
+                    for (int tjj = ti; tjj < GT; ++tjj) dmma884(acc[UIDX(ti, tjj)], a[ti], b[tjj]);
             }
         }
 
@@ -244,21 +263,28 @@ __global__ void __launch_bounds__(GT <= 3 ? 448 : 256, GT <= 4 ? 2 : 1) k_mma(co
         };
 
         if (is_valid) {
-            // publish the two columns of C' that w touches: column j lives in tile column j>>3, lanes with
-            // c4 == (j&7)>>1, element j&1
+            // publish the two columns of C' that w touches.  Column j, tile column tjz = j >> 3: rows of tile
+            // rows ti <= tjz come from the upper tile (ti, tjz) (lanes c4 == (j&7)>>1, element j&1); rows of
+            // tile rows ti > tjz come, by symmetry, from row j of the upper tile (tjz, ti) (lanes g == j&7).
 #pragma unroll
             for (int z = 0; z < 2; ++z) {
                 const int jz = z ? j1 : j0;
-                if (c4 == ((jz & 7) >> 1)) {
-                    const int tjz = jz >> 3;
-                    const bool hi = jz & 1;
+                const int tjz = jz >> 3, cj = jz & 7;
 #pragma unroll
-                    for (int tjj = 0; tjj < GT; ++tjj)
-                        if (tjj == tjz) {
+                for (int tjj = 0; tjj < GT; ++tjj)
+                    if (tjj == tjz) {
+                        if (c4 == (cj >> 1)) {
 #pragma unroll
-                            for (int ti = 0; ti < GT; ++ti) colb[z * NPm + 8 * ti + g] = hi ? acc[ti][tjj][1] : acc[ti][tjj][0];
+                            for (int ti = 0; ti <= tjj; ++ti)
+                                colb[z * NPm + 8 * ti + g] = (cj & 1) ? acc[UIDX(ti, tjj)][1] : acc[UIDX(ti, tjj)][0];
                         }
-                }
+                        if (g == cj) {
+#pragma unroll
+                            for (int ti = tjj + 1; ti < GT; ++ti)
+                                *reinterpret_cast<double2*>(colb + z * NPm + 8 * ti + 2 * c4) =
+                                    make_double2(acc[UIDX(tjj, ti)][0], acc[UIDX(tjj, ti)][1]);
+                        }
+                    }
             }
             if (t == 0) {   // at t = 0 the mean is not in the buffer yet: put it where w . M' reads it
 #pragma unroll
@@ -288,12 +314,13 @@ __global__ void __launch_bounds__(GT <= 3 ? 448 : 256, GT <= 4 ? 2 : 1) k_mma(co
                 const double2 v = *reinterpret_cast<const double2*>(colb + NPm + 8 * tjj + 2 * c4);
                 const double c0v = fma(w1, v.x, w0 * u.x), c1v = fma(w1, v.y, w0 * u.y);   // (C' w)[column pair]
 #pragma unroll
-                for (int ti = 0; ti < GT; ++ti) {
-                    acc[ti][tjj][0] = fma(-kr[ti], c0v, acc[ti][tjj][0]);   // pyx:71-75
-                    acc[ti][tjj][1] = fma(-kr[ti], c1v, acc[ti][tjj][1]);
+                for (int ti = 0; ti <= tjj; ++ti) {
+                    acc[UIDX(ti, tjj)][0] = fma(-kr[ti], c0v, acc[UIDX(ti, tjj)][0]);   // pyx:71-75
+                    acc[UIDX(ti, tjj)][1] = fma(-kr[ti], c1v, acc[UIDX(ti, tjj)][1]);
                 }
             }
             // innovation (pyx:79): x - w . M'  (G, if any, is not in the buffer: add w . G)
+            const int sw0 = swz(j0), sw1 = swz(j1);
             if (qv0) {
                 double ma = Cb[j0 * LDC + pcol(mp.MC0 + q0, sw0)], mb = Cb[j1 * LDC + pcol(mp.MC0 + q0, sw1)];
                 if (p.hasG && t > 0) { ma += __ldg(p.Gm + (s * N + j0) * D + xc0); mb += __ldg(p.Gm + (s * N + j1) * D + xc0); }
@@ -317,7 +344,8 @@ __global__ void __launch_bounds__(GT <= 3 ? 448 : 256, GT <= 4 ? 2 : 1) k_mma(co
             }
             __syncwarp();   // everybody has read w . M' before M+ lands in the buffer
         }
-        // ---------------- C+ (and M+ in its columns) becomes the operand of the next propagation
+        // ---------------- C+ (and M+ in its columns) becomes the operand of the next propagation:
+        //                  upper tiles as accumulator pairs, strictly-upper tiles also mirrored
         if (t + 1 < T) {
 #pragma unroll
             for (int ti = 0; ti < GT; ++ti) {
@@ -327,9 +355,18 @@ __global__ void __launch_bounds__(GT <= 3 ? 448 : 256, GT <= 4 ? 2 : 1) k_mma(co
                     m0 = fma(kr[ti], xm0, m0);   // pyx:82-85
                     m1 = fma(kr[ti], xm1, m1);
                 }
+                if (!MX && ti > 0) {
+                    // tile (ti, TJM) with ti <= TJM is upper and handled below; the mean pair of tile rows whose
+                    // (ti, TJM) store happens in the loop below is merged there
+                }
 #pragma unroll
-                for (int tjj = 0; tjj < GT; ++tjj) {
-                    double v0 = acc[ti][tjj][0], v1 = acc[ti][tjj][1];
+                for (int tjj = ti; tjj < GT; ++tjj) {
+                    double v0 = acc[UIDX(ti, tjj)][0], v1 = acc[UIDX(ti, tjj)][1];
+                    if (tjj > ti) {   // mirror: C[8 tjj + 2 c4 + e][8 ti + g] = C[8 ti + g][8 tjj + 2 c4 + e]
+                        const int r0 = 8 * tjj + 2 * c4;
+                        Cb[r0 * LDC + pcol(8 * ti + g, swz(r0))] = v0;
+                        Cb[(r0 + 1) * LDC + pcol(8 * ti + g, swz(r0 + 1))] = v1;
+                    }
                     if (!MX && tjj == TJM) {
                         if (qv0) v0 = m0;
                         if (qv1) v1 = m1;
@@ -353,6 +390,7 @@ __global__ void __launch_bounds__(GT <= 3 ? 448 : 256, GT <= 4 ? 2 : 1) k_mma(co
 }
 
 #undef DPAIR
+#undef UIDX
 #undef qv0
 #undef qv1
 #undef xc0
