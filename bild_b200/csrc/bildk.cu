@@ -81,7 +81,7 @@ struct bildk_model {
     double *dG = nullptr, *dM0 = nullptr, *dw = nullptr;
     uint16_t* d_lane_ab = nullptr;   // [G*G] lane -> tile map (2x2 tile blocks per lane quad)
     // tensor-core (DMMA) layout: 8x8 tiles, row strides == 4 (mod 8)
-    bool mma_ok = false, mma_mx = false;
+    bool mma_ok = false, mma_mx = false, mmac_ok = false;
     int GT = 0, NPm = 0, LDBm = 0, LDCm = 0, MC0 = 0, NK = 0;
     double *dBm = nullptr, *dSigm = nullptr, *dC0m = nullptr;
     // per-model scratch for the host-pointer entry points
@@ -263,7 +263,7 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
     // tensor-core layout (one warp per filter): N <= 56, sparse measurement vector
     {
         const int GT = (N + 7) / 8;
-        if (GT <= 7 && m->nnz == 2) {
+        if (GT <= 14 && m->nnz == 2) {
             m->GT = GT; m->NPm = 8 * GT;
             m->mma_mx = (m->NPm - N) < d;
             m->MC0 = m->mma_mx ? m->NPm : N;
@@ -297,6 +297,10 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
             fill(C0, padg);
             if ((rc = upload(&m->dC0m, padg.data(), S * matg))) { bildk_model_destroy(m); return rc; }
             const size_t fbytes = (static_cast<size_t>(m->NPm) * m->LDCm + static_cast<size_t>(2) * m->NPm + 2) * 8;
+            if (GT > 7) {   // one CTA per filter, one warp per tile column (k_mmac); at least one propagator resident
+                m->mmac_ok = 16 + matb * 8 + fbytes <= static_cast<size_t>(m->max_smem_optin);
+                m->mma_ok = false;
+            } else
             m->mma_ok = 16 + matb * 8 * S + fbytes <= static_cast<size_t>(m->max_smem_optin);
         }
     }
@@ -372,6 +376,8 @@ extern "C" int bildk_traj_create(bildk_model_t m, int T, const double* x, int ds
 // ------------------------------------------------------------------------------------------------
 struct Plan {
     bool mma = false;      // tensor-core kernel, one warp per filter
+    bool mmac = false;     // tensor-core kernel, one CTA per filter, one warp per tile column
+    unsigned char colmap[16] = {0};
     int WPC = 0;
     bool tile;
     bool ws, densew, b_all;
@@ -420,8 +426,66 @@ static cudaError_t mma_launch_for(int GT, bool MX, const MParams& mp, dim3 grid,
     return cudaErrorInvalidValue;
 }
 
+template <int GT, bool MX>
+static cudaError_t mmac_launch(const CParams& cp, dim3 grid, size_t smem, cudaStream_t st) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_mmac<GT, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    k_mmac<GT, MX><<<grid, 32 * GT, smem, st>>>(cp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        cudaFuncAttributes a{};
+        cudaFuncGetAttributes(&a, k_mmac<GT, MX>);
+        fprintf(stderr, "k_mmac<%d,%d> launch failed: regs=%d maxThreads=%d static_smem=%zu local=%zu dyn_smem=%zu threads=%d max_dyn=%d\n",
+                GT, (int)MX, a.numRegs, a.maxThreadsPerBlock, a.sharedSizeBytes, a.localSizeBytes, smem, 32 * GT, a.maxDynamicSharedSizeBytes);
+    }
+    return e;
+}
+static cudaError_t mmac_launch_for(int GT, bool MX, const CParams& cp, dim3 grid, size_t smem, cudaStream_t st) {
+    switch (GT * 2 + (MX ? 1 : 0)) {
+        case 16: return mmac_launch<8, false>(cp, grid, smem, st);   case 17: return mmac_launch<8, true>(cp, grid, smem, st);
+        case 18: return mmac_launch<9, false>(cp, grid, smem, st);   case 19: return mmac_launch<9, true>(cp, grid, smem, st);
+        case 20: return mmac_launch<10, false>(cp, grid, smem, st);  case 21: return mmac_launch<10, true>(cp, grid, smem, st);
+        case 22: return mmac_launch<11, false>(cp, grid, smem, st);  case 23: return mmac_launch<11, true>(cp, grid, smem, st);
+        case 24: return mmac_launch<12, false>(cp, grid, smem, st);  case 25: return mmac_launch<12, true>(cp, grid, smem, st);
+        case 26: return mmac_launch<13, false>(cp, grid, smem, st);  case 27: return mmac_launch<13, true>(cp, grid, smem, st);
+        case 28: return mmac_launch<14, false>(cp, grid, smem, st);  case 29: return mmac_launch<14, true>(cp, grid, smem, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
 static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
     Plan pl{};
+    {
+        const char* force0 = getenv("BILDK_KERNEL");
+        if (m->mmac_ok && !(force0 && !strcmp(force0, "tile")) && !env_int("BILDK_FORCE_GENERIC", 0)) {
+            const int GT = m->GT;
+            const size_t matb = static_cast<size_t>(m->NPm) * m->LDBm * 8;
+            const size_t fbytes = (static_cast<size_t>(m->NPm) * m->LDCm + static_cast<size_t>(2) * m->NPm + 2) * 8;
+            pl.mmac = true;
+            pl.tile = false;
+            pl.b_all = 16 + matb * m->S + fbytes <= static_cast<size_t>(m->max_smem_optin);
+            pl.smem = 16 + matb * (pl.b_all ? m->S : 1) + fbytes;
+            pl.threads = 32 * GT;
+            pl.FPC = 1;
+            // column -> warp: longest-processing-time first onto the four schedulers (warp i runs on scheduler i % 4)
+            double load[4] = {0, 0, 0, 0};
+            int slots[4], used[4] = {0, 0, 0, 0};
+            for (int k = 0; k < 4; ++k) slots[k] = (GT - k + 3) / 4;
+            for (int c = GT - 1; c >= 0; --c) {   // weight GT (P1) + c + 1 (P2) decreases with c
+                int best = -1;
+                for (int k = 0; k < 4; ++k)
+                    if (used[k] < slots[k] && (best < 0 || load[k] < load[best])) best = k;
+                pl.colmap[best + 4 * used[best]] = static_cast<unsigned char>(c);
+                load[best] += GT + c + 1 + ((c == 0 && m->mma_mx) ? GT : 0);
+                ++used[best];
+            }
+            return pl;
+        }
+    }
     {
         const char* force = getenv("BILDK_KERNEL");
         const bool want_mma = m->mma_ok && !(force && !strcmp(force, "tile")) && !env_int("BILDK_FORCE_GENERIC", 0);
@@ -537,7 +601,10 @@ static cudaError_t launch_tile(const Plan& pl, const KParams& kp, dim3 grid, cud
 
 static std::string plan_string(const bildk_model* m, const Plan& pl) {
     char buf[256];
-    if (pl.mma)
+    if (pl.mmac)
+        snprintf(buf, sizeof buf, "mmac (DMMA m8n8k4) GT=%d %s cta-per-filter warp-per-tile-column B=%s threads=%d smem=%zu", m->GT,
+                 m->mma_mx ? "mean-in-extra-tile" : "mean-in-padding", pl.b_all ? "all" : "one", pl.threads, pl.smem);
+    else if (pl.mma)
         snprintf(buf, sizeof buf, "mma (DMMA m8n8k4) GT=%d %s warp-per-filter WPC=%d threads=%d smem=%zu", m->GT,
                  m->mma_mx ? "mean-in-extra-tile" : "mean-in-padding", pl.WPC, pl.threads, pl.smem);
     else if (!pl.tile)
@@ -571,7 +638,7 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
         if (rc) return rc;
         d_part = m->part.p;
     }
-    if (pl.mma || pl.tile) {
+    if (pl.mma || pl.mmac || pl.tile) {
         KParams kp{};
         kp.N = m->N; kp.D = m->D; kp.S = m->S; kp.G = m->G; kp.LD = m->LD; kp.NP = m->NP;
         kp.Bpad = m->dBpad; kp.Sigpad = m->dSigpad; kp.C0pad = m->dC0pad; kp.Gm = m->dG; kp.M0 = m->dM0; kp.w = m->dw;
@@ -585,6 +652,7 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
         }
         kp.P = P; kp.K1 = K1; kp.run_starts = d_starts; kp.run_states = d_states; kp.out = d_part;
         if (pl.mma) pl.FPC = pl.WPC;   // CTA -> first filter maps use FPC
+        if (pl.mmac) pl.FPC = 1;
         kp.FPC = pl.FPC; kp.TPFS = pl.TPFS; kp.b_all = pl.b_all; kp.fstride = pl.fstride; kp.bstride = pl.bstride; kp.lane_ab = m->d_lane_ab;
         int n_cta = 0;
         if (n_traj == 1) {
@@ -604,12 +672,19 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
             kp.cta_traj = m->meta.p; kp.cta_first = m->meta.p + n_cta;
         }
         dim3 grid(n_cta, dstar);
-        if (pl.mma) {
+        if (pl.mma || pl.mmac) {
             MParams mp{};
             mp.k = kp;
             mp.NPm = m->NPm; mp.LDB = m->LDBm; mp.LDC = m->LDCm; mp.MC0 = m->MC0; mp.NK = m->NK;
             mp.Bm = m->dBm; mp.Sigm = m->dSigm; mp.C0m = m->dC0m;
             mp.WPC = pl.WPC; mp.fstride_m = pl.fstride; mp.bstride_m = pl.bstride;
+            if (pl.mmac) {
+                CParams cp{};
+                cp.m = mp;
+                cp.b_all = pl.b_all;
+                for (int i = 0; i < 16; ++i) cp.colmap[i] = pl.colmap[i];
+                CU(mmac_launch_for(m->GT, m->mma_mx, cp, grid, pl.smem, st));
+            } else
             CU(mma_launch_for(m->GT, m->mma_mx, mp, grid, pl.threads, pl.smem, st));
         } else {
             CU(launch_tile(pl, kp, grid, st));

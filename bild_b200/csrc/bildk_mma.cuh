@@ -395,4 +395,307 @@ __global__ void __launch_bounds__(GT <= 3 ? 448 : 256, GT <= 4 ? 2 : 1) k_mma(co
 #undef qv1
 #undef xc0
 #undef xc1
+
+// ================================================================================================
+// k_mmac - FP64 tensor cores for polymers that do not fit one warp (8 < GT <= 14, N <= 112):
+// ONE CTA PER FILTER, ONE WARP PER TILE COLUMN.
+//
+//   P1   warp(c):  T[:, c] = B_s C[:, c]   in place (it is the only reader of column c: __syncwarp only);
+//                  GT DMMAs per k-step fed by GT fragments of B_s and one of C
+//   ---- CTA barrier: T complete
+//   P2   warp(c):  the c+1 upper tiles (ti <= c) of C'[:, c] = T B_s[:, c] + Sig
+//   ---- publish the two columns of C' that w touches; CTA barrier
+//   upd  rank-1 update of the warp's tiles; the owner of the last tile column also carries the mean
+//   ---- C+ written back (upper pairs + mirrored), CTA barrier
+// Symmetric output as in k_mma: (GT^2 + GT (GT+1)/2) DMMAs per k-step instead of 2 GT^2.
+// The column -> warp map (mp.colmap) is chosen on the host so that the four warp schedulers of the SM
+// carry equal numbers of DMMAs (P2 work grows with the column index).  The propagator of the current
+// state is resident in shared memory (all states when they fit), re-staged by TMA at a state switch.
+struct CParams {
+    MParams m;
+    unsigned char colmap[16];   // warp -> tile column
+    int b_all;                  // all S propagators resident
+};
+
+template <int GT, bool MX>
+// registers are allocated per scheduler (16 K each): ceil(GT / 4) warps share one
+__global__ void __maxnreg__((16384 / (32 * ((GT + 3) / 4))) / 8 * 8 > 240 ? 240 : (16384 / (32 * ((GT + 3) / 4))) / 8 * 8) k_mmac(const __grid_constant__ CParams cp) {
+    constexpr int GTC = GT + (MX ? 1 : 0);
+    constexpr int TJM = MX ? GT : GT - 1;
+    constexpr int NPm = 8 * GT, LDB = NPm + 4, LDC = 8 * GTC + 4;
+    constexpr int MATB = NPm * LDB, MATG = NPm * NPm;
+    const MParams& mp = cp.m;
+    const KParams& p = mp.k;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
+    double* Bsm = reinterpret_cast<double*>(smem_raw + 16);
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int g = lane >> 2, c4 = lane & 3;
+    const int e_sub = blockIdx.y;
+    const int N = p.N, D = p.D, NK = mp.NK;
+    const int c = cp.colmap[wid];                 // this warp's tile column
+    const bool mown = (c == GT - 1);              // ... which also carries the mean columns
+    const bool mxw = MX && (c == 0);              // ... or computes the extra mean tile column of T
+
+    const int tj = p.cta_traj ? p.cta_traj[blockIdx.x] : 0;
+    const int pidx = p.cta_first ? p.cta_first[blockIdx.x] : blockIdx.x;
+
+    if (tid == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    auto stage_B = [&](int st, int slot) {
+        constexpr uint32_t CH = 32768;
+        constexpr uint32_t bytes = MATB * sizeof(double);
+        for (uint32_t off = 0; off < bytes; off += CH)
+            tma_load_1d(reinterpret_cast<char*>(Bsm + slot * MATB) + off, reinterpret_cast<const char*>(mp.Bm + static_cast<size_t>(MATB) * st) + off,
+                        bytes - off < CH ? bytes - off : CH, mbar);
+    };
+    uint32_t bphase = 0;
+    int s_loaded = -1;
+    if (cp.b_all) {
+        if (tid == 0) {
+            mbar_expect_tx(mbar, static_cast<uint32_t>(MATB * p.S * sizeof(double)));
+            for (int st = 0; st < p.S; ++st) stage_B(st, st);
+        }
+    }
+
+    double* Cb = Bsm + MATB * (cp.b_all ? p.S : 1);   // [NPm][LDC]
+    double* colb = Cb + NPm * LDC;                    // [2][NPm]
+    double* const lst = colb + 2 * NPm;               // [0] mantissa  [1] (int2) exponent sum, valid frames
+
+    const int T = p.T[tj];
+    const double* __restrict__ xg = p.x[tj];
+    const uint32_t* __restrict__ vbits = reinterpret_cast<const uint32_t*>(p.valid[tj] + (T + 3) / 4 * 4);
+    uint32_t vword = 0;
+    const int ncols = p.ncols[e_sub];
+    const double s2 = p.s2[e_sub];
+    const int j0 = p.wz_idx[0], j1 = p.wz_idx[1];
+    const double w0 = p.wz_val[0], w1 = p.wz_val[1];
+
+    const int q0 = 2 * c4 - (mp.MC0 - 8 * TJM), q1 = q0 + 1;
+    const bool qv0 = static_cast<unsigned>(q0) < static_cast<unsigned>(ncols);
+    const bool qv1 = static_cast<unsigned>(q1) < static_cast<unsigned>(ncols);
+    const int xc0 = p.cols[e_sub][qv0 ? q0 : 0], xc1 = p.cols[e_sub][qv1 ? q1 : 0];
+    double quad = 0.0;
+    if (tid == 0) { lst[0] = 1.0; reinterpret_cast<int*>(lst + 1)[0] = 0; reinterpret_cast<int*>(lst + 1)[1] = 0; }
+
+    int r_cur = 0;
+    int s = p.run_states[static_cast<size_t>(pidx) * p.K1];
+    int next_sw = (p.K1 > 1) ? p.run_starts[static_cast<size_t>(pidx) * p.K1 + 1] : 0x7fffffff;
+
+    double acc[GT][2];
+    double* const myC = Cb + g * LDC + 2 * c4;   // accumulator pair of tile (ti, tj): myC + 8 ti LDC + 8 tj
+
+    if (cp.b_all) mbar_wait(mbar, 0);
+
+    for (int t = 0; t < T; ++t) {
+        while (t >= next_sw) {
+            ++r_cur;
+            s = p.run_states[static_cast<size_t>(pidx) * p.K1 + r_cur];
+            next_sw = (r_cur + 1 < p.K1) ? p.run_starts[static_cast<size_t>(pidx) * p.K1 + r_cur + 1] : 0x7fffffff;
+        }
+        if ((t & 31) == 0) vword = __ldg(vbits + (t >> 5));
+        const bool is_valid = (vword >> (t & 31)) & 1u;
+        double x0 = 0.0, x1 = 0.0;
+        if (is_valid && mown) {
+            if (qv0) x0 = __ldg(xg + t * D + xc0);
+            if (qv1) x1 = __ldg(xg + t * D + xc1);
+        }
+        if (!cp.b_all && t > 0 && s != s_loaded) {   // all readers of the old propagator passed the last barrier
+            if (tid == 0) {
+                mbar_expect_tx(mbar, static_cast<uint32_t>(MATB * sizeof(double)));
+                stage_B(s, 0);
+            }
+            mbar_wait(mbar, bphase);
+            bphase ^= 1;
+            s_loaded = s;
+        }
+        const double* Bs = Bsm + (cp.b_all ? s * MATB : 0);
+        const double* Gsrc = ((t == 0) ? mp.C0m : mp.Sigm) + static_cast<size_t>(MATG) * s + g * NPm + 2 * c4;
+
+        if (t > 0) {
+            // ---------------- P1: T[:, cc] = B_s Caug[:, cc], in place
+            auto p1_column = [&](int cc) {
+#pragma unroll
+                for (int ti = 0; ti < GT; ++ti) acc[ti][0] = acc[ti][1] = 0.0;
+                const double* Ap = Bs + g * LDB + c4;
+                const double* Bp = Cb + c4 * LDC + 8 * cc + g;
+#pragma unroll 1
+                for (int k0 = 0; k0 < NK; k0 += 4) {
+                    double a[GT];
+#pragma unroll
+                    for (int ti = 0; ti < GT; ++ti) a[ti] = Ap[8 * ti * LDB + k0];
+                    const double b = Bp[k0 * LDC];
+#pragma unroll
+                    for (int ti = 0; ti < GT; ++ti) dmma884(acc[ti], a[ti], b);
+                }
+                __syncwarp();   // this warp is the only reader of column cc
+#pragma unroll
+                for (int ti = 0; ti < GT; ++ti)
+                    *reinterpret_cast<double2*>(myC + 8 * ti * LDC + 8 * cc) = make_double2(acc[ti][0], acc[ti][1]);
+            };
+            p1_column(c);
+            if (mxw) p1_column(GT);
+        }
+        // upper tiles of this column start at Sig (t > 0) / hold C0 (t = 0)
+#pragma unroll
+        for (int ti = 0; ti < GT; ++ti)
+            if (ti <= c) {
+                const double2 v = __ldg(reinterpret_cast<const double2*>(Gsrc + 8 * ti * NPm + 8 * c));
+                acc[ti][0] = v.x;
+                acc[ti][1] = v.y;
+            }
+        if (t > 0) {
+            __syncthreads();   // T complete
+            // ---------------- P2: upper tiles of C'[:, c] = T B_s[:, c] + Sig
+            const double* Ap = Cb + g * LDC + c4;
+            const double* Bp = Bs + c4 * LDB + 8 * c + g;
+#pragma unroll 1
+            for (int k0 = 0; k0 < NK; k0 += 4) {
+                double a[GT];
+#pragma unroll
+                for (int ti = 0; ti < GT; ++ti)
+                    if (ti <= c) a[ti] = Ap[8 * ti * LDC + k0];
+                const double b = Bp[k0 * LDB];
+#pragma unroll
+                for (int ti = 0; ti < GT; ++ti)
+                    if (ti <= c) dmma884(acc[ti], a[ti], b);
+            }
+        }
+
+        auto mean_prior = [&](int ti, double& m0, double& m1) {
+            const int row = 8 * ti + g;
+            if (t == 0) {
+                m0 = (qv0 && row < N) ? __ldg(p.M0 + (s * N + row) * D + xc0) : 0.0;
+                m1 = (qv1 && row < N) ? __ldg(p.M0 + (s * N + row) * D + xc1) : 0.0;
+            } else {
+                const double2 v = *reinterpret_cast<const double2*>(myC + 8 * ti * LDC + 8 * TJM);
+                m0 = qv0 ? v.x : 0.0;
+                m1 = qv1 ? v.y : 0.0;
+                if (p.hasG && row < N) {
+                    if (qv0) m0 += __ldg(p.Gm + (s * N + row) * D + xc0);
+                    if (qv1) m1 += __ldg(p.Gm + (s * N + row) * D + xc1);
+                }
+            }
+        };
+
+        if (is_valid) {
+            // publish column j of C' (j = j0, j1; tile column tjz = j >> 3): the warp of column tjz has its rows
+            // 8 ti + g for ti <= tjz; warps of columns c > tjz hold, by symmetry, row j of tile (tjz, c)
+#pragma unroll
+            for (int z = 0; z < 2; ++z) {
+                const int jz = z ? j1 : j0;
+                const int tjz = jz >> 3, cj = jz & 7;
+                if (c == tjz) {
+                    if (c4 == (cj >> 1)) {
+#pragma unroll
+                        for (int ti = 0; ti < GT; ++ti)
+                            if (ti <= c) colb[z * NPm + 8 * ti + g] = (cj & 1) ? acc[ti][1] : acc[ti][0];
+                    }
+                } else if (c > tjz) {
+                    if (g == cj) {
+#pragma unroll
+                        for (int ti = 0; ti < GT; ++ti)
+                            if (ti == tjz) *reinterpret_cast<double2*>(colb + z * NPm + 8 * c + 2 * c4) = make_double2(acc[ti][0], acc[ti][1]);
+                    }
+                }
+            }
+            if (t == 0 && mown) {
+#pragma unroll
+                for (int ti = 0; ti < GT; ++ti) {
+                    double m0, m1;
+                    mean_prior(ti, m0, m1);
+                    if (qv0) Cb[(8 * ti + g) * LDC + mp.MC0 + q0] = m0;
+                    if (qv1) Cb[(8 * ti + g) * LDC + mp.MC0 + q1] = m1;
+                }
+            }
+        }
+        __syncthreads();   // T no longer needed; published columns (and M') visible
+        double kr[GT];
+        double xm0 = 0.0, xm1 = 0.0;
+        if (is_valid) {
+            const double cw_j0 = fma(w1, colb[NPm + j0], w0 * colb[j0]);
+            const double cw_j1 = fma(w1, colb[NPm + j1], w0 * colb[j1]);
+            const double S = fma(w1, cw_j1, fma(w0, cw_j0, s2));
+            const double Sinv = __drcp_rn(S);                               // pyx:63
+#pragma unroll
+            for (int ti = 0; ti < GT; ++ti)
+                if (ti <= c) kr[ti] = fma(w1, colb[NPm + 8 * ti + g], w0 * colb[8 * ti + g]) * Sinv;   // pyx:66-67
+            {
+                const double2 u = *reinterpret_cast<const double2*>(colb + 8 * c + 2 * c4);
+                const double2 v = *reinterpret_cast<const double2*>(colb + NPm + 8 * c + 2 * c4);
+                const double c0v = fma(w1, v.x, w0 * u.x), c1v = fma(w1, v.y, w0 * u.y);
+#pragma unroll
+                for (int ti = 0; ti < GT; ++ti)
+                    if (ti <= c) {
+                        acc[ti][0] = fma(-kr[ti], c0v, acc[ti][0]);   // pyx:71-75
+                        acc[ti][1] = fma(-kr[ti], c1v, acc[ti][1]);
+                    }
+            }
+            if (mown) {
+                if (qv0) {
+                    double ma = Cb[j0 * LDC + mp.MC0 + q0], mb = Cb[j1 * LDC + mp.MC0 + q0];
+                    if (p.hasG && t > 0) { ma += __ldg(p.Gm + (s * N + j0) * D + xc0); mb += __ldg(p.Gm + (s * N + j1) * D + xc0); }
+                    xm0 = x0 - fma(w1, mb, w0 * ma);                       // pyx:79
+                    if (g == 0) quad = fma(xm0 * xm0, Sinv, quad);
+                }
+                if (qv1) {
+                    double ma = Cb[j0 * LDC + mp.MC0 + q1], mb = Cb[j1 * LDC + mp.MC0 + q1];
+                    if (p.hasG && t > 0) { ma += __ldg(p.Gm + (s * N + j0) * D + xc1); mb += __ldg(p.Gm + (s * N + j1) * D + xc1); }
+                    xm1 = x1 - fma(w1, mb, w0 * ma);
+                    if (g == 0) quad = fma(xm1 * xm1, Sinv, quad);
+                }
+                if (lane == 0) {
+                    double lmant = lst[0] * Sinv;
+                    const int ex = ((__double2hiint(lmant) >> 20) & 0x7ff) - 1023;
+                    lmant = __hiloint2double(__double2hiint(lmant) - (ex << 20), __double2loint(lmant));
+                    lst[0] = lmant;
+                    reinterpret_cast<int*>(lst + 1)[0] += ex;
+                    reinterpret_cast<int*>(lst + 1)[1] += 1;
+                }
+                __syncwarp();   // the mean owner has read w . M' before M+ lands in the buffer
+            }
+        }
+        // ---------------- C+ written back: upper pairs of this column, mirrored below the diagonal
+        if (t + 1 < T) {
+#pragma unroll
+            for (int ti = 0; ti < GT; ++ti)
+                if (ti <= c) {
+                    double v0 = acc[ti][0], v1 = acc[ti][1];
+                    if (ti < c) {   // mirror: C[8 c + 2 c4 + e][8 ti + g]
+                        const int r0 = 8 * c + 2 * c4;
+                        Cb[r0 * LDC + 8 * ti + g] = v0;
+                        Cb[(r0 + 1) * LDC + 8 * ti + g] = v1;
+                    }
+                    if (mown) {
+                        double m0, m1;
+                        mean_prior(ti, m0, m1);
+                        if (is_valid) {
+                            m0 = fma(kr[ti], xm0, m0);   // pyx:82-85
+                            m1 = fma(kr[ti], xm1, m1);
+                        }
+                        if (!MX) {
+                            if (qv0) v0 = m0;
+                            if (qv1) v1 = m1;
+                        } else {
+                            *reinterpret_cast<double2*>(myC + 8 * ti * LDC + 8 * TJM) = make_double2(m0, m1);
+                        }
+                    }
+                    *reinterpret_cast<double2*>(myC + 8 * ti * LDC + 8 * c) = make_double2(v0, v1);
+                }
+        }
+        __syncthreads();   // C+ complete
+    }
+
+    if (mown) {
+        quad += __shfl_xor_sync(0xffffffffu, quad, 1);
+        quad += __shfl_xor_sync(0xffffffffu, quad, 2);
+        if (lane == 0) {
+            const int lexp = reinterpret_cast<const int*>(lst + 1)[0], nvalid = reinterpret_cast<const int*>(lst + 1)[1];
+            const double logdet = log(lst[0]) + lexp * 0.6931471805599453;
+            p.out[static_cast<size_t>(e_sub) * p.P + pidx] = -0.5 * (quad - ncols * logdet + static_cast<double>(nvalid) * ncols * LOG_2PI);
+        }
+    }
+}
+
 }  // namespace bildk

@@ -41,6 +41,10 @@ CASES = [
     (7, 1, 30, 9, 0.0, 0.5, (None, [(0, -1)]), 2),              # tiny
     (3, 3, 25, 6, 0.0, 0.5, (None, [(0, -1)]), 2),              # N == d
     (2, 3, 25, 6, 0.1, 0.5, (None, [(0, -1, 0.5)]), 2),         # N < d: catch-all kernel
+    (60, 3, 30, 4, 0.1, 0.3, (None, [(0, -1)]), 4),             # GT=8: one CTA per filter, one warp per tile column
+    (64, 3, 20, 3, 0.0, 0.3, (None, [(0, -1)]), 3),             # GT=8, no padding room: mean in an extra tile column
+    (96, 2, 16, 3, 0.2, 0.3, (None, [(0, -1)], [(10, 50)]), 3), # GT=12, 3 states: single resident propagator, TMA swaps
+    (110, 3, 12, 2, 0.0, 0.3, (None, [(0, -1)]), 2),            # GT=14
     (130, 2, 12, 3, 0.0, 0.3, (None, [(0, -1)]), 2),            # beyond the on-chip limit: catch-all kernel
 ]
 
