@@ -1,0 +1,123 @@
+"""
+BASELINE.json configs[4]: throughput sweep of the batched logL over N x T x batch, next to the reference
+Cython path on all host cores (bounded sample per point).  One JSON object per point + a markdown table.
+
+    python tools/sweep.py [--quick] > profiles/sweep.jsonl
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--quick", action="store_true")
+ap.add_argument("--cpu-seconds", type=float, default=4.0, help="CPU work per point (core-seconds) for the reference sample")
+a = ap.parse_args()
+
+Ns = [10, 25, 50, 100, 200]
+Ts = [100, 1000]
+Ps = [1024, 65536]
+points = [(N, T, P) for N in Ns for T in Ts for P in Ps]
+if a.quick:
+    points = [(N, 100, 1024) for N in Ns]
+
+# CPU legs first (fork pools must precede CUDA initialisation)
+sys.path.insert(0, os.path.join(bench.ROOT, "oracle"))
+import kalman_oracle as ko  # noqa: E402
+cpu = {}
+inputs = {}
+for N, T, P in points:
+    key = (N, T)
+    if key in cpu:
+        continue
+    wl = dict(N=N, T=T, P=2048, p_nan=0.0)
+    model, traj, ss, thetas = bench.make_inputs(wl, 0)
+    inputs[key] = (model, traj)
+    probe_states = np.array([ko.st2states(ss[i], thetas[i], T) for i in range(16)])
+    probe = bench.cpu_reference(model, traj, probe_states, 16)
+    per_eval = probe["seconds"] * min(probe["cores"], probe["n"]) / probe["n"]
+    n = int(min(2048, max(probe["cores"], a.cpu_seconds / max(per_eval, 1e-9))))
+    states = np.array([ko.st2states(ss[i], thetas[i], T) for i in range(n)])
+    r = bench.cpu_reference(model, traj, states, n)
+    cpu[key] = dict(frame_steps_per_s=n * (T - 1) / r["seconds"], cores=r["cores"], kind=r["kind"], n=n, logL=r["logL"], ss=ss[:n], thetas=thetas[:n])
+    print(f"# cpu N={N} T={T}: {cpu[key]['frame_steps_per_s']:.4g} frame-steps/s on {r['cores']} cores ({n} profiles)", file=sys.stderr, flush=True)
+
+import torch  # noqa: E402
+from bild_b200 import _lib  # noqa: E402
+from bild_b200.engine import st_to_runs  # noqa: E402
+lib = _lib.load()
+dfma, dmma = ctypes.c_double(), ctypes.c_double()
+_lib.check(lib.bildk_measure_fp64_peak(0, ctypes.byref(dfma), ctypes.byref(dmma)))
+peak = max(dfma.value, dmma.value)
+dev = torch.device("cuda", 0)
+flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+rows = []
+for N, T, P in points:
+    if N == 200 and P > 1024:
+        rows.append(dict(N=N, T=T, P=P, skipped="catch-all kernel only (covariance does not fit on chip); not run at 64k"))
+        print(json.dumps(rows[-1]), flush=True)
+        continue
+    wl = dict(N=N, T=T, P=P, p_nan=0.0)
+    model, traj, ss, thetas = bench.make_inputs(wl, 0)
+    th = model._handle(traj)
+    starts, rstates = st_to_runs(ss, thetas, T)
+    d_s, d_r = torch.from_numpy(starts).to(dev), torch.from_numpy(rstates).to(dev)
+    d_o = torch.empty(P, dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream()
+
+    def run():
+        model.engine.logl_runs_device(th, P, starts.shape[1], d_s.data_ptr(), d_r.data_ptr(), d_o.data_ptr(), st.cuda_stream)
+
+    run()
+    torch.cuda.synchronize()
+    times = []
+    reps = 3 if N < 200 else 1
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st); run(); e1.record(st)
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = float(np.mean(times))
+    t0 = time.perf_counter()
+    host = model.logL_st_batch(ss, thetas, traj)
+    e2e_s = time.perf_counter() - t0
+    c = cpu[(N, T)]
+    ref_model, ref_traj = inputs[(N, T)]
+    # parity on the CPU sample: same model parameters and seed -> same trajectory; evaluate the CPU sample's profiles
+    chk = model.logL_st_batch(c["ss"], c["thetas"], traj)
+    want, note = c["logL"], ""
+    if not np.all(np.isfinite(want)):
+        # the reference .pyx returns NaN here (N = 200: its dsymv calls with beta = 0 write into np.empty buffers,
+        # pyx:168, 199, and scipy's OpenBLAS propagates the uninitialised NaNs for large N); check against the C oracle
+        m = min(4, len(chk))
+        arrs = ko.model_arrays(model.models)
+        s2o, cio = ko.noise_to_s2_cind(model._get_noise(traj))
+        want = ko.logl_c(*arrs, model.measurement, traj[:], s2o, cio, np.array([ko.st2states(c["ss"][i], c["thetas"][i], T) for i in range(m)]))
+        chk = chk[:m]
+        note = "reference returned NaN; parity vs C oracle"
+    rel = float(np.max(np.abs(chk - want) / np.maximum(1, np.abs(want))))
+    fl = bench.flops_per_eval(N, 3, 1, T, T) * P
+    row = dict(N=N, T=T, P=P, kernel_ms=ms, frame_steps_per_s=P * (T - 1) / (ms * 1e-3), evals_per_s=P / (ms * 1e-3),
+               e2e_frame_steps_per_s=P * (T - 1) / e2e_s, tflops=fl / (ms * 1e-3) * 1e-12, frac_of_fp64_peak=fl / (ms * 1e-3) * 1e-12 / peak,
+               cpu_frame_steps_per_s=c["frame_steps_per_s"], cpu_cores=c["cores"], cpu_kind=c["kind"], cpu_sample=c["n"],
+               speedup_vs_cpu=P * (T - 1) / (ms * 1e-3) / c["frame_steps_per_s"], max_rel_err_vs_cpu=rel,
+               plan=th.describe_plan(P), peak_tflops=peak, note=note)
+    rows.append(row)
+    print(json.dumps(row), flush=True)
+
+print("\n| N | T | P | kernel ms | frame-steps/s | TFLOP/s (alg.) | of FP64 peak | CPU ref (all cores) | speed-up | max rel err | kernel |", file=sys.stderr)
+print("|---|---|---|---|---|---|---|---|---|---|---|", file=sys.stderr)
+for r in rows:
+    if "skipped" in r:
+        print(f"| {r['N']} | {r['T']} | {r['P']} | - | - | - | - | - | - | - | {r['skipped']} |", file=sys.stderr)
+    else:
+        print(f"| {r['N']} | {r['T']} | {r['P']} | {r['kernel_ms']:.2f} | {r['frame_steps_per_s']:.3g} | {r['tflops']:.1f} | {r['frac_of_fp64_peak']:.2f} | "
+              f"{r['cpu_frame_steps_per_s']:.3g} ({r['cpu_cores']} cores) | {r['speedup_vs_cpu']:.0f}x | {r['max_rel_err_vs_cpu']:.1e} | {r['plan'].split(' threads')[0]} |", file=sys.stderr)
