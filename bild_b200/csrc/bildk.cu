@@ -267,7 +267,7 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
             m->GT = GT; m->NPm = 8 * GT;
             m->mma_mx = (m->NPm - N) < d;
             m->MC0 = m->mma_mx ? m->NPm : N;
-            const bool swz = GT <= 4;   // must match k_mma's SWZ
+            const bool swz = BILDK_MMA_SWZ && GT <= 4;   // must match k_mma's SWZ
             m->LDBm = swz ? (m->NPm + 15) / 16 * 16 : m->NPm + 4;
             m->LDCm = swz ? (8 * (GT + (m->mma_mx ? 1 : 0)) + 15) / 16 * 16 : 8 * (GT + (m->mma_mx ? 1 : 0)) + 4;
             m->NK = (N + 3) / 4 * 4;
