@@ -415,6 +415,19 @@ __global__ void __launch_bounds__(GT <= 3 ? 448 : 256, GT <= 4 ? 2 : 1) k_mma(co
 // The column -> warp map (mp.colmap) is chosen on the host so that the four warp schedulers of the SM
 // carry equal numbers of DMMAs (P2 work grows with the column index).  The propagator of the current
 // state is resident in shared memory (all states when they fit), re-staged by TMA at a state switch.
+template <int GT, int NT, int LDA, int LDBB>
+__device__ __forceinline__ void mmac_p2(double (&acc)[GT][2], const double* __restrict__ Ap, const double* __restrict__ Bp, int NK) {
+#pragma unroll 1
+    for (int k0 = 0; k0 < NK; k0 += 4) {
+        double a[NT];
+#pragma unroll
+        for (int ti = 0; ti < NT; ++ti) a[ti] = Ap[8 * ti * LDA + k0];
+        const double b = Bp[k0 * LDBB];
+#pragma unroll
+        for (int ti = 0; ti < NT; ++ti) dmma884(acc[ti], a[ti], b);
+    }
+}
+
 struct CParams {
     MParams m;
     unsigned char colmap[16];   // warp -> tile column
@@ -551,19 +564,15 @@ __global__ void __maxnreg__((16384 / (32 * ((GT + 3) / 4))) / 8 * 8 > 240 ? 240 
             }
         if (t > 0) {
             __syncthreads();   // T complete
-            // ---------------- P2: upper tiles of C'[:, c] = T B_s[:, c] + Sig
+            // ---------------- P2: upper tiles of C'[:, c] = T B_s[:, c] + Sig.  The number of tiles (c + 1) is fixed
+            // per warp; the loop is instantiated for every count so that the hot loop carries no predicates.
             const double* Ap = Cb + g * LDC + c4;
             const double* Bp = Bs + c4 * LDB + 8 * c + g;
-#pragma unroll 1
-            for (int k0 = 0; k0 < NK; k0 += 4) {
-                double a[GT];
-#pragma unroll
-                for (int ti = 0; ti < GT; ++ti)
-                    if (ti <= c) a[ti] = Ap[8 * ti * LDC + k0];
-                const double b = Bp[k0 * LDB];
-#pragma unroll
-                for (int ti = 0; ti < GT; ++ti)
-                    if (ti <= c) dmma884(acc[ti], a[ti], b);
+            switch (c) {
+#define P2_CASE(CC) case CC: if (CC < GT) mmac_p2<GT, (CC < GT ? CC + 1 : 1), LDC, LDB>(acc, Ap, Bp, NK); break;
+                P2_CASE(0) P2_CASE(1) P2_CASE(2) P2_CASE(3) P2_CASE(4) P2_CASE(5) P2_CASE(6)
+                P2_CASE(7) P2_CASE(8) P2_CASE(9) P2_CASE(10) P2_CASE(11) P2_CASE(12) P2_CASE(13)
+#undef P2_CASE
             }
         }
 
