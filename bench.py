@@ -141,10 +141,10 @@ class ClockSampler:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+                    self.rows.append([time.perf_counter()] + [c.strip() for c in out.splitlines()[0].split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.1)
+            self.stop.wait(0.02)
 
     def __enter__(self):
         self.thread.start()
@@ -154,14 +154,17 @@ class ClockSampler:
         self.stop.set()
         self.thread.join(timeout=6)
 
-    def summary(self):
-        if not self.rows:
+    def summary(self, t0=None, t1=None):
+        """Median SM clock / reasons over the samples taken inside [t0, t1] (all samples if none fell inside)."""
+        rows = [r[1:] for r in self.rows if t0 is None or t0 <= r[0] <= t1] or [r[1:] for r in self.rows]
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = sorted(float(r[0]) for r in self.rows)
+        self_rows = rows
+        sm = sorted(float(r[0]) for r in self_rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]),
-                "power_w_max": max(float(r[2]) for r in self.rows), "reasons": reasons, "samples": len(self.rows)}
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self_rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self_rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in self_rows), "reasons": reasons, "samples": len(self_rows)}
 
 
 # ------------------------------------------------------------------------------------------------ arms
@@ -281,9 +284,9 @@ def run_gpu_arm(args, wl, rank, world, local_rank):
         torch.cuda.synchronize()
         return [a.elapsed_time(b) for a, b in evs]
 
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    with ClockSampler(local_rank) as clk:
+    with ClockSampler(local_rank) as clk:       # started before the warm-up so that nvidia-smi is warm; only samples
+        for _ in range(max(args.warmup, 3)):    # inside the timed window are reported
+            step_device()
         barrier()
         launches0 = lib.bildk_launch_count()
         wall0 = time.perf_counter()
@@ -294,7 +297,7 @@ def run_gpu_arm(args, wl, rank, world, local_rank):
         # kernel-only duration of the filter kernel for the roofline (same stream, CUDA events, L2 flushed)
         kms = timed_steps(lambda: eng.logl_runs_device(th, P, K1, d_starts.data_ptr(), d_states.data_ptr(), d_out.data_ptr(),
                                                        stream.cuda_stream), max(3, min(args.steps, 10)))
-        clocks = clk.summary()
+        clocks = clk.summary(wall0, time.perf_counter())
     t_total = torch.tensor([float(np.sum(ms))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
@@ -347,8 +350,10 @@ def run_gpu_arm(args, wl, rank, world, local_rank):
         "wall_s_timed_region": wall,
         "clocks": clocks,
         "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-                     "traffic": None, "kernel": th.describe_plan(P).split(" FPC")[0].split(" WPC")[0], "kernel_ms": kavg_ms,
-                     "flop_per_launch": fl, "flop_model": "4N^3 d* per frame-step + lower-order terms (SURVEY.md 8d)",
+                     "traffic": _ncu_traffic(args.workload if not args.profiles else None), "kernel": th.describe_plan(P).split(" FPC")[0].split(" WPC")[0], "kernel_ms": kavg_ms,
+                     "flop_per_launch": fl, "flop_model": "4N^3 d* per frame-step + lower-order terms (SURVEY.md 8d); the DMMA kernels execute "
+                                                          "3N^3 (symmetric output) on 8x8 tiles - achieved counts ALGORITHMIC flops only",
+                     "algorithmic_hbm_bytes_per_launch": int(starts.nbytes + rstates.nbytes + traj[:].nbytes + P * 8),
                      "peak_source": f"measured in this run: DFMA {dfma.value:.2f}, DMMA {dmma.value:.2f} TFLOP/s (bildk_measure_fp64_peak)",
                      "hbm_streaming_model": {"bytes_per_frame_step": 16 * N * N,
                                              "achieved_gbs": 16 * N * N * P * (T - 1) / (kavg_ms * 1e-3) * 1e-9,
@@ -364,6 +369,14 @@ def run_gpu_arm(args, wl, rank, world, local_rank):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _ncu_traffic(workload):
+    """DRAM bytes of one launch from the committed ncu capture of this workload (None if there is none)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[workload]["bytes"]
+    except Exception:
+        return None
 
 
 def _hbm_peak():

@@ -297,10 +297,10 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
             fill(C0, padg);
             if ((rc = upload(&m->dC0m, padg.data(), S * matg))) { bildk_model_destroy(m); return rc; }
             const size_t fbytes = (static_cast<size_t>(m->NPm) * m->LDCm + static_cast<size_t>(2) * m->NPm + 2) * 8;
-            if (GT > 7) {   // one CTA per filter, one warp per tile column (k_mmac); at least one propagator resident
-                m->mmac_ok = 16 + matb * 8 + fbytes <= static_cast<size_t>(m->max_smem_optin);
-                m->mma_ok = false;
-            } else
+            // one CTA per filter, one warp per tile column (k_mmac); at least one propagator resident
+            if (GT >= 5) m->mmac_ok = 16 + matb * 8 + fbytes <= static_cast<size_t>(m->max_smem_optin);
+            if (GT > 7) m->mma_ok = false;
+            else
             m->mma_ok = 16 + matb * 8 * S + fbytes <= static_cast<size_t>(m->max_smem_optin);
         }
     }
@@ -446,6 +446,9 @@ static cudaError_t mmac_launch(const CParams& cp, dim3 grid, size_t smem, cudaSt
 }
 static cudaError_t mmac_launch_for(int GT, bool MX, const CParams& cp, dim3 grid, size_t smem, cudaStream_t st) {
     switch (GT * 2 + (MX ? 1 : 0)) {
+        case 10: return mmac_launch<5, false>(cp, grid, smem, st);   case 11: return mmac_launch<5, true>(cp, grid, smem, st);
+        case 12: return mmac_launch<6, false>(cp, grid, smem, st);   case 13: return mmac_launch<6, true>(cp, grid, smem, st);
+        case 14: return mmac_launch<7, false>(cp, grid, smem, st);   case 15: return mmac_launch<7, true>(cp, grid, smem, st);
         case 16: return mmac_launch<8, false>(cp, grid, smem, st);   case 17: return mmac_launch<8, true>(cp, grid, smem, st);
         case 18: return mmac_launch<9, false>(cp, grid, smem, st);   case 19: return mmac_launch<9, true>(cp, grid, smem, st);
         case 20: return mmac_launch<10, false>(cp, grid, smem, st);  case 21: return mmac_launch<10, true>(cp, grid, smem, st);
@@ -461,7 +464,7 @@ static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
     Plan pl{};
     {
         const char* force0 = getenv("BILDK_KERNEL");
-        if (m->mmac_ok && !(force0 && !strcmp(force0, "tile")) && !env_int("BILDK_FORCE_GENERIC", 0)) {
+        if (m->mmac_ok && (m->GT >= env_int("BILDK_MMAC_MIN_GT", 8)) && !(force0 && !strcmp(force0, "tile")) && !env_int("BILDK_FORCE_GENERIC", 0)) {
             const int GT = m->GT;
             const size_t matb = static_cast<size_t>(m->NPm) * m->LDBm * 8;
             const size_t fbytes = (static_cast<size_t>(m->NPm) * m->LDCm + static_cast<size_t>(2) * m->NPm + 2) * 8;

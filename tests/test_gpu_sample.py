@@ -88,3 +88,21 @@ def test_postproc_batched_on_gpu():
     assert abs(lr[1, 1] - (model.logL(moved, traj) - base)) < 1e-9
     opt = postproc.optimize_boundary(start, traj, model)
     assert model.logL(opt, traj) >= base and opt.count_switches() == 2
+
+
+def test_sample_many_on_gpu_equals_one_by_one():
+    """Dataset driver with the real engine: fused multi-trajectory launches == sequential bild.sample runs."""
+    from bild_b200.dataset import sample_many
+    model = bild.models.MultiStateRouse(12, 1, 5, d=3, localization_error=0.3)
+    np.random.seed(3)
+    trajs = [model.trajectory_from_loopingprofile(bild.Loopingprofile([0] * a + [1] * b + [0] * c))
+             for a, b, c in [(10, 12, 8), (15, 15, 0), (7, 6, 12)]]
+    kw = dict(init_runs=5, sampler_kw={"N": 40}, k_max=5)
+    seeds = [11, 12, 13]
+    res, stats = sample_many(trajs, model, seeds=seeds, **kw)
+    assert stats["launches"] == stats["rounds"] > 0
+    for i, tr in enumerate(trajs):
+        np.random.seed(seeds[i])
+        solo = bild.sample(tr, model, **kw)
+        assert np.array_equal(solo.log["k"], res[i].log["k"])
+        assert np.array_equal(solo.evidence, res[i].evidence)       # bitwise: same kernels, same random numbers
