@@ -31,6 +31,16 @@ for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
 
 import numpy as np
 
+# The contract is ONE JSON line on stdout.  Native libraries (NCCL prints its version banner to fd 1) must not
+# add lines: keep a private copy of the real stdout for the result and point fd 1 at stderr for everybody else.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -201,7 +211,7 @@ def run_reference_arm(args, wl, rank, world):
         "e2e": {"value": fs, "unit": "frame-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_gpu_arm(args, wl, rank, world, local_rank):
@@ -366,7 +376,7 @@ def run_gpu_arm(args, wl, rank, world, local_rank):
                                 "sample": f"first {cpu['n']} of {P} profiles, multiprocessing fork pool, 1 BLAS thread per worker",
                                 "evals_per_s": cpu["n"] / cpu["seconds"]}
         line["parity"] = {"max_rel_err_vs_cpu": rel, "n": cpu["n"], "gate": 1e-9, "ok": rel < 1e-9}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

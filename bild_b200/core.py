@@ -91,6 +91,7 @@ def sample(traj, model, dE=0, init_runs=20, certainty_in_k=0.99, k_lookahead=2, 
 
     k_next = 0
     running = True
+    failure = None
     try:
         while running:
             if k_next < len(samplers):
@@ -109,7 +110,14 @@ def sample(traj, model, dE=0, init_runs=20, certainty_in_k=0.99, k_lookahead=2, 
         bar.close()
     except KeyboardInterrupt:  # pragma: no cover
         pass                                       # hand back what we have
-    return SamplingResults(traj, model, dE, samplers, log)
+    except Exception as err:  # noqa: BLE001
+        # The reference returns from a ``finally`` block (core.py:231-236), i.e. it hands back the partial
+        # results on ANY exception (e.g. "Iteration did not converge" from the CFC fit, amis.py:392).  Same here,
+        # but the exception is kept on the results instead of being dropped silently.
+        failure = err
+    out = SamplingResults(traj, model, dE, samplers, log)
+    out.error = failure
+    return out
 
 
 class SamplingResults:
@@ -122,7 +130,10 @@ class SamplingResults:
     log : dict of arrays - per AMIS step: ``k`` sampled, choice distribution ``pk``, expected gains ``KLD``,
         lookahead importance ``I_la`` (ragged entries are NaN padded)
     k, evidence, evidence_se : arrays over the samplers
+    error : None, or the exception that ended the run early (the results are then partial)
     """
+
+    error = None
 
     def __init__(self, traj, model, dE, samplers, log=None):
         self.traj, self.model, self.dE, self.samplers = traj, model, dE, samplers
