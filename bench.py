@@ -51,6 +51,8 @@ WORKLOADS = {
     "n50": dict(N=50, T=1000, P=16384, p_nan=0.0, desc="north-star target shape: N=50, T=1000"),
     "n10": dict(N=10, T=1000, P=65536, p_nan=0.0, desc="sweep point N=10, T=1000, 64k profiles"),
     "n25": dict(N=25, T=1000, P=65536, p_nan=0.0, desc="sweep point N=25, T=1000, 64k profiles"),
+    "n200": dict(N=200, T=100, P=1024, p_nan=0.0, desc="sweep point N=200, T=100, 1024 profiles"),
+    "n150": dict(N=150, T=100, P=2048, p_nan=0.0, desc="N=150, T=100, 2048 profiles"),
     "n20big": dict(N=20, T=500, P=65536, p_nan=0.0, desc="N=20, T=500, 64k profiles"),
 }
 D_SPATIAL, DIFF, KSPRING, LOC_ERR, KMAX = 3, 1.0, 5.0, 0.3, 10

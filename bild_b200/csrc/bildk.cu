@@ -81,7 +81,7 @@ struct bildk_model {
     double *dG = nullptr, *dM0 = nullptr, *dw = nullptr;
     uint16_t* d_lane_ab = nullptr;   // [G*G] lane -> tile map (2x2 tile blocks per lane quad)
     // tensor-core (DMMA) layout: 8x8 tiles, row strides == 4 (mod 8)
-    bool mma_ok = false, mma_mx = false, mmac_ok = false;
+    bool mma_ok = false, mma_mx = false, mmac_ok = false, mmag_ok = false;
     int GT = 0, NPm = 0, LDBm = 0, LDCm = 0, MC0 = 0, NK = 0;
     double *dBm = nullptr, *dSigm = nullptr, *dC0m = nullptr;
     // per-model scratch for the host-pointer entry points
@@ -89,6 +89,7 @@ struct bildk_model {
     DevBuf<uint8_t> states;
     DevBuf<double> out, part, work;
     DevBuf<int> meta;          // traj_first / cta maps / prof_traj
+    DevBuf<int> meta2;         // prof_traj of the L2-workspace tensor-core kernel
     DevBuf<const double*> xptrs;
     DevBuf<const uint8_t*> vptrs;
     int max_smem_optin = 0;
@@ -185,7 +186,7 @@ extern "C" int bildk_model_destroy(bildk_model_t m) {
         if (p) cudaFree(p);
     if (m->d_lane_ab) cudaFree(m->d_lane_ab);
     m->starts.release(); m->states.release(); m->out.release(); m->part.release(); m->work.release();
-    m->meta.release(); m->xptrs.release(); m->vptrs.release();
+    m->meta.release(); m->meta2.release(); m->xptrs.release(); m->vptrs.release();
     delete m;
     return BILDK_OK;
 }
@@ -263,7 +264,7 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
     // tensor-core layout (one warp per filter): N <= 56, sparse measurement vector
     {
         const int GT = (N + 7) / 8;
-        if (GT <= 14 && m->nnz == 2) {
+        if (GT <= 32 && m->nnz == 2) {
             m->GT = GT; m->NPm = 8 * GT;
             m->mma_mx = (m->NPm - N) < d;
             m->MC0 = m->mma_mx ? m->NPm : N;
@@ -298,7 +299,8 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
             if ((rc = upload(&m->dC0m, padg.data(), S * matg))) { bildk_model_destroy(m); return rc; }
             const size_t fbytes = (static_cast<size_t>(m->NPm) * m->LDCm + static_cast<size_t>(2) * m->NPm + 2) * 8;
             // one CTA per filter, one warp per tile column (k_mmac); at least one propagator resident
-            if (GT >= 5) m->mmac_ok = 16 + matb * 8 + fbytes <= static_cast<size_t>(m->max_smem_optin);
+            if (GT >= 5 && GT <= 14) m->mmac_ok = 16 + matb * 8 + fbytes <= static_cast<size_t>(m->max_smem_optin);
+            if (GT > 7) m->mmag_ok = true;   // covariance in an L2 workspace: any GT <= 32
             if (GT > 7) m->mma_ok = false;
             else
             m->mma_ok = 16 + matb * 8 * S + fbytes <= static_cast<size_t>(m->max_smem_optin);
@@ -377,7 +379,8 @@ extern "C" int bildk_traj_create(bildk_model_t m, int T, const double* x, int ds
 struct Plan {
     bool mma = false;      // tensor-core kernel, one warp per filter
     bool mmac = false;     // tensor-core kernel, one CTA per filter, one warp per tile column
-    unsigned char colmap[16] = {0};
+    bool mmag = false;     // same, covariance in an L2 workspace (N > 112)
+    unsigned char colmap[40] = {0};
     int WPC = 0;
     bool tile;
     bool ws, densew, b_all;
@@ -464,6 +467,27 @@ static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
     Plan pl{};
     {
         const char* force0 = getenv("BILDK_KERNEL");
+        const bool no_tc = (force0 && !strcmp(force0, "tile")) || env_int("BILDK_FORCE_GENERIC", 0);
+        if (m->mmag_ok && !no_tc && (!m->mmac_ok || (force0 && !strcmp(force0, "mmag")))) {
+            const int GT = m->GT;
+            pl.mmag = true;
+            pl.tile = false;
+            pl.smem = (static_cast<size_t>(2) * m->NPm + 2) * 8;
+            pl.threads = 32 * GT;
+            pl.FPC = 1;
+            double load[4] = {0, 0, 0, 0};
+            int slots[4], used[4] = {0, 0, 0, 0};
+            for (int k = 0; k < 4; ++k) slots[k] = (GT - k + 3) / 4;
+            for (int c = GT - 1; c >= 0; --c) {
+                int best = -1;
+                for (int k = 0; k < 4; ++k)
+                    if (used[k] < slots[k] && (best < 0 || load[k] < load[best])) best = k;
+                pl.colmap[best + 4 * used[best]] = static_cast<unsigned char>(c);
+                load[best] += GT + c + 1 + ((c == 0 && m->mma_mx) ? GT : 0);
+                ++used[best];
+            }
+            return pl;
+        }
         if (m->mmac_ok && (m->GT >= env_int("BILDK_MMAC_MIN_GT", 8)) && !(force0 && !strcmp(force0, "tile")) && !env_int("BILDK_FORCE_GENERIC", 0)) {
             const int GT = m->GT;
             const size_t matb = static_cast<size_t>(m->NPm) * m->LDBm * 8;
@@ -604,7 +628,10 @@ static cudaError_t launch_tile(const Plan& pl, const KParams& kp, dim3 grid, cud
 
 static std::string plan_string(const bildk_model* m, const Plan& pl) {
     char buf[256];
-    if (pl.mmac)
+    if (pl.mmag)
+        snprintf(buf, sizeof buf, "mmag (DMMA m8n8k4) GT=%d %s cta-per-filter warp-per-tile-column covariance-in-L2-workspace threads=%d", m->GT,
+                 m->mma_mx ? "mean-in-extra-tile" : "mean-in-padding", pl.threads);
+    else if (pl.mmac)
         snprintf(buf, sizeof buf, "mmac (DMMA m8n8k4) GT=%d %s cta-per-filter warp-per-tile-column B=%s threads=%d smem=%zu", m->GT,
                  m->mma_mx ? "mean-in-extra-tile" : "mean-in-padding", pl.b_all ? "all" : "one", pl.threads, pl.smem);
     else if (pl.mma)
@@ -641,7 +668,7 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
         if (rc) return rc;
         d_part = m->part.p;
     }
-    if (pl.mma || pl.mmac || pl.tile) {
+    if (pl.mma || pl.mmac || pl.mmag || pl.tile) {
         KParams kp{};
         kp.N = m->N; kp.D = m->D; kp.S = m->S; kp.G = m->G; kp.LD = m->LD; kp.NP = m->NP;
         kp.Bpad = m->dBpad; kp.Sigpad = m->dSigpad; kp.C0pad = m->dC0pad; kp.Gm = m->dG; kp.M0 = m->dM0; kp.w = m->dw;
@@ -655,7 +682,7 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
         }
         kp.P = P; kp.K1 = K1; kp.run_starts = d_starts; kp.run_states = d_states; kp.out = d_part;
         if (pl.mma) pl.FPC = pl.WPC;   // CTA -> first filter maps use FPC
-        if (pl.mmac) pl.FPC = 1;
+        if (pl.mmac || pl.mmag) pl.FPC = 1;
         kp.FPC = pl.FPC; kp.TPFS = pl.TPFS; kp.b_all = pl.b_all; kp.fstride = pl.fstride; kp.bstride = pl.bstride; kp.lane_ab = m->d_lane_ab;
         int n_cta = 0;
         if (n_traj == 1) {
@@ -675,7 +702,31 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
             kp.cta_traj = m->meta.p; kp.cta_first = m->meta.p + n_cta;
         }
         dim3 grid(n_cta, dstar);
-        if (pl.mma || pl.mmac) {
+        if (pl.mmag) {
+            GMParams gp{};
+            MParams& mp = gp.m;
+            mp.k = kp;
+            mp.k.cta_traj = nullptr; mp.k.cta_first = nullptr;
+            mp.NPm = m->NPm; mp.LDB = m->LDBm; mp.LDC = m->LDCm; mp.MC0 = m->MC0; mp.NK = m->NK;
+            mp.Bm = m->dBm; mp.Sigm = m->dSigm; mp.C0m = m->dC0m;
+            for (int i = 0; i < 40; ++i) gp.colmap[i] = pl.colmap[i];
+            gp.prof_traj = nullptr;
+            if (n_traj > 1) {
+                std::vector<int> pt(P);
+                for (int i = 0; i < n_traj; ++i) for (int f = h_first[i]; f < h_first[i + 1]; ++f) pt[f] = i;
+                int rc = m->meta2.reserve(P);
+                if (rc) return rc;
+                CU(cudaMemcpy(m->meta2.p, pt.data(), P * sizeof(int), cudaMemcpyHostToDevice));
+                gp.prof_traj = m->meta2.p;
+            }
+            const int nc = std::min(P, 2 * m->n_sm);
+            const size_t wsz = static_cast<size_t>(2) * m->NPm * m->LDCm;
+            int rc = m->work.reserve(wsz * nc * dstar);
+            if (rc) return rc;
+            gp.work = m->work.p;
+            k_mmag<4><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);
+            CU(cudaGetLastError());
+        } else if (pl.mma || pl.mmac) {
             MParams mp{};
             mp.k = kp;
             mp.NPm = m->NPm; mp.LDB = m->LDBm; mp.LDC = m->LDCm; mp.MC0 = m->MC0; mp.NK = m->NK;
@@ -685,7 +736,7 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
                 CParams cp{};
                 cp.m = mp;
                 cp.b_all = pl.b_all;
-                for (int i = 0; i < 16; ++i) cp.colmap[i] = pl.colmap[i];
+                for (int i = 0; i < 16; ++i) cp.colmap[i] = pl.colmap[i];   // GT <= 14
                 CU(mmac_launch_for(m->GT, m->mma_mx, cp, grid, pl.smem, st));
             } else
             CU(mma_launch_for(m->GT, m->mma_mx, mp, grid, pl.threads, pl.smem, st));

@@ -712,3 +712,267 @@ __global__ void __maxnreg__((16384 / (32 * ((GT + 3) / 4))) / 8 * 8 > 240 ? 240 
 }
 
 }  // namespace bildk
+
+namespace bildk {
+
+// ================================================================================================
+// k_mmag - FP64 tensor cores for polymers whose covariance does not fit in shared memory
+// (112 < N <= 256): ONE CTA PER FILTER, ONE WARP PER TILE COLUMN, covariance and intermediate in a per-CTA
+// L2-resident workspace (two buffers, so no in-place constraint), fragments loaded with plain global
+// loads (L1-cached; block barriers order them), tiles processed in row chunks of CH to stay within the
+// 64-72 registers that 7-8 warps per scheduler leave.  Same symmetric scheme as k_mmac.
+//   P1   warp(c): T[:, c] = B_s C[:, c]          (chunks of CH tile rows, stored to the T buffer)
+//   ---- CTA barrier
+//   P2   warp(c): prior C'[ti <= c, c] = T B_s[:, c] + Sig  (chunks; published columns; stored to the C buffer)
+//   ---- CTA barrier
+//   upd  read-modify-write of the warp's own tiles in the C buffer (rank-1 update), mirrored; mean by the
+//        owner of the last tile column
+//   ---- CTA barrier
+struct GMParams {
+    MParams m;
+    unsigned char colmap[40];   // warp -> tile column
+    double* work;               // [gridDim.x * gridDim.y][2 * NPm * LDC]
+    const int* prof_traj;       // [P] trajectory of every profile (nullptr: single trajectory)
+};
+
+template <int CH>
+__global__ void __launch_bounds__(1024, 1) k_mmag(const __grid_constant__ GMParams gp, const int GT, const int MXi) {
+    const MParams& mp = gp.m;
+    const KParams& p = mp.k;
+    const bool MX = MXi != 0;
+    const int GTC = GT + (MX ? 1 : 0);
+    const int TJM = MX ? GT : GT - 1;
+    const int NPm = 8 * GT, LDB = mp.LDB, LDC = mp.LDC;
+    const size_t MATB = static_cast<size_t>(NPm) * LDB, MATG = static_cast<size_t>(NPm) * NPm;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* colb = reinterpret_cast<double*>(smem_raw);    // [2][NPm]
+    double* const lst = colb + 2 * NPm;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int g = lane >> 2, c4 = lane & 3;
+    const int e_sub = blockIdx.y;
+    const int N = p.N, D = p.D, NK = mp.NK;
+    const int c = gp.colmap[wid];
+    const bool mown = (c == GT - 1);
+    const bool mxw = MX && (c == 0);
+
+    double* Cg = gp.work + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 2 * NPm * LDC;
+    double* Tg = Cg + static_cast<size_t>(NPm) * LDC;
+    const int ncols = p.ncols[e_sub];
+    const double s2 = p.s2[e_sub];
+    const int j0 = p.wz_idx[0], j1 = p.wz_idx[1];
+    const double w0 = p.wz_val[0], w1 = p.wz_val[1];
+    const int q0 = 2 * c4 - (mp.MC0 - 8 * TJM), q1 = q0 + 1;
+    const bool qv0 = static_cast<unsigned>(q0) < static_cast<unsigned>(ncols);
+    const bool qv1 = static_cast<unsigned>(q1) < static_cast<unsigned>(ncols);
+    const int xc0 = p.cols[e_sub][qv0 ? q0 : 0], xc1 = p.cols[e_sub][qv1 ? q1 : 0];
+    const int pairoff = g * LDC + 2 * c4;   // accumulator pair of tile (ti, tj): + 8 ti LDC + 8 tj
+
+  for (int pidx = blockIdx.x; pidx < p.P; pidx += gridDim.x) {   // a CTA (and its workspace) serves several filters in turn
+    const int tj = gp.prof_traj ? gp.prof_traj[pidx] : 0;
+    const int T = p.T[tj];
+    const double* __restrict__ xg = p.x[tj];
+    const uint32_t* __restrict__ vbits = reinterpret_cast<const uint32_t*>(p.valid[tj] + (T + 3) / 4 * 4);
+    uint32_t vword = 0;
+    double quad = 0.0;
+    if (tid == 0) { lst[0] = 1.0; reinterpret_cast<int*>(lst + 1)[0] = 0; reinterpret_cast<int*>(lst + 1)[1] = 0; }
+
+    int r_cur = 0;
+    int s = p.run_states[static_cast<size_t>(pidx) * p.K1];
+    int next_sw = (p.K1 > 1) ? p.run_starts[static_cast<size_t>(pidx) * p.K1 + 1] : 0x7fffffff;
+
+    for (int t = 0; t < T; ++t) {
+        while (t >= next_sw) {
+            ++r_cur;
+            s = p.run_states[static_cast<size_t>(pidx) * p.K1 + r_cur];
+            next_sw = (r_cur + 1 < p.K1) ? p.run_starts[static_cast<size_t>(pidx) * p.K1 + r_cur + 1] : 0x7fffffff;
+        }
+        if ((t & 31) == 0) vword = __ldg(vbits + (t >> 5));
+        const bool is_valid = (vword >> (t & 31)) & 1u;
+        const double* Bs = mp.Bm + MATB * s;
+        const double* Gsrc = ((t == 0) ? mp.C0m : mp.Sigm) + MATG * s + g * NPm + 2 * c4;
+
+        if (t > 0) {
+            // ---------------- P1: T[:, cc] = B_s Caug[:, cc]
+            for (int pass = 0; pass < (mxw ? 2 : 1); ++pass) {
+                const int cc = pass ? GT : c;
+                for (int r0 = 0; r0 < GT; r0 += CH) {
+                    double acc[CH][2];
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) acc[i][0] = acc[i][1] = 0.0;
+                    const double* Ap = Bs + static_cast<size_t>(8 * r0 + g) * LDB + c4;
+                    const double* Bp = Cg + c4 * LDC + 8 * cc + g;
+#pragma unroll 1
+                    for (int k0 = 0; k0 < NK; k0 += 4) {
+                        double a[CH];
+#pragma unroll
+                        for (int i = 0; i < CH; ++i) a[i] = (r0 + i < GT) ? Ap[8 * i * LDB + k0] : 0.0;
+                        const double b = Bp[k0 * LDC];
+#pragma unroll
+                        for (int i = 0; i < CH; ++i) dmma884(acc[i], a[i], b);
+                    }
+#pragma unroll
+                    for (int i = 0; i < CH; ++i)
+                        if (r0 + i < GT)
+                            *reinterpret_cast<double2*>(Tg + pairoff + 8 * (r0 + i) * LDC + 8 * cc) = make_double2(acc[i][0], acc[i][1]);
+                }
+            }
+            __syncthreads();   // T complete
+        }
+        // ---------------- P2 (t > 0) / steady state (t = 0): prior C' tiles (ti <= c, c), published columns, stored to C
+        for (int r0 = 0; r0 <= c; r0 += CH) {
+            double acc[CH][2];
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                acc[i][0] = acc[i][1] = 0.0;
+                if (r0 + i <= c) {
+                    const double2 v = __ldg(reinterpret_cast<const double2*>(Gsrc + 8 * (r0 + i) * NPm + 8 * c));
+                    acc[i][0] = v.x;
+                    acc[i][1] = v.y;
+                }
+            }
+            if (t > 0) {
+                const double* Ap = Tg + (8 * r0 + g) * LDC + c4;
+                const double* Bp = Bs + c4 * LDB + 8 * c + g;
+#pragma unroll 1
+                for (int k0 = 0; k0 < NK; k0 += 4) {
+                    double a[CH];
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) a[i] = (r0 + i <= c) ? Ap[8 * i * LDC + k0] : 0.0;
+                    const double b = Bp[k0 * LDB];
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) dmma884(acc[i], a[i], b);
+                }
+            }
+            if (is_valid) {
+#pragma unroll
+                for (int z = 0; z < 2; ++z) {
+                    const int jz = z ? j1 : j0;
+                    const int tjz = jz >> 3, cj = jz & 7;
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) {
+                        const int ti = r0 + i;
+                        if (ti <= c) {
+                            if (c == tjz && c4 == (cj >> 1)) colb[z * NPm + 8 * ti + g] = (cj & 1) ? acc[i][1] : acc[i][0];
+                            if (c > tjz && ti == tjz && g == cj)
+                                *reinterpret_cast<double2*>(colb + z * NPm + 8 * c + 2 * c4) = make_double2(acc[i][0], acc[i][1]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < CH; ++i)
+                if (r0 + i <= c) *reinterpret_cast<double2*>(Cg + pairoff + 8 * (r0 + i) * LDC + 8 * c) = make_double2(acc[i][0], acc[i][1]);
+        }
+        // mean prior: M0 at t = 0, else M' from the T buffer (written with T); kept in Cg's mean columns
+        auto mean_prior = [&](int ti, double& m0, double& m1) {
+            const int row = 8 * ti + g;
+            if (t == 0) {
+                m0 = (qv0 && row < N) ? __ldg(p.M0 + (s * N + row) * D + xc0) : 0.0;
+                m1 = (qv1 && row < N) ? __ldg(p.M0 + (s * N + row) * D + xc1) : 0.0;
+            } else {
+                const double2 v = *reinterpret_cast<const double2*>(Tg + pairoff + 8 * ti * LDC + 8 * TJM);
+                m0 = qv0 ? v.x : 0.0;
+                m1 = qv1 ? v.y : 0.0;
+                if (p.hasG && row < N) {
+                    if (qv0) m0 += __ldg(p.Gm + (s * N + row) * D + xc0);
+                    if (qv1) m1 += __ldg(p.Gm + (s * N + row) * D + xc1);
+                }
+            }
+        };
+        double* Msrc = (t == 0) ? Cg : Tg;   // where w . M' is read from
+        if (is_valid && t == 0 && mown) {
+            for (int ti = 0; ti < GT; ++ti) {
+                double m0, m1;
+                mean_prior(ti, m0, m1);
+                if (qv0) Cg[(8 * ti + g) * LDC + mp.MC0 + q0] = m0;
+                if (qv1) Cg[(8 * ti + g) * LDC + mp.MC0 + q1] = m1;
+            }
+        }
+        __syncthreads();   // prior C' (and published columns, M') visible
+        double xm0 = 0.0, xm1 = 0.0, Sinv = 0.0;
+        if (is_valid) {
+            const double cw_j0 = fma(w1, colb[NPm + j0], w0 * colb[j0]);
+            const double cw_j1 = fma(w1, colb[NPm + j1], w0 * colb[j1]);
+            const double S = fma(w1, cw_j1, fma(w0, cw_j0, s2));
+            Sinv = __drcp_rn(S);                                            // pyx:63
+            if (mown) {
+                if (qv0) {
+                    double ma = Msrc[j0 * LDC + mp.MC0 + q0], mb = Msrc[j1 * LDC + mp.MC0 + q0];
+                    if (p.hasG && t > 0) { ma += __ldg(p.Gm + (s * N + j0) * D + xc0); mb += __ldg(p.Gm + (s * N + j1) * D + xc0); }
+                    xm0 = __ldg(xg + t * D + xc0) - fma(w1, mb, w0 * ma);   // pyx:79
+                    if (g == 0) quad = fma(xm0 * xm0, Sinv, quad);
+                }
+                if (qv1) {
+                    double ma = Msrc[j0 * LDC + mp.MC0 + q1], mb = Msrc[j1 * LDC + mp.MC0 + q1];
+                    if (p.hasG && t > 0) { ma += __ldg(p.Gm + (s * N + j0) * D + xc1); mb += __ldg(p.Gm + (s * N + j1) * D + xc1); }
+                    xm1 = __ldg(xg + t * D + xc1) - fma(w1, mb, w0 * ma);
+                    if (g == 0) quad = fma(xm1 * xm1, Sinv, quad);
+                }
+                if (lane == 0) {
+                    double lmant = lst[0] * Sinv;
+                    const int ex = ((__double2hiint(lmant) >> 20) & 0x7ff) - 1023;
+                    lmant = __hiloint2double(__double2hiint(lmant) - (ex << 20), __double2loint(lmant));
+                    lst[0] = lmant;
+                    reinterpret_cast<int*>(lst + 1)[0] += ex;
+                    reinterpret_cast<int*>(lst + 1)[1] += 1;
+                }
+                __syncwarp();
+            }
+        }
+        // ---------------- update + write-back of the warp's own tiles (read-modify-write in the C buffer), mirrored
+        if (t + 1 < T) {
+            double c0v = 0.0, c1v = 0.0;
+            if (is_valid) {
+                const double2 u = *reinterpret_cast<const double2*>(colb + 8 * c + 2 * c4);
+                const double2 v = *reinterpret_cast<const double2*>(colb + NPm + 8 * c + 2 * c4);
+                c0v = fma(w1, v.x, w0 * u.x);
+                c1v = fma(w1, v.y, w0 * u.y);
+            }
+            for (int ti = 0; ti <= c; ++ti) {
+                double2 v = *reinterpret_cast<const double2*>(Cg + pairoff + 8 * ti * LDC + 8 * c);
+                double kr = 0.0;
+                if (is_valid) {
+                    kr = fma(w1, colb[NPm + 8 * ti + g], w0 * colb[8 * ti + g]) * Sinv;   // pyx:66-67
+                    v.x = fma(-kr, c0v, v.x);                                               // pyx:71-75
+                    v.y = fma(-kr, c1v, v.y);
+                }
+                if (ti < c) {
+                    const int r0 = 8 * c + 2 * c4;
+                    Cg[r0 * LDC + 8 * ti + g] = v.x;
+                    Cg[(r0 + 1) * LDC + 8 * ti + g] = v.y;
+                }
+                if (mown) {
+                    double m0, m1;
+                    mean_prior(ti, m0, m1);
+                    if (is_valid) {
+                        m0 = fma(kr, xm0, m0);   // pyx:82-85
+                        m1 = fma(kr, xm1, m1);
+                    }
+                    if (!MX) {
+                        if (qv0) v.x = m0;
+                        if (qv1) v.y = m1;
+                    } else {
+                        *reinterpret_cast<double2*>(Cg + pairoff + 8 * ti * LDC + 8 * TJM) = make_double2(m0, m1);
+                    }
+                }
+                *reinterpret_cast<double2*>(Cg + pairoff + 8 * ti * LDC + 8 * c) = v;
+            }
+        }
+        __syncthreads();   // C+ complete
+    }
+
+    if (mown) {
+        quad += __shfl_xor_sync(0xffffffffu, quad, 1);
+        quad += __shfl_xor_sync(0xffffffffu, quad, 2);
+        if (lane == 0) {
+            const int lexp = reinterpret_cast<const int*>(lst + 1)[0], nvalid = reinterpret_cast<const int*>(lst + 1)[1];
+            const double logdet = log(lst[0]) + lexp * 0.6931471805599453;
+            p.out[static_cast<size_t>(e_sub) * p.P + pidx] = -0.5 * (quad - ncols * logdet + static_cast<double>(nvalid) * ncols * LOG_2PI);
+        }
+    }
+    __syncthreads();   // the log-likelihood state and the workspace are reused by the next filter
+  }
+}
+
+}  // namespace bildk

@@ -45,7 +45,9 @@ CASES = [
     (64, 3, 20, 3, 0.0, 0.3, (None, [(0, -1)]), 3),             # GT=8, no padding room: mean in an extra tile column
     (96, 2, 16, 3, 0.2, 0.3, (None, [(0, -1)], [(10, 50)]), 3), # GT=12, 3 states: single resident propagator, TMA swaps
     (110, 3, 12, 2, 0.0, 0.3, (None, [(0, -1)]), 2),            # GT=14
-    (130, 2, 12, 3, 0.0, 0.3, (None, [(0, -1)]), 2),            # beyond the on-chip limit: catch-all kernel
+    (120, 2, 12, 3, 0.1, 0.3, (None, [(0, -1)]), 2),            # GT=15, no padding room: tensor cores with the covariance in L2
+    (130, 2, 12, 3, 0.0, 0.3, (None, [(0, -1)]), 2),            # GT=17: beyond the shared-memory limit
+    (200, 3, 8, 2, 0.0, 0.3, (None, [(0, -1)], [(20, 150)]), 2),  # BASELINE sweep size N=200, 3 states
 ]
 
 
@@ -67,6 +69,28 @@ def test_against_c_oracle(N, d, T, P, p_nan, noise, loops, kmax):
     assert rel_err(got_st, want) < TOL
     assert rel_err(got_states, want) < TOL
     assert np.array_equal(got_st, got_states)          # same filters, same arithmetic
+
+
+@pytest.mark.parametrize("kernel", ["tile", "mmag"])
+@pytest.mark.parametrize("N", [20, 60, 100])
+def test_kernel_variants_agree(kernel, N, monkeypatch):
+    """Every kernel family that can run a shape gives the oracle's answer (BILDK_KERNEL forces the family)."""
+    if kernel == "mmag" and N < 57:
+        pytest.skip("the L2-workspace tensor-core kernel starts at GT = 8")
+    rng = np.random.default_rng(N)
+    mod = oracle_model(N, d=3)
+    T, P = 25, 5
+    x, _ = synth_traj(mod, T, rng, 0.3, p_nan=0.1)
+    ss, thetas = random_profiles(rng, P, T, 2, 4)
+    s2, Cind = ko.noise_to_s2_cind([0.3] * 3)
+    states = np.array([ko.st2states(s, th, T) for s, th in zip(ss, thetas)])
+    want = ko.logl_c(*(mod[k] for k in MODEL_KEYS), x, s2, Cind, states)
+    eng = engine_for(mod)
+    traj = eng.trajectory(x, [0.3] * 3)
+    monkeypatch.setenv("BILDK_KERNEL", kernel)
+    assert kernel in traj.describe_plan(P).split()[0]
+    got = eng.logl_st(traj, ss, thetas)
+    assert rel_err(got, want) < TOL
 
 
 def test_dense_measurement_vector():
