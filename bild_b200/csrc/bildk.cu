@@ -724,7 +724,12 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
             int rc = m->work.reserve(wsz * nc * dstar);
             if (rc) return rc;
             gp.work = m->work.p;
-            k_mmag<4><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);
+            // row-chunk size by the registers the warp count leaves (registers are allocated per scheduler)
+            auto waste = [&](int chv) { return ((m->GT + chv - 1) / chv) * chv; };   // padded tile rows per column
+            const int ch = env_int("BILDK_MMAG_CH", m->GT <= 16 ? 8 : ((m->GT <= 28 && waste(6) <= waste(4)) ? 6 : 4));
+            if (ch >= 8 && m->GT <= 16) k_mmag<8, 512><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);
+            else if (ch >= 6 && m->GT <= 28) k_mmag<6, 896><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);
+            else k_mmag<4, 1024><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);
             CU(cudaGetLastError());
         } else if (pl.mma || pl.mmac) {
             MParams mp{};

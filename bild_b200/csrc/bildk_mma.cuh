@@ -735,8 +735,8 @@ struct GMParams {
     const int* prof_traj;       // [P] trajectory of every profile (nullptr: single trajectory)
 };
 
-template <int CH>
-__global__ void __launch_bounds__(1024, 1) k_mmag(const __grid_constant__ GMParams gp, const int GT, const int MXi) {
+template <int CH, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) k_mmag(const __grid_constant__ GMParams gp, const int GT, const int MXi) {
     const MParams& mp = gp.m;
     const KParams& p = mp.k;
     const bool MX = MXi != 0;

@@ -60,8 +60,8 @@ dev = torch.device("cuda", 0)
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 rows = []
 for N, T, P in points:
-    if N == 200 and P > 1024:
-        rows.append(dict(N=N, T=T, P=P, skipped="catch-all kernel only (covariance does not fit on chip); not run at 64k"))
+    if N == 200 and P > 1024 and T > 100:
+        rows.append(dict(N=N, T=T, P=P, skipped="not run: 2.1e15 flop (about 3 minutes at the measured N=200 rate)"))
         print(json.dumps(rows[-1]), flush=True)
         continue
     wl = dict(N=N, T=T, P=P, p_nan=0.0)
@@ -79,6 +79,8 @@ for N, T, P in points:
     torch.cuda.synchronize()
     times = []
     reps = 3 if N < 200 else 1
+    if N == 200 and P > 1024:
+        reps = 1
     for _ in range(reps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
