@@ -93,6 +93,36 @@ def test_kernel_variants_agree(kernel, N, monkeypatch):
     assert rel_err(got, want) < TOL
 
 
+@pytest.mark.parametrize("N,nz", [
+    (20, {3: -1.0, 14: 1.0}),            # two interior monomers (k_mma)
+    (20, {7: 0.5, 8: -2.0}),             # neighbours in one tile, unequal weights
+    (26, {0: -1.0, 25: 1.0}),            # GT=4, mean columns in padding
+    (50, {10: -1.0, 40: 1.0}),           # k_mma GT=7
+    (60, {5: 1.0, 58: -1.0}),            # k_mmac
+    (100, {49: -1.0, 50: 1.0}),          # k_mmac, both non-zeros in one tile column
+    (130, {1: -1.0, 120: 1.0}),          # k_mmag
+    (20, {4: 1.0}),                      # one non-zero: absolute position of one monomer (tile kernel, sparse path)
+    (20, {2: -1.0, 9: 0.5, 17: 0.5}),    # three non-zeros
+    (24, {0: -1.0, 5: 1.0, 11: -1.0, 23: 1.0}),   # four non-zeros
+])
+def test_sparse_measurement_vectors(N, nz):
+    """The measurement vector is arbitrary in the API (models.py:193-196); kernels specialise on its sparsity."""
+    rng = np.random.default_rng(N + len(nz))
+    w = np.zeros(N)
+    for i, v in nz.items():
+        w[i] = v
+    mod = oracle_model(N, d=3, w=w)
+    T, P = 30, 6
+    x, _ = synth_traj(mod, T, rng, 0.25, p_nan=0.1)
+    ss, thetas = random_profiles(rng, P, T, 2, 4)
+    s2, Cind = ko.noise_to_s2_cind([0.25] * 3)
+    states = np.array([ko.st2states(s, th, T) for s, th in zip(ss, thetas)])
+    want = ko.logl_c(*(mod[k] for k in MODEL_KEYS), x, s2, Cind, states)
+    eng = engine_for(mod)
+    got = eng.logl_st(eng.trajectory(x, [0.25] * 3), ss, thetas)
+    assert rel_err(got, want) < TOL
+
+
 def test_dense_measurement_vector():
     rng = np.random.default_rng(5)
     N, d, T, P = 20, 3, 60, 21
