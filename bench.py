@@ -140,6 +140,8 @@ def cpu_reference(model, traj, states, n_sample, repeats=1):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock, power and clock-event (throttle) reasons sampled DURING the timed region: NVML in-process
+    (a few hundred samples per second); falls back to polling nvidia-smi when NVML is unavailable."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -147,7 +149,42 @@ class ClockSampler:
         self.index, self.rows, self.stop = index, [], threading.Event()
         self.thread = threading.Thread(target=self._run, daemon=True)
 
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        # CUDA_VISIBLE_DEVICES may renumber devices; resolve through the UUID of the CUDA device when possible
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            for i in range(nv.nvmlDeviceGetCount()):
+                hi = nv.nvmlDeviceGetHandleByIndex(i)
+                u = nv.nvmlDeviceGetUUID(hi)
+                u = u.decode() if isinstance(u, bytes) else u
+                if uuid in u:
+                    h = hi
+                    break
+        except Exception:
+            pass
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop.is_set():
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            self.rows.append([time.perf_counter(), str(sm), str(mx), str(pw)] + ["Active" if r & bits[n] else "Not Active" for n in names])
+            self.stop.wait(0.004)
+
     def _run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            pass
         while not self.stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],

@@ -29,6 +29,7 @@ SYMBOLS = {
                                           ctypes.POINTER(ctypes.c_void_p)]),
     "bildk_traj_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "bildk_logl_runs": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_int32_p, c_uint8_p, c_double_p]),
+    "bildk_logl_st": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_double_p, ctypes.POINTER(ctypes.c_int64), c_double_p]),
     "bildk_logl_states": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_int32_p, c_double_p]),
     "bildk_logl_runs_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                                ctypes.c_void_p, ctypes.c_void_p]),

@@ -526,7 +526,7 @@ static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
             double best = -1;
             int best_w = 1;
             const int forced = env_int("BILDK_WPC", 0);
-            const int wmax = m->GT <= 3 ? 14 : 8;   // __launch_bounds__ of k_mma
+            const int wmax = m->GT <= 3 ? 28 : 8;   // __launch_bounds__ of k_mma
             for (int w = 1; w <= wmax; ++w) {
                 if (forced && w != forced) continue;
                 const size_t smem = 16 + matb * m->S + fbytes * w;
@@ -537,10 +537,12 @@ static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
                 if (per_sm < 1) continue;
                 const long long slots = static_cast<long long>(m->n_sm) * per_sm * w;
                 const long long waves = (P + slots - 1) / slots;
-                // efficiency of the last wave plus a mild preference for more resident warps (latency hiding)
-                // tail efficiency of the last wave x how well the resident warps can keep the FP64 pipe fed
-                // (>= 2 warps per scheduler hide the store / update / barrier phases of each other)
-                const double eff = static_cast<double>(P) / (waves * slots) * std::min(1.0, per_sm * w / 8.0) + 1e-4 * per_sm * w;
+                // warp i of a CTA runs on scheduler i % 4: the busiest scheduler sets the pace
+                const int busiest = per_sm * ((w + 3) / 4);
+                const double balance = (per_sm * w / 4.0) / busiest;
+                // tail efficiency of the last wave x scheduler balance x how well the resident warps can keep the
+                // FP64 pipe fed (>= 2 warps per scheduler hide each other's store / update / barrier phases)
+                const double eff = static_cast<double>(P) / (waves * slots) * balance * std::min(1.0, 0.6 + 0.4 * per_sm * w / 8.0) + 1e-4 * per_sm * w;
                 if (eff > best) { best = eff; best_w = w; }
             }
             if (best > 0) {
@@ -881,6 +883,38 @@ extern "C" int bildk_logl_runs(bildk_traj_t t, int P, int K1, const int32_t* sta
     int32_t off[2] = {0, P};
     bildk_traj_t arr[1] = {t};
     return bildk_logl_runs_multi(1, arr, off, K1, starts, states, out);
+}
+
+extern "C" int bildk_logl_st(bildk_traj_t t, int P, int K1, const double* ss, const int64_t* thetas, double* out) {
+    if (!t) return fail(BILDK_EINVAL, "NULL trajectory");
+    if (P < 0 || K1 < 1) return fail(BILDK_EINVAL, "need P >= 0 and K1 >= 1");
+    if (P == 0) return BILDK_OK;
+    if (!ss || !thetas || !out) return fail(BILDK_EINVAL, "NULL array argument");
+    const int T = t->T, S = t->m->S;
+    thread_local std::vector<int32_t> rs;
+    thread_local std::vector<uint8_t> rt;
+    rs.resize(static_cast<size_t>(P) * K1);
+    rt.resize(static_cast<size_t>(P) * K1);
+    const double Tm1 = static_cast<double>(T - 1);
+    for (int p = 0; p < P; ++p) {
+        const double* s = ss + static_cast<size_t>(p) * K1;
+        const int64_t* th = thetas + static_cast<size_t>(p) * K1;
+        int32_t* r = rs.data() + static_cast<size_t>(p) * K1;
+        uint8_t* q = rt.data() + static_cast<size_t>(p) * K1;
+        double cs = 0.0;   // np.cumsum: sequential adds in index order
+        r[0] = 0;
+        for (int i = 0; i < K1; ++i) {
+            if (th[i] < 0 || th[i] >= S) return fail(BILDK_EINVAL, "profile %d: state %lld out of range [0,%d)", p, static_cast<long long>(th[i]), S);
+            q[i] = static_cast<uint8_t>(th[i]);
+            if (i + 1 < K1) {
+                cs += s[i];
+                const double f = std::floor(cs * Tm1);
+                if (!(f >= -1.0 && f <= 2147483000.0)) return fail(BILDK_EINVAL, "profile %d: interval lengths are not finite", p);
+                r[i + 1] = static_cast<int32_t>(f) + 1;
+            }
+        }
+    }
+    return bildk_logl_runs(t, P, K1, rs.data(), rt.data(), out);
 }
 
 extern "C" int bildk_logl_states(bildk_traj_t t, int P, const int32_t* states, double* out) {

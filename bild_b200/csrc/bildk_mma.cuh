@@ -63,7 +63,7 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
 // the comparatively rare stores) because the padded stride would cost a resident filter per SM.
 // Register budget: GT <= 3 must keep 28 warps per SM resident (BASELINE config 2 is 27.7 filters per SM).
 template <int GT, bool MX>
-__global__ void __launch_bounds__(GT <= 3 ? 448 : 256, GT <= 4 ? 2 : 1) k_mma(const __grid_constant__ MParams mp) {
+__global__ void __launch_bounds__(GT <= 3 ? 896 : 256, GT == 4 ? 2 : 1) k_mma(const __grid_constant__ MParams mp) {
     constexpr int GTC = GT + (MX ? 1 : 0);
     constexpr int TJM = MX ? GT : GT - 1;   // tile column that contains the mean columns
     constexpr bool SWZ = BILDK_MMA_SWZ && GT <= 4;

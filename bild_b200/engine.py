@@ -143,12 +143,20 @@ class RouseEngine:
         return out
 
     def logl_st(self, traj, ss, thetas):
-        """Batched ``logL(st2profile(s, theta), traj)`` (amis.py:717-739)."""
-        thetas = np.asarray(thetas)
-        if thetas.size and (thetas.min() < 0 or thetas.max() >= self.S):
-            raise ValueError(f"state index out of range [0, {self.S})")
-        starts, rstates = st_to_runs(ss, thetas, traj.T)
-        return self.logl_runs(traj, starts, rstates)
+        """Batched ``logL(st2profile(s, theta), traj)`` (amis.py:717-739); the (s, theta) -> run-length conversion
+        happens inside the library with numpy's exact arithmetic (`st_to_runs` is the Python statement of it)."""
+        ss = np.ascontiguousarray(ss, dtype=np.float64)
+        thetas = np.ascontiguousarray(thetas, dtype=np.int64)
+        if ss.ndim == 1:
+            ss, thetas = ss[None, :], thetas[None, :]
+        if ss.ndim != 2 or ss.shape != thetas.shape:
+            raise ValueError("ss and thetas must both have shape (P, K1)")
+        P, K1 = ss.shape
+        out = np.empty(P, dtype=np.float64)
+        if P:
+            _lib.check(_lib.load().bildk_logl_st(traj._h, P, K1, ptr(ss, c_double_p), ptr(thetas, ctypes.POINTER(ctypes.c_int64)),
+                                                 ptr(out, c_double_p)))
+        return out
 
     def logl_states(self, traj, states):
         """Per-frame state arrays (P, T) or (T,) -> (P,) log-likelihoods."""

@@ -79,6 +79,14 @@ int bildk_traj_destroy(bildk_traj_t traj);
 int bildk_logl_runs(bildk_traj_t traj, int P, int K1,
                     const int32_t *run_starts, const uint8_t *run_states, double *out);
 
+/*
+ * Same batch, straight from the AMIS parametrisation (ss (P,K1) float64 interval lengths on the simplex,
+ * thetas (P,K1) int64 states): the conversion FixedkSampler.st2profile does per profile (amis.py:685-693:
+ * switches = floor(cumsum(s)[:-1] * (T-1)) + 1) is done here with the same IEEE operations in the same
+ * order, so the discrete profiles are the very same ones.
+ */
+int bildk_logl_st(bildk_traj_t traj, int P, int K1, const double *ss, const int64_t *thetas, double *out);
+
 /* Same, from per-frame state arrays states[p*T + t] (the Loopingprofile format, util.py:15-23). */
 int bildk_logl_states(bildk_traj_t traj, int P, const int32_t *states, double *out);
 

@@ -231,3 +231,31 @@ def test_round_trip_properties_full_size():
     traj_p = eng.trajectory(x[:, [2, 0, 1]], [0.3] * d)
     e = eng.logl_st(traj_p, ss[:256], thetas[:256])
     assert rel_err(e, a[:256]) < 1e-12
+
+
+def test_in_library_profile_coding_matches_numpy():
+    """bildk_logl_st codes (s, theta) with numpy's arithmetic: same logL bits as coding with st_to_runs first."""
+    from bild_b200.engine import st_to_runs
+    rng = np.random.default_rng(9)
+    N, d, T, P = 20, 3, 101, 512
+    mod = oracle_model(N, d=d)
+    x, _ = synth_traj(mod, T, rng, 0.3)
+    ss, thetas = random_profiles(rng, P, T, 2, 10)
+    # adversarial rows: exact ties on frame boundaries, zero-length intervals, cumsum reaching 1.0 early
+    ss[0] = 0; ss[0, :4] = [0.25, 0.5, 0.25, 0.0]
+    ss[1] = 0; ss[1, :3] = [0.5, 0.0, 0.5]
+    ss[2] = 0; ss[2, :3] = [0.999, 0.0005, 0.0005]
+    ss[3] = 0; ss[3, :2] = [1.0, 0.0]
+    ss[4] = 0; ss[4, :11] = np.full(11, 1 / 11)
+    ss[5] = 0; ss[5, :3] = [1e-17, 1.0 - 1e-16, 1e-16]
+    eng = engine_for(mod)
+    traj = eng.trajectory(x, [0.3] * d)
+    a = eng.logl_st(traj, ss, thetas)
+    starts, rst = st_to_runs(ss, thetas, T)
+    b = eng.logl_runs(traj, starts, rst)
+    assert np.array_equal(a, b)
+    with pytest.raises(ValueError):
+        eng.logl_st(traj, ss, thetas + 2)                       # state out of range
+    bad = ss.copy(); bad[7, 0] = np.nan
+    with pytest.raises(ValueError):
+        eng.logl_st(traj, bad, thetas)
