@@ -147,9 +147,12 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.stop = index, [], threading.Event()
+        self.nvml_error = None
+        self._nv = None
         self.thread = threading.Thread(target=self._run, daemon=True)
 
-    def _run_nvml(self):
+    def _init_nvml(self):
+        """Synchronous (NVML start-up can take longer than the whole timed region)."""
         import pynvml as nv
         nv.nvmlInit()
         # CUDA_VISIBLE_DEVICES may renumber devices; resolve through the UUID of the CUDA device when possible
@@ -166,25 +169,34 @@ class ClockSampler:
                     break
         except Exception:
             pass
-        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        self._nv, self._h = nv, h
+        self._mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        self._sample_nvml()            # fails here, not in the thread, if a query is unsupported
+
+    def _sample_nvml(self):
+        nv, h = self._nv, self._h
         bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        self.rows.append([time.perf_counter(), str(sm), str(self._mx), str(pw)] +
+                         ["Active" if r & bits[n] else "Not Active" for n in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")])
+
+    def _run_nvml(self):
         while not self.stop.is_set():
-            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
-            pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
-            try:
-                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-            except Exception:
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-            self.rows.append([time.perf_counter(), str(sm), str(mx), str(pw)] + ["Active" if r & bits[n] else "Not Active" for n in names])
+            self._sample_nvml()
             self.stop.wait(0.004)
 
     def _run(self):
-        try:
-            self._run_nvml()
-            return
-        except Exception:
-            pass
+        if self._nv is not None:
+            try:
+                self._run_nvml()
+                return
+            except Exception as err:  # noqa: BLE001
+                self.nvml_error = repr(err)
         while not self.stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
@@ -196,6 +208,10 @@ class ClockSampler:
             self.stop.wait(0.02)
 
     def __enter__(self):
+        try:
+            self._init_nvml()
+        except Exception as err:  # noqa: BLE001
+            self._nv, self.nvml_error = None, repr(err)
         self.thread.start()
         return self
 
@@ -207,7 +223,7 @@ class ClockSampler:
         """Median SM clock / reasons over the samples taken inside [t0, t1] (all samples if none fell inside)."""
         rows = [r[1:] for r in self.rows if t0 is None or t0 <= r[0] <= t1] or [r[1:] for r in self.rows]
         if not rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "error": self.nvml_error}
         self_rows = rows
         sm = sorted(float(r[0]) for r in self_rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
