@@ -380,6 +380,7 @@ struct Plan {
     bool mma = false;      // tensor-core kernel, one warp per filter
     bool mmac = false;     // tensor-core kernel, one CTA per filter, one warp per tile column
     bool mmag = false;     // same, covariance in an L2 workspace (N > 112)
+    bool mma2 = false;     // tensor-core kernel, two warps per filter (GT 5..7)
     unsigned char colmap[40] = {0};
     int WPC = 0;
     bool tile;
@@ -463,10 +464,49 @@ static cudaError_t mmac_launch_for(int GT, bool MX, const CParams& cp, dim3 grid
     return cudaErrorInvalidValue;
 }
 
+template <int GT, bool MX>
+static cudaError_t mma2_launch(const M2Params& mp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_mma2<GT, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    k_mma2<GT, MX><<<grid, threads, smem, st>>>(mp);
+    return cudaGetLastError();
+}
+static cudaError_t mma2_launch_for(int GT, bool MX, const M2Params& mp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    switch (GT * 2 + (MX ? 1 : 0)) {
+        case 10: return mma2_launch<5, false>(mp, grid, threads, smem, st);  case 11: return mma2_launch<5, true>(mp, grid, threads, smem, st);
+        case 12: return mma2_launch<6, false>(mp, grid, threads, smem, st);  case 13: return mma2_launch<6, true>(mp, grid, threads, smem, st);
+        case 14: return mma2_launch<7, false>(mp, grid, threads, smem, st);  case 15: return mma2_launch<7, true>(mp, grid, threads, smem, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
 static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
     Plan pl{};
     {
         const char* force0 = getenv("BILDK_KERNEL");
+        if (m->mma_ok && m->GT >= 5 && m->GT <= 7 && !(force0 && (!strcmp(force0, "tile") || !strcmp(force0, "mma1") || !strcmp(force0, "mmag"))) &&
+            !env_int("BILDK_FORCE_GENERIC", 0) && m->GT < env_int("BILDK_MMAC_MIN_GT", 8)) {
+            const size_t matb = static_cast<size_t>(m->NPm) * m->LDBm * 8;
+            const size_t fbytes = (static_cast<size_t>(m->NPm) * m->LDCm + static_cast<size_t>(2) * m->NPm + 2) * 8;
+            const size_t cap = static_cast<size_t>(m->max_smem_optin);
+            int f = env_int("BILDK_FPC2", 6);
+            while (f > 1 && 16 + matb * m->S + fbytes * f > cap) --f;
+            if (16 + matb * m->S + fbytes * f <= cap) {
+                pl.mma2 = true;
+                pl.tile = false;
+                pl.FPC = f;
+                pl.WPC = f;
+                pl.threads = 64 * f;
+                pl.smem = 16 + matb * m->S + fbytes * f;
+                pl.fstride = static_cast<int>(fbytes / 8);
+                pl.bstride = static_cast<int>(matb / 8);
+                return pl;
+            }
+        }
         const bool no_tc = (force0 && !strcmp(force0, "tile")) || env_int("BILDK_FORCE_GENERIC", 0);
         if (m->mmag_ok && !no_tc && (!m->mmac_ok || (force0 && !strcmp(force0, "mmag")))) {
             const int GT = m->GT;
@@ -630,7 +670,10 @@ static cudaError_t launch_tile(const Plan& pl, const KParams& kp, dim3 grid, cud
 
 static std::string plan_string(const bildk_model* m, const Plan& pl) {
     char buf[256];
-    if (pl.mmag)
+    if (pl.mma2)
+        snprintf(buf, sizeof buf, "mma2 (DMMA m8n8k4) GT=%d %s two-warps-per-filter FPC=%d threads=%d smem=%zu", m->GT,
+                 m->mma_mx ? "mean-in-extra-tile" : "mean-in-padding", pl.FPC, pl.threads, pl.smem);
+    else if (pl.mmag)
         snprintf(buf, sizeof buf, "mmag (DMMA m8n8k4) GT=%d %s cta-per-filter warp-per-tile-column covariance-in-L2-workspace threads=%d", m->GT,
                  m->mma_mx ? "mean-in-extra-tile" : "mean-in-padding", pl.threads);
     else if (pl.mmac)
@@ -670,7 +713,7 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
         if (rc) return rc;
         d_part = m->part.p;
     }
-    if (pl.mma || pl.mmac || pl.mmag || pl.tile) {
+    if (pl.mma || pl.mma2 || pl.mmac || pl.mmag || pl.tile) {
         KParams kp{};
         kp.N = m->N; kp.D = m->D; kp.S = m->S; kp.G = m->G; kp.LD = m->LD; kp.NP = m->NP;
         kp.Bpad = m->dBpad; kp.Sigpad = m->dSigpad; kp.C0pad = m->dC0pad; kp.Gm = m->dG; kp.M0 = m->dM0; kp.w = m->dw;
@@ -683,7 +726,7 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
             for (int c = 0; c < DMAX; ++c) kp.cols[e][c] = t0->cols[e][c];
         }
         kp.P = P; kp.K1 = K1; kp.run_starts = d_starts; kp.run_states = d_states; kp.out = d_part;
-        if (pl.mma) pl.FPC = pl.WPC;   // CTA -> first filter maps use FPC
+        if (pl.mma) pl.FPC = pl.WPC;   // CTA -> first filter maps use FPC (mma2 sets FPC itself)
         if (pl.mmac || pl.mmag) pl.FPC = 1;
         kp.FPC = pl.FPC; kp.TPFS = pl.TPFS; kp.b_all = pl.b_all; kp.fstride = pl.fstride; kp.bstride = pl.bstride; kp.lane_ab = m->d_lane_ab;
         int n_cta = 0;
@@ -733,6 +776,15 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
             else if (ch >= 6 && m->GT <= 28) k_mmag<6, 896><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);
             else k_mmag<4, 1024><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);
             CU(cudaGetLastError());
+        } else if (pl.mma2) {
+            M2Params m2{};
+            MParams& mp = m2.m;
+            mp.k = kp;
+            mp.NPm = m->NPm; mp.LDB = m->LDBm; mp.LDC = m->LDCm; mp.MC0 = m->MC0; mp.NK = m->NK;
+            mp.Bm = m->dBm; mp.Sigm = m->dSigm; mp.C0m = m->dC0m;
+            mp.WPC = pl.FPC; mp.fstride_m = pl.fstride; mp.bstride_m = pl.bstride;
+            m2.FPC2 = pl.FPC;
+            CU(mma2_launch_for(m->GT, m->mma_mx, m2, grid, pl.threads, pl.smem, st));
         } else if (pl.mma || pl.mmac) {
             MParams mp{};
             mp.k = kp;

@@ -976,3 +976,332 @@ __global__ void __launch_bounds__(MAXT, 1) k_mmag(const __grid_constant__ GMPara
 }
 
 }  // namespace bildk
+
+namespace bildk {
+
+// ================================================================================================
+// k_mma2 - FP64 tensor cores, TWO WARPS PER FILTER (5 <= GT <= 7, i.e. 33 <= N <= 56).
+//
+// At these sizes shared memory holds only 4-6 filters per SM, so with one warp per filter (k_mma) every
+// scheduler has a single warp and the FP64 pipe idles through that warp's update / write-back phases
+// (ncu: DMMA pipe 70 % active, profiles/r01_ncu_n50_mma_v7_final.txt).  Here each filter is shared by a
+// warp pair, so every scheduler holds two warps of different filters that cover each other's gaps:
+//   role 0: P1 tile columns [0, CB)        P2 upper tiles of columns [0, CS)
+//   role 1: P1 tile columns [CB, GTC)      P2 upper tiles of columns [CS, GT), the mean, the log-likelihood
+// P1 is in place per column block, so the pair needs no barrier inside P1; three named barriers
+// (bar.sync id, 64) per frame: T complete / published columns visible / posterior written back.
+// CS balances the DMMA counts of the roles; roles alternate between filters so that each scheduler gets one
+// warp of either role.
+struct M2Params {
+    MParams m;
+    int FPC2;   // filters per CTA (2 warps each)
+};
+
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+template <int GT, bool MX>
+struct Mma2Cfg {
+    static constexpr int GTC = GT + (MX ? 1 : 0);
+    static constexpr int TJM = MX ? GT : GT - 1;
+    static constexpr int NPm = 8 * GT, LDB = NPm + 4, LDC = 8 * GTC + 4;
+    static constexpr int CB = (GT + 1) / 2;
+    static constexpr int NU = GT * (GT + 1) / 2;
+    static constexpr int pick_cs() {
+        int best = 1, bestd = 1 << 30;
+        for (int cs = 1; cs < GT; ++cs) {
+            const int r0 = GT * CB + cs * (cs + 1) / 2, r1 = GT * (GTC - CB) + NU - cs * (cs + 1) / 2;
+            const int d = r0 > r1 ? r0 - r1 : r1 - r0;
+            if (d < bestd) { bestd = d; best = cs; }
+        }
+        return best;
+    }
+    static constexpr int CS = pick_cs();
+};
+
+template <int GT, bool MX, int ROLE>
+__device__ __forceinline__ void mma2_run(const MParams& mp, double* Bsm, double* Cb, double* colb, double* lst,
+                                         int pidx, int tj, int e_sub, int barid, int lane) {
+    using C = Mma2Cfg<GT, MX>;
+    constexpr int GTC = C::GTC, TJM = C::TJM, NPm = C::NPm, LDB = C::LDB, LDC = C::LDC, CB = C::CB, CS = C::CS;
+    constexpr int MATB = NPm * LDB, MATG = NPm * NPm;
+    constexpr int C1LO = ROLE == 0 ? 0 : CB, C1HI = ROLE == 0 ? CB : GTC, NC1 = C1HI - C1LO;       // P1 columns
+    constexpr int C2LO = ROLE == 0 ? 0 : CS, C2HI = ROLE == 0 ? CS : GT;                            // P2 columns
+    constexpr int RMAX = C2HI;                                                                       // tile rows touched in P2
+    constexpr int NU2 = C2HI * (C2HI + 1) / 2 - C2LO * (C2LO + 1) / 2;
+    constexpr int NACC = (GT * NC1 > NU2) ? GT * NC1 : NU2;
+#define U2(ti, tjj) ((tjj) * ((tjj) + 1) / 2 - C2LO * (C2LO + 1) / 2 + (ti))
+    const KParams& p = mp.k;
+    const int g = lane >> 2, c4 = lane & 3;
+    const int N = p.N, D = p.D, NK = mp.NK;
+    const int T = p.T[tj];
+    const double* __restrict__ xg = p.x[tj];
+    const uint32_t* __restrict__ vbits = reinterpret_cast<const uint32_t*>(p.valid[tj] + (T + 3) / 4 * 4);
+    uint32_t vword = 0;
+    const int ncols = p.ncols[e_sub];
+    const double s2 = p.s2[e_sub];
+    const int j0 = p.wz_idx[0], j1 = p.wz_idx[1];
+    const double w0 = p.wz_val[0], w1 = p.wz_val[1];
+    const int q0 = 2 * c4 - (mp.MC0 - 8 * TJM), q1 = q0 + 1;
+    const bool qv0 = static_cast<unsigned>(q0) < static_cast<unsigned>(ncols);
+    const bool qv1 = static_cast<unsigned>(q1) < static_cast<unsigned>(ncols);
+    const int xc0 = p.cols[e_sub][qv0 ? q0 : 0], xc1 = p.cols[e_sub][qv1 ? q1 : 0];
+    double quad = 0.0;
+    if (ROLE == 1 && lane == 0) { lst[0] = 1.0; reinterpret_cast<int*>(lst + 1)[0] = 0; reinterpret_cast<int*>(lst + 1)[1] = 0; }
+
+    int r_cur = 0;
+    int s = p.run_states[static_cast<size_t>(pidx) * p.K1];
+    int next_sw = (p.K1 > 1) ? p.run_starts[static_cast<size_t>(pidx) * p.K1 + 1] : 0x7fffffff;
+
+    double acc[NACC][2];
+    double* const myC = Cb + g * LDC + 2 * c4;   // accumulator pair of tile (ti, tj): + 8 ti LDC + 8 tj
+
+    for (int t = 0; t < T; ++t) {
+        while (t >= next_sw) {
+            ++r_cur;
+            s = p.run_states[static_cast<size_t>(pidx) * p.K1 + r_cur];
+            next_sw = (r_cur + 1 < p.K1) ? p.run_starts[static_cast<size_t>(pidx) * p.K1 + r_cur + 1] : 0x7fffffff;
+        }
+        if ((t & 31) == 0) vword = __ldg(vbits + (t >> 5));
+        const bool is_valid = (vword >> (t & 31)) & 1u;
+        double x0 = 0.0, x1 = 0.0;
+        if (ROLE == 1 && is_valid) {
+            if (qv0) x0 = __ldg(xg + t * D + xc0);
+            if (qv1) x1 = __ldg(xg + t * D + xc1);
+        }
+        const double* Bs = Bsm + s * MATB;
+        const double* Gsrc = ((t == 0) ? mp.C0m : mp.Sigm) + static_cast<size_t>(MATG) * s + g * NPm + 2 * c4;
+
+        if (t > 0) {
+            // ---------------- P1: T[:, J] = B_s Caug[:, J] for this role's column block, in place
+#pragma unroll
+            for (int i = 0; i < GT * NC1; ++i) acc[i][0] = acc[i][1] = 0.0;
+            {
+                const double* Ap = Bs + g * LDB + c4;
+                const double* Bp = Cb + c4 * LDC + 8 * C1LO + g;
+#pragma unroll 1
+                for (int k0 = 0; k0 < NK; k0 += 4) {
+                    double a[GT], b[NC1];
+#pragma unroll
+                    for (int ti = 0; ti < GT; ++ti) a[ti] = Ap[8 * ti * LDB + k0];
+#pragma unroll
+                    for (int tc = 0; tc < NC1; ++tc) b[tc] = Bp[k0 * LDC + 8 * tc];
+#pragma unroll
+                    for (int ti = 0; ti < GT; ++ti)
+#pragma unroll
+                        for (int tc = 0; tc < NC1; ++tc) dmma884(acc[ti * NC1 + tc], a[ti], b[tc]);
+                }
+            }
+            __syncwarp();   // this warp is the only reader of its column block
+#pragma unroll
+            for (int ti = 0; ti < GT; ++ti)
+#pragma unroll
+                for (int tc = 0; tc < NC1; ++tc)
+                    *reinterpret_cast<double2*>(myC + 8 * ti * LDC + 8 * (C1LO + tc)) = make_double2(acc[ti * NC1 + tc][0], acc[ti * NC1 + tc][1]);
+        }
+        // upper tiles of this role's P2 columns start at Sig (t > 0) / hold C0 (t = 0)
+#pragma unroll
+        for (int tjj = C2LO; tjj < C2HI; ++tjj)
+#pragma unroll
+            for (int ti = 0; ti <= tjj; ++ti) {
+                const double2 v = __ldg(reinterpret_cast<const double2*>(Gsrc + 8 * ti * NPm + 8 * tjj));
+                acc[U2(ti, tjj)][0] = v.x;
+                acc[U2(ti, tjj)][1] = v.y;
+            }
+        if (t > 0) {
+            pair_sync(barid);   // T complete (both column blocks)
+            // ---------------- P2: C' = T B_s + Sig on this role's upper tiles
+            const double* Ap = Cb + g * LDC + c4;
+            const double* Bp = Bs + c4 * LDB + g;
+#pragma unroll 1
+            for (int k0 = 0; k0 < NK; k0 += 4) {
+                double a[RMAX], b[C2HI - C2LO];
+#pragma unroll
+                for (int ti = 0; ti < RMAX; ++ti) a[ti] = Ap[8 * ti * LDC + k0];
+#pragma unroll
+                for (int tjj = C2LO; tjj < C2HI; ++tjj) b[tjj - C2LO] = Bp[k0 * LDB + 8 * tjj];
+#pragma unroll
+                for (int tjj = C2LO; tjj < C2HI; ++tjj)
+#pragma unroll
+                    for (int ti = 0; ti <= tjj; ++ti) dmma884(acc[U2(ti, tjj)], a[ti], b[tjj - C2LO]);
+            }
+        }
+
+        auto mean_prior = [&](int ti, double& m0, double& m1) {
+            const int row = 8 * ti + g;
+            if (t == 0) {
+                m0 = (qv0 && row < N) ? __ldg(p.M0 + (s * N + row) * D + xc0) : 0.0;
+                m1 = (qv1 && row < N) ? __ldg(p.M0 + (s * N + row) * D + xc1) : 0.0;
+            } else {
+                const double2 v = *reinterpret_cast<const double2*>(myC + 8 * ti * LDC + 8 * TJM);
+                m0 = qv0 ? v.x : 0.0;
+                m1 = qv1 ? v.y : 0.0;
+                if (p.hasG && row < N) {
+                    if (qv0) m0 += __ldg(p.Gm + (s * N + row) * D + xc0);
+                    if (qv1) m1 += __ldg(p.Gm + (s * N + row) * D + xc1);
+                }
+            }
+        };
+
+        if (is_valid) {
+            // publish column j of C' (j = j0, j1): rows of tile rows ti <= tjz from the upper tile (ti, tjz) if this
+            // role owns column tjz; rows of owned columns tjj > tjz from row j of the upper tile (tjz, tjj)
+#pragma unroll
+            for (int z = 0; z < 2; ++z) {
+                const int jz = z ? j1 : j0;
+                const int tjz = jz >> 3, cj = jz & 7;
+#pragma unroll
+                for (int tjj = C2LO; tjj < C2HI; ++tjj) {
+                    if (tjj == tjz) {
+                        if (c4 == (cj >> 1)) {
+#pragma unroll
+                            for (int ti = 0; ti <= tjj; ++ti) colb[z * NPm + 8 * ti + g] = (cj & 1) ? acc[U2(ti, tjj)][1] : acc[U2(ti, tjj)][0];
+                        }
+                    } else if (tjj > tjz) {
+                        if (g == cj) {
+#pragma unroll
+                            for (int ti = 0; ti < tjj; ++ti)
+                                if (ti == tjz)
+                                    *reinterpret_cast<double2*>(colb + z * NPm + 8 * tjj + 2 * c4) = make_double2(acc[U2(ti, tjj)][0], acc[U2(ti, tjj)][1]);
+                        }
+                    }
+                }
+            }
+            if (ROLE == 1 && t == 0) {
+#pragma unroll
+                for (int ti = 0; ti < GT; ++ti) {
+                    double m0, m1;
+                    mean_prior(ti, m0, m1);
+                    if (qv0) Cb[(8 * ti + g) * LDC + mp.MC0 + q0] = m0;
+                    if (qv1) Cb[(8 * ti + g) * LDC + mp.MC0 + q1] = m1;
+                }
+            }
+        }
+        pair_sync(barid);   // T no longer needed by either warp; published columns (and M') visible
+        double kr[RMAX];
+        double xm0 = 0.0, xm1 = 0.0;
+        if (is_valid) {
+            const double cw_j0 = fma(w1, colb[NPm + j0], w0 * colb[j0]);
+            const double cw_j1 = fma(w1, colb[NPm + j1], w0 * colb[j1]);
+            const double S = fma(w1, cw_j1, fma(w0, cw_j0, s2));
+            const double Sinv = __drcp_rn(S);                               // pyx:63
+#pragma unroll
+            for (int ti = 0; ti < RMAX; ++ti) kr[ti] = fma(w1, colb[NPm + 8 * ti + g], w0 * colb[8 * ti + g]) * Sinv;   // pyx:66-67
+#pragma unroll
+            for (int tjj = C2LO; tjj < C2HI; ++tjj) {
+                const double2 u = *reinterpret_cast<const double2*>(colb + 8 * tjj + 2 * c4);
+                const double2 v = *reinterpret_cast<const double2*>(colb + NPm + 8 * tjj + 2 * c4);
+                const double c0v = fma(w1, v.x, w0 * u.x), c1v = fma(w1, v.y, w0 * u.y);
+#pragma unroll
+                for (int ti = 0; ti <= tjj; ++ti) {
+                    acc[U2(ti, tjj)][0] = fma(-kr[ti], c0v, acc[U2(ti, tjj)][0]);   // pyx:71-75
+                    acc[U2(ti, tjj)][1] = fma(-kr[ti], c1v, acc[U2(ti, tjj)][1]);
+                }
+            }
+            if (ROLE == 1) {
+                if (qv0) {
+                    double ma = Cb[j0 * LDC + mp.MC0 + q0], mb = Cb[j1 * LDC + mp.MC0 + q0];
+                    if (p.hasG && t > 0) { ma += __ldg(p.Gm + (s * N + j0) * D + xc0); mb += __ldg(p.Gm + (s * N + j1) * D + xc0); }
+                    xm0 = x0 - fma(w1, mb, w0 * ma);                       // pyx:79
+                    if (g == 0) quad = fma(xm0 * xm0, Sinv, quad);
+                }
+                if (qv1) {
+                    double ma = Cb[j0 * LDC + mp.MC0 + q1], mb = Cb[j1 * LDC + mp.MC0 + q1];
+                    if (p.hasG && t > 0) { ma += __ldg(p.Gm + (s * N + j0) * D + xc1); mb += __ldg(p.Gm + (s * N + j1) * D + xc1); }
+                    xm1 = x1 - fma(w1, mb, w0 * ma);
+                    if (g == 0) quad = fma(xm1 * xm1, Sinv, quad);
+                }
+                if (lane == 0) {
+                    double lmant = lst[0] * Sinv;
+                    const int ex = ((__double2hiint(lmant) >> 20) & 0x7ff) - 1023;
+                    lmant = __hiloint2double(__double2hiint(lmant) - (ex << 20), __double2loint(lmant));
+                    lst[0] = lmant;
+                    reinterpret_cast<int*>(lst + 1)[0] += ex;
+                    reinterpret_cast<int*>(lst + 1)[1] += 1;
+                }
+                __syncwarp();   // this warp has read w . M' before M+ lands in the buffer
+            }
+        }
+        // ---------------- C+ written back: this role's upper pairs, mirrored below the diagonal; role 1 merges the mean
+        if (t + 1 < T) {
+#pragma unroll
+            for (int tjj = C2LO; tjj < C2HI; ++tjj)
+#pragma unroll
+                for (int ti = 0; ti <= tjj; ++ti) {
+                    double v0 = acc[U2(ti, tjj)][0], v1 = acc[U2(ti, tjj)][1];
+                    if (ti < tjj) {
+                        const int r0 = 8 * tjj + 2 * c4;
+                        Cb[r0 * LDC + 8 * ti + g] = v0;
+                        Cb[(r0 + 1) * LDC + 8 * ti + g] = v1;
+                    }
+                    if (ROLE == 1 && tjj == GT - 1) {   // the last tile column sees every tile row: carry the mean here
+                        double m0, m1;
+                        mean_prior(ti, m0, m1);
+                        if (is_valid) {
+                            m0 = fma(kr[ti], xm0, m0);   // pyx:82-85
+                            m1 = fma(kr[ti], xm1, m1);
+                        }
+                        if (!MX) {
+                            if (qv0) v0 = m0;
+                            if (qv1) v1 = m1;
+                        } else {
+                            *reinterpret_cast<double2*>(myC + 8 * ti * LDC + 8 * TJM) = make_double2(m0, m1);
+                        }
+                    }
+                    *reinterpret_cast<double2*>(myC + 8 * ti * LDC + 8 * tjj) = make_double2(v0, v1);
+                }
+        }
+        pair_sync(barid);   // C+ complete
+    }
+
+    if (ROLE == 1) {
+        quad += __shfl_xor_sync(0xffffffffu, quad, 1);
+        quad += __shfl_xor_sync(0xffffffffu, quad, 2);
+        if (lane == 0) {
+            const int lexp = reinterpret_cast<const int*>(lst + 1)[0], nvalid = reinterpret_cast<const int*>(lst + 1)[1];
+            const double logdet = log(lst[0]) + lexp * 0.6931471805599453;
+            p.out[static_cast<size_t>(e_sub) * p.P + pidx] = -0.5 * (quad - ncols * logdet + static_cast<double>(nvalid) * ncols * LOG_2PI);
+        }
+    }
+#undef U2
+}
+
+template <int GT, bool MX>
+__global__ void __launch_bounds__(384, 1) k_mma2(const __grid_constant__ M2Params mp2) {
+    using C = Mma2Cfg<GT, MX>;
+    constexpr int MATB = C::NPm * C::LDB;
+    const MParams& mp = mp2.m;
+    const KParams& p = mp.k;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
+    double* Bsm = reinterpret_cast<double*>(smem_raw + 16);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int fl = wid >> 1;                          // filter within the CTA
+    const int role = (wid & 1) ^ ((fl >> 1) & 1);     // roles alternate so that every scheduler holds one warp of each
+    const int tj = p.cta_traj ? p.cta_traj[blockIdx.x] : 0;
+    const int first = p.cta_first ? p.cta_first[blockIdx.x] : blockIdx.x * mp2.FPC2;
+    const int pend = p.traj_first[tj + 1];
+    const int pidx = first + fl;
+    const bool alive = (fl < mp2.FPC2) && (pidx < pend);
+
+    if (tid == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(mbar, static_cast<uint32_t>(MATB * p.S * sizeof(double)));
+        for (int st = 0; st < p.S; ++st) {
+            constexpr uint32_t CH = 32768;
+            constexpr uint32_t bytes = MATB * sizeof(double);
+            for (uint32_t off = 0; off < bytes; off += CH)
+                tma_load_1d(reinterpret_cast<char*>(Bsm + st * MATB) + off, reinterpret_cast<const char*>(mp.Bm + static_cast<size_t>(MATB) * st) + off,
+                            bytes - off < CH ? bytes - off : CH, mbar);
+        }
+    }
+    if (!alive) return;   // both warps of a pair leave together; the named barriers below are per pair
+    double* Cb = Bsm + MATB * p.S + fl * mp.fstride_m;
+    double* colb = Cb + C::NPm * C::LDC;
+    double* lst = colb + 2 * C::NPm;
+    mbar_wait(mbar, 0);
+    if (role == 0) mma2_run<GT, MX, 0>(mp, Bsm, Cb, colb, lst, pidx, tj, blockIdx.y, 1 + fl, lane);
+    else mma2_run<GT, MX, 1>(mp, Bsm, Cb, colb, lst, pidx, tj, blockIdx.y, 1 + fl, lane);
+}
+
+}  // namespace bildk
