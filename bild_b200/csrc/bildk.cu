@@ -6,6 +6,7 @@
 #include "../../include/bild_b200.h"
 #include "bildk_kernels.cuh"
 #include "bildk_mma.cuh"
+#include "bildk_mmar.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -84,6 +85,10 @@ struct bildk_model {
     bool mma_ok = false, mma_mx = false, mmac_ok = false, mmag_ok = false;
     int GT = 0, NPm = 0, LDBm = 0, LDCm = 0, MC0 = 0, NK = 0;
     double *dBm = nullptr, *dSigm = nullptr, *dC0m = nullptr;
+    // register-chained tensor-core kernel (k_mmar): GT <= 4 and N mod 8 in 1..4
+    bool mmar_ok = false;
+    int r_last = 0, LDr = 0, fstride_r = 0;
+    double* dBr = nullptr;
     // per-model scratch for the host-pointer entry points
     DevBuf<int32_t> starts;
     DevBuf<uint8_t> states;
@@ -182,7 +187,7 @@ extern "C" int bildk_device_count(void) {
 extern "C" int bildk_model_destroy(bildk_model_t m) {
     if (!m) return BILDK_OK;
     cudaSetDevice(m->device);
-    for (double* p : {m->dB, m->dSig, m->dC0, m->dBpad, m->dSigpad, m->dC0pad, m->dG, m->dM0, m->dw, m->dBm, m->dSigm, m->dC0m})
+    for (double* p : {m->dB, m->dSig, m->dC0, m->dBpad, m->dSigpad, m->dC0pad, m->dG, m->dM0, m->dw, m->dBm, m->dSigm, m->dC0m, m->dBr})
         if (p) cudaFree(p);
     if (m->d_lane_ab) cudaFree(m->d_lane_ab);
     m->starts.release(); m->states.release(); m->out.release(); m->part.release(); m->work.release();
@@ -304,6 +309,23 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
             if (GT > 7) m->mma_ok = false;
             else
             m->mma_ok = 16 + matb * 8 * S + fbytes <= static_cast<size_t>(m->max_smem_optin);
+            // register-chained kernel: the last tile-row block must have room for M^T (and a zero row)
+            const int rl = N - 8 * (GT - 1);
+            if (GT <= 4 && rl >= 1 && rl <= 4 && d <= 4 && m->wz_idx[0] == 0 && m->wz_idx[1] == N - 1 && N >= 2) {   // end-to-end measurement only
+                const int R = 8 * GT;
+                const int LDr = (R % 16 == 8) ? R : R + 8;
+                const size_t matr = static_cast<size_t>(R) * LDr;
+                std::vector<double> pad(S * matr, 0.0);
+                for (int s = 0; s < S; ++s)
+                    for (int i = 0; i < N; ++i)
+                        for (int j = 0; j < N; ++j)
+                            pad[s * matr + static_cast<size_t>(i) * LDr + (j ^ (4 * ((i >> 1) & 1)))] =
+                                B[s * NN + static_cast<size_t>(std::max(i, j)) * N + std::min(i, j)];
+                if ((rc = upload(&m->dBr, pad.data(), S * matr))) { bildk_model_destroy(m); return rc; }
+                m->r_last = rl; m->LDr = LDr;
+                m->fstride_r = static_cast<int>(matr) + 2 * R + 8;
+                m->mmar_ok = 16 + matr * 8 * S + static_cast<size_t>(m->fstride_r) * 8 * 4 <= static_cast<size_t>(m->max_smem_optin);
+            }
         }
     }
     *out = m;
@@ -381,6 +403,8 @@ struct Plan {
     bool mmac = false;     // tensor-core kernel, one CTA per filter, one warp per tile column
     bool mmag = false;     // same, covariance in an L2 workspace (N > 112)
     bool mma2 = false;     // tensor-core kernel, two warps per filter (GT 5..7)
+    bool mmar = false;     // tensor-core kernel, one warp per filter, T chained through registers (GT <= 4)
+    int nb = 0;            // ... its variant: resident 4-warp CTAs per SM it is compiled for
     unsigned char colmap[40] = {0};
     int WPC = 0;
     bool tile;
@@ -428,6 +452,74 @@ static cudaError_t mma_launch_for(int GT, bool MX, const MParams& mp, dim3 grid,
     MMA_DISPATCH(GT, MX, CALL_LAUNCH)
 #undef CALL_LAUNCH
     return cudaErrorInvalidValue;
+}
+
+template <int GT, int NB>
+static cudaError_t mmar_launch(const RParams& rp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_mmar<GT, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    k_mmar<GT, NB><<<grid, threads, smem, st>>>(rp);
+    return cudaGetLastError();
+}
+// compiled register budgets (resident 4-warp CTAs per SM = warps per scheduler)
+#define MMAR_VARIANTS(X) X(1, 4) X(1, 7) X(2, 4) X(2, 5) X(2, 7) X(3, 4) X(3, 5) X(3, 7) X(4, 3) X(4, 4) X(4, 5)
+static bool mmar_has(int GT, int NB) {
+#define X(G_, N_) if (GT == G_ && NB == N_) return true;
+    MMAR_VARIANTS(X)
+#undef X
+    return false;
+}
+static cudaError_t mmar_launch_for(int GT, int NB, const RParams& rp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+#define X(G_, N_) if (GT == G_ && NB == N_) return mmar_launch<G_, N_>(rp, grid, threads, smem, st);
+    MMAR_VARIANTS(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+// Rows of the last tile-row block that carry M^T (and one all-zero row), placed so that the B-fragment loads of the
+// permuted last tile column are bank-conflict free: a 128-bit load is served per quarter warp (lanes g = 2i, 2i+1:
+// the two rows must differ in parity), a 64-bit load per half warp (lanes g = 4h..4h+3: rows distinct mod 4).
+static void mmar_tables(int GT, int r, int ncols, unsigned char* lastrow, unsigned char* mrow) {
+    const int base = 8 * (GT - 1);
+    std::vector<int> avail;
+    for (int i = r; i < 8; ++i) avail.push_back(base + i);
+    const bool need_zero = (r < 4) || (ncols < 4);
+    const int want = ncols + (need_zero ? 1 : 0);
+    std::vector<int> idx(avail.size());
+    for (size_t i = 0; i < idx.size(); ++i) idx[i] = static_cast<int>(i);
+    int best = 1 << 30;
+    std::vector<int> pick(want, base + r);
+    std::sort(idx.begin(), idx.end());
+    do {   // permutations of the spare rows; the first `want` entries are (m_0 .. m_{ncols-1}, zero)
+        int rows[8];
+        const int Z = need_zero ? avail[idx[ncols]] : -1;
+        for (int i = 0; i < 4; ++i) {
+            rows[2 * i] = i < r ? base + i : Z;
+            rows[2 * i + 1] = i < ncols ? avail[idx[i]] : Z;
+        }
+        int cost = 0;
+        for (int i = 0; i < 4; ++i)
+            if (rows[2 * i] != rows[2 * i + 1] && ((rows[2 * i] - rows[2 * i + 1]) & 1) == 0) cost += 4;
+        for (int h = 0; h < 2; ++h)
+            for (int a = 0; a < 4; ++a)
+                for (int b = a + 1; b < 4; ++b)
+                    if (rows[4 * h + a] != rows[4 * h + b] && ((rows[4 * h + a] - rows[4 * h + b]) & 3) == 0) cost += 1;
+        if (cost < best) {
+            best = cost;
+            for (int i = 0; i < want; ++i) pick[i] = avail[idx[i]];
+        }
+        std::reverse(idx.begin() + std::min<size_t>(want, idx.size()), idx.end());   // skip permutations of the unused tail
+    } while (std::next_permutation(idx.begin(), idx.end()));
+    const int Z = need_zero ? pick[ncols] : base;
+    for (int i = 0; i < 4; ++i) {
+        lastrow[2 * i] = static_cast<unsigned char>(i < r ? base + i : Z);
+        lastrow[2 * i + 1] = static_cast<unsigned char>(i < ncols ? pick[i] : Z);
+        mrow[i] = static_cast<unsigned char>(i < ncols ? pick[i] : Z);
+    }
 }
 
 template <int GT, bool MX>
@@ -550,6 +642,27 @@ static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
                 load[best] += GT + c + 1 + ((c == 0 && m->mma_mx) ? GT : 0);
                 ++used[best];
             }
+            return pl;
+        }
+    }
+    {
+        const char* force = getenv("BILDK_KERNEL");
+        const bool want_mmar = m->mmar_ok && !(force && strcmp(force, "mmar")) && !env_int("BILDK_FORCE_GENERIC", 0) && env_int("BILDK_MMAR", 1);
+        if (want_mmar) {
+            // measured on B200 (profiles/r01_mmar_variants.txt): 4 warps per scheduler with ~128 registers beat 7 warps
+            // with 72 (spills) for every GT; GT = 4 needs 3 per scheduler to stay spill-free
+            int nb = env_int("BILDK_MMAR_NB", m->GT <= 3 ? 4 : 3);
+            if (!mmar_has(m->GT, nb)) nb = m->GT <= 3 ? 4 : 3;
+            const size_t matb = static_cast<size_t>(8 * m->GT) * m->LDr * 8;
+            const size_t fbytes = static_cast<size_t>(m->fstride_r) * 8;
+            pl.mmar = true;
+            pl.nb = nb;
+            pl.WPC = 4;
+            pl.threads = 128;
+            pl.smem = 16 + matb * m->S + fbytes * 4;
+            pl.fstride = m->fstride_r;
+            pl.bstride = static_cast<int>(matb / 8);
+            pl.tile = false;
             return pl;
         }
     }
@@ -679,6 +792,9 @@ static std::string plan_string(const bildk_model* m, const Plan& pl) {
     else if (pl.mmac)
         snprintf(buf, sizeof buf, "mmac (DMMA m8n8k4) GT=%d %s cta-per-filter warp-per-tile-column B=%s threads=%d smem=%zu", m->GT,
                  m->mma_mx ? "mean-in-extra-tile" : "mean-in-padding", pl.b_all ? "all" : "one", pl.threads, pl.smem);
+    else if (pl.mmar)
+        snprintf(buf, sizeof buf, "mmar (DMMA m8n8k4) GT=%d register-chained warp-per-filter WPC=%d CTAs/SM=%d threads=%d smem=%zu", m->GT,
+                 pl.WPC, pl.nb, pl.threads, pl.smem);
     else if (pl.mma)
         snprintf(buf, sizeof buf, "mma (DMMA m8n8k4) GT=%d %s warp-per-filter WPC=%d threads=%d smem=%zu", m->GT,
                  m->mma_mx ? "mean-in-extra-tile" : "mean-in-padding", pl.WPC, pl.threads, pl.smem);
@@ -713,7 +829,7 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
         if (rc) return rc;
         d_part = m->part.p;
     }
-    if (pl.mma || pl.mma2 || pl.mmac || pl.mmag || pl.tile) {
+    if (pl.mma || pl.mmar || pl.mma2 || pl.mmac || pl.mmag || pl.tile) {
         KParams kp{};
         kp.N = m->N; kp.D = m->D; kp.S = m->S; kp.G = m->G; kp.LD = m->LD; kp.NP = m->NP;
         kp.Bpad = m->dBpad; kp.Sigpad = m->dSigpad; kp.C0pad = m->dC0pad; kp.Gm = m->dG; kp.M0 = m->dM0; kp.w = m->dw;
@@ -726,7 +842,7 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
             for (int c = 0; c < DMAX; ++c) kp.cols[e][c] = t0->cols[e][c];
         }
         kp.P = P; kp.K1 = K1; kp.run_starts = d_starts; kp.run_states = d_states; kp.out = d_part;
-        if (pl.mma) pl.FPC = pl.WPC;   // CTA -> first filter maps use FPC (mma2 sets FPC itself)
+        if (pl.mma || pl.mmar) pl.FPC = pl.WPC;   // CTA -> first filter maps use FPC (mma2 sets FPC itself)
         if (pl.mmac || pl.mmag) pl.FPC = 1;
         kp.FPC = pl.FPC; kp.TPFS = pl.TPFS; kp.b_all = pl.b_all; kp.fstride = pl.fstride; kp.bstride = pl.bstride; kp.lane_ab = m->d_lane_ab;
         int n_cta = 0;
@@ -776,6 +892,13 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
             else if (ch >= 6 && m->GT <= 28) k_mmag<6, 896><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);
             else k_mmag<4, 1024><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);
             CU(cudaGetLastError());
+        } else if (pl.mmar) {
+            RParams rp{};
+            rp.k = kp;
+            rp.Br = m->dBr; rp.Sigm = m->dSigm; rp.C0m = m->dC0m;
+            rp.WPC = pl.WPC; rp.fstride = pl.fstride; rp.r = m->r_last;
+            for (int e = 0; e < dstar; ++e) mmar_tables(m->GT, m->r_last, t0->ncols[e], rp.lastrow[e], rp.mrow[e]);
+            CU(mmar_launch_for(m->GT, pl.nb, rp, grid, pl.threads, pl.smem, st));
         } else if (pl.mma2) {
             M2Params m2{};
             MParams& mp = m2.m;

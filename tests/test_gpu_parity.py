@@ -93,6 +93,47 @@ def test_kernel_variants_agree(kernel, N, monkeypatch):
     assert rel_err(got, want) < TOL
 
 
+MMAR_CASES = [
+    # N, d, noise, loops                      register-chained kernel: GT <= 4, N mod 8 in 1..4
+    (3, 3, 0.5, (None, [(0, -1)])),           # GT=1, r=3
+    (4, 4, 0.4, (None, [(0, -1)])),           # GT=1, r=4, d=4: every spare row carries a mean column, no zero row
+    (10, 3, 0.2, (None, [(0, -1)])),          # GT=2, r=2 (sweep size N=10)
+    (12, 2, [0.1, 0.4], (None, [(0, -1)])),   # GT=2, r=4, d*=2
+    (17, 1, 0.3, (None, [(0, -1)])),          # GT=3, r=1, d=1
+    (20, 3, 0.3, (None, [(0, -1)], [(2, 9), (5, 15, 0.5)])),   # GT=3, r=4 (configs[1]), 3 states
+    (20, 3, [0.2, 0.2, 0.5], (None, [(0, -1)])),               # ... anisotropic error: sub-filters with 2 and 1 columns
+    (25, 3, 0.3, (None, [(0, -1)])),          # GT=4, r=1 (sweep size N=25)
+    (28, 3, 0.3, (None, [(0, -1)])),          # GT=4, r=4
+]
+
+
+@pytest.mark.parametrize("nb", [0, 1], ids=["default-budget", "smallest-budget"])
+@pytest.mark.parametrize("N,d,noise,loops", MMAR_CASES)
+def test_register_chained_kernel(N, d, noise, loops, nb, monkeypatch):
+    """k_mmar (T chained through registers) in two register budgets vs the C oracle and vs k_mma."""
+    rng = np.random.default_rng(77 + N)
+    mod = oracle_model(N, d=d, loops=loops)
+    T, P = 70, 37
+    x, _ = synth_traj(mod, T, rng, noise, p_nan=0.15)
+    x[0] = np.nan if N % 2 else x[0]                     # odd N: first frame missing
+    ss, thetas = random_profiles(rng, P, T, len(loops), 6)
+    err = np.broadcast_to(np.asarray(noise, dtype=float), (d,))
+    s2, Cind = ko.noise_to_s2_cind(err)
+    states = np.array([ko.st2states(s, th, T) for s, th in zip(ss, thetas)])
+    want = ko.logl_c(*(mod[k] for k in MODEL_KEYS), x, s2, Cind, states)
+    eng = engine_for(mod)
+    traj = eng.trajectory(x, err)
+    if nb:   # most resident CTAs per SM = fewest registers (fragments re-read per tile row, some spills)
+        monkeypatch.setenv("BILDK_MMAR_NB", "7" if N <= 24 else "5")
+    assert traj.describe_plan(P).split()[0] == "mmar"
+    assert f"CTAs/SM={(7 if N <= 24 else 5) if nb else (4 if N <= 24 else 3)}" in traj.describe_plan(P)
+    got = eng.logl_st(traj, ss, thetas)
+    assert rel_err(got, want) < TOL
+    monkeypatch.setenv("BILDK_KERNEL", "mma1")           # the shared-memory round-trip kernel on the same inputs
+    assert traj.describe_plan(P).split()[0] != "mmar"
+    assert rel_err(eng.logl_st(traj, ss, thetas), got) < 1e-12
+
+
 @pytest.mark.parametrize("N,nz", [
     (20, {3: -1.0, 14: 1.0}),            # two interior monomers (k_mma)
     (20, {7: 0.5, 8: -2.0}),             # neighbours in one tile, unequal weights
@@ -139,10 +180,11 @@ def test_dense_measurement_vector():
     assert rel_err(got, want) < TOL
 
 
-def test_external_force_mean_offset():
+@pytest.mark.parametrize("N", [15, 19])   # 15: k_mma; 19: k_mmar (G added to the chained mean)
+def test_external_force_mean_offset(N):
     """G != 0 (pyx:209): constant force on the chain ends."""
     rng = np.random.default_rng(6)
-    N, d, T, P = 15, 2, 40, 10
+    d, T, P = 2, 40, 10
     F = np.zeros((N, d))
     F[0, 0], F[-1, 0] = -0.7, 0.7
     mod = oracle_model(N, d=d, F=F)
