@@ -68,6 +68,15 @@ class Dirichlet:
         out = np.where(bad, np.inf, out)
         return out[0] if single else out
 
+    def logpdf_multi(self, A, ss):
+        """``(n_par, N)`` log-densities of the samples ``ss (N, k+1)`` under every row of ``A (n_par, k+1)``."""
+        A = np.asarray(A, dtype=float)
+        ss = np.asarray(ss, dtype=float)
+        if np.any(ss <= 0) or np.any(ss > 1) or np.any(np.abs(np.sum(ss, axis=1) - 1.0) > 1e-9):
+            return np.array([self.logpdf(a, ss) for a in A])        # boundary conventions live in `logpdf`
+        lognorm = gammaln(np.sum(A, axis=1)) - np.sum(gammaln(A), axis=1)
+        return lognorm[:, None] + (A - 1.0) @ np.log(ss).T
+
     def estimate(self, ss, log_weights):
         """Weighted method of moments (amis.py:137-151): ``alpha = A m`` with ``A = mean(m (1-m) / v) - 1``."""
         with np.errstate(under="ignore"):
@@ -119,6 +128,19 @@ class CFC:
         # normaliser of slot i given the previous state: LSE over the states reachable from it
         reach = _lse(logp.T[None, 1:, :], axis=-1, mask=self.transitions[thetas[:, :-1]])   # (N, k)
         return np.sum(picked, axis=1) - np.sum(reach, axis=1) - _lse(logp[:, 0])
+
+    def logpmf_multi(self, logps, thetas):
+        """``(n_par, N)`` log-probabilities of the traces ``thetas (N, k+1)`` under every ``logps[j] (n, k+1)``."""
+        L = np.asarray(logps, dtype=float)                                   # (n_par, n, k+1)
+        thetas = np.asarray(thetas)
+        slots = np.arange(L.shape[2])
+        picked = L[:, thetas, slots[None, :]]                                # (n_par, N, k+1)
+        out = np.sum(picked, axis=2) - _lse(L[:, :, 0], axis=1)[:, None]
+        if L.shape[2] > 1:
+            mask = self.transitions[thetas[:, :-1]]                          # (N, k, n) states reachable from the previous one
+            reach = _lse(L.transpose(0, 2, 1)[:, None, 1:, :], axis=-1, mask=mask[None])   # (n_par, N, k)
+            out = out - np.sum(reach, axis=2)
+        return out
 
     def estimate(self, thetas, log_weights):
         """Method of marginals (amis.py:283-305): weighted state marginals per slot -> weight parameters."""
@@ -255,6 +277,14 @@ class FixedkSampler:
     def log_proposal(self, parameters, ss, thetas):
         return self.dirichlet.logpdf(parameters[0], ss) + self.cfc.logpmf(parameters[1], thetas)
 
+    def log_proposal_multi(self, parameters, ss, thetas):
+        """``(len(parameters), N)``: the samples under every proposal of the list, in one vectorised pass (the
+        reference evaluates past proposals one by one, amis.py:836-839 - O(steps) scipy constructions per step)."""
+        if len(parameters) == 0:
+            return np.empty((0, len(ss)))
+        return (self.dirichlet.logpdf_multi(np.array([par[0] for par in parameters]), ss)
+                + self.cfc.logpmf_multi(np.array([par[1] for par in parameters]), thetas))
+
     def logL(self, ss, thetas):
         """Model likelihood of a batch of samples -> (N,) float64.  One GPU launch when the model can."""
         if hasattr(self.model, "logL_st_batch"):
@@ -320,9 +350,9 @@ class FixedkSampler:
         # new sample: RNG order Dirichlet -> CFC, as the reference
         new = {"ss": self.dirichlet.sample(cur[0], self.N), "thetas": self.cfc.sample(cur[1], self.N)}
         new["logLs"] = self.logL(new["ss"], new["thetas"])
-        new["cur_log_proposal"] = self.log_proposal(cur, new["ss"], new["thetas"])
-        past = [self.log_proposal(par, new["ss"], new["thetas"]) for par in self.parameters[:-1]]
-        new["logδs"] = _lse(np.array(past + [new["cur_log_proposal"]]), axis=0)
+        all_lp = self.log_proposal_multi(self.parameters, new["ss"], new["thetas"])   # past proposals and the current one
+        new["cur_log_proposal"] = all_lp[-1]
+        new["logδs"] = _lse(all_lp, axis=0)
         self.samples.append(new)
 
         # deterministic-mixture weights of the full ensemble
@@ -368,7 +398,7 @@ class FixedkSampler:
             with np.errstate(under="ignore"):
                 w = np.exp(log_w - top)
             ev = np.mean(w)
-            sem = stats.sem(w)
+            sem = np.std(w, ddof=1) / np.sqrt(n) if n > 1 else np.nan
             with np.errstate(under="ignore", invalid="ignore"):
                 s3 = np.nansum(w * (ens["logLs"] - ens["cur_log_proposal"]))
         logev = np.log(ev) + top + self.logprior
