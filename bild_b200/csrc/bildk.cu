@@ -1137,24 +1137,32 @@ extern "C" int bildk_amis_weights(int n, const double* logL, const double* logde
     if (ndev == 0) return fail(BILDK_ECUDA, "no CUDA device available (this library has no CPU fallback)");
     if (device < 0 || device >= ndev) return fail(BILDK_EINVAL, "device %d out of range", device);
     CU(cudaSetDevice(device));
-    double* d = nullptr;
+    // one grow-only scratch buffer per device and thread, one packed copy in, one out (a cudaMalloc / cudaFree pair
+    // and five small copies per call used to cost more than the reduction itself: the AMIS loop calls this every step)
+    struct Scratch { DevBuf<double> dev; std::vector<double> host; };
+    static thread_local std::vector<Scratch> scratch;
+    if (scratch.size() < static_cast<size_t>(ndev)) scratch.resize(ndev);
+    Scratch& sc = scratch[device];
     const size_t nn = static_cast<size_t>(n);
-    CU(cudaMalloc(&d, (4 * nn + 4) * sizeof(double)));
-    int rc = BILDK_OK;
+    int rc = sc.dev.reserve(4 * nn + 4);
+    if (rc) return rc;
+    if (sc.host.size() < 3 * nn + 4) sc.host.resize(2 * (3 * nn + 4));
+    double* d = sc.dev.p;
+    std::memcpy(sc.host.data(), logL, nn * 8);
+    std::memcpy(sc.host.data() + nn, logdelta, nn * 8);
+    std::memcpy(sc.host.data() + 2 * nn, curlp, nn * 8);
     cudaError_t e;
-    if ((e = cudaMemcpy(d, logL, nn * 8, cudaMemcpyHostToDevice)) != cudaSuccess ||
-        (e = cudaMemcpy(d + nn, logdelta, nn * 8, cudaMemcpyHostToDevice)) != cudaSuccess ||
-        (e = cudaMemcpy(d + 2 * nn, curlp, nn * 8, cudaMemcpyHostToDevice)) != cudaSuccess) {
-        rc = fail(BILDK_ECUDA, "copy failed: %s", cudaGetErrorString(e));
-    } else {
-        k_amis_weights<<<1, 1024>>>(n, d, d + nn, d + 2 * nn, log_nsteps, log_w ? d + 3 * nn : nullptr, d + 4 * nn);
-        g_launches++;
-        if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaMemcpy(stats, d + 4 * nn, 4 * 8, cudaMemcpyDeviceToHost)) != cudaSuccess ||
-            (log_w && (e = cudaMemcpy(log_w, d + 3 * nn, nn * 8, cudaMemcpyDeviceToHost)) != cudaSuccess))
-            rc = fail(BILDK_ECUDA, "weights kernel failed: %s", cudaGetErrorString(e));
-    }
-    cudaFree(d);
-    return rc;
+    if ((e = cudaMemcpy(d, sc.host.data(), 3 * nn * 8, cudaMemcpyHostToDevice)) != cudaSuccess)
+        return fail(BILDK_ECUDA, "copy failed: %s", cudaGetErrorString(e));
+    k_amis_weights<<<1, 1024>>>(n, d, d + nn, d + 2 * nn, log_nsteps, log_w ? d + 3 * nn : nullptr, d + 4 * nn);
+    g_launches++;
+    // log_w (n) and the four statistics are contiguous on the device: [3n, 4n + 4)
+    const size_t off = log_w ? 3 * nn : 4 * nn, cnt = log_w ? nn + 4 : 4;
+    if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaMemcpy(sc.host.data(), d + off, cnt * 8, cudaMemcpyDeviceToHost)) != cudaSuccess)
+        return fail(BILDK_ECUDA, "weights kernel failed: %s", cudaGetErrorString(e));
+    if (log_w) std::memcpy(log_w, sc.host.data(), nn * 8);
+    std::memcpy(stats, sc.host.data() + (log_w ? nn : 0), 4 * 8);
+    return BILDK_OK;
 }
 
 extern "C" int bildk_amis_weights_device(int n, const double* d_logL, const double* d_logdelta, const double* d_curlp,

@@ -17,6 +17,7 @@ the sequential runs, independent of how many trajectories share a launch or a GP
 Multi-GPU: trajectories are partitioned across ranks (`rank`, `world`); no communication during sampling.
 """
 import threading
+import time
 
 import numpy as np
 
@@ -93,7 +94,8 @@ def sample_many(trajs, model, seeds=None, rank=0, world=1, max_active=None, **sa
     mine = list(range(rank, len(trajs), world))
     sched = threading.Semaphore(0)
     outer_rng = np.random.get_state()
-    stats = {"launches": 0, "profiles": 0, "frame_steps": 0, "rounds": 0}
+    stats = {"launches": 0, "profiles": 0, "frame_steps": 0, "rounds": 0,
+             "t_host_lanes": 0.0, "t_pack": 0.0, "t_gpu": 0.0}      # wall seconds: AMIS host code / run-length packing / fused launches
 
     def body(lane):
         lane.go.acquire()
@@ -115,10 +117,12 @@ def sample_many(trajs, model, seeds=None, rank=0, world=1, max_active=None, **sa
             threading.Thread(target=body, args=(lane,), daemon=True).start()
             active.append(lane)
         # let every active lane run (one at a time, fixed order) until it asks for likelihoods or finishes
+        tic = time.perf_counter()
         for lane in active:
             if lane.request is None and not lane.done:
                 lane.go.release()
                 sched.acquire()
+        stats["t_host_lanes"] += time.perf_counter() - tic
         for lane in [ln for ln in active if ln.done]:
             if lane.error is not None:
                 raise lane.error
@@ -130,6 +134,7 @@ def sample_many(trajs, model, seeds=None, rank=0, world=1, max_active=None, **sa
         # ---- fuse: one launch for all waiting trajectories; profiles with fewer runs are padded with
         #      empty runs (start = T), which vanish exactly like the empty slices of st2profile
         stats["rounds"] += 1
+        tic = time.perf_counter()
         K1 = max(ln.request[0].shape[1] for ln in waiting)
         starts, states, offsets = [], [], [0]
         for ln in waiting:
@@ -145,7 +150,11 @@ def sample_many(trajs, model, seeds=None, rank=0, world=1, max_active=None, **sa
             states.append(b)
             offsets.append(offsets[-1] + len(a))
             stats["frame_steps"] += len(a) * (len(ln.traj) - 1)
-        out = model.logL_runs_multi([ln.traj for ln in waiting], offsets, np.concatenate(starts), np.concatenate(states))
+        all_starts, all_states = np.concatenate(starts), np.concatenate(states)
+        stats["t_pack"] += time.perf_counter() - tic
+        tic = time.perf_counter()
+        out = model.logL_runs_multi([ln.traj for ln in waiting], offsets, all_starts, all_states)
+        stats["t_gpu"] += time.perf_counter() - tic
         stats["launches"] += 1
         stats["profiles"] += offsets[-1]
         for ln, lo, hi in zip(waiting, offsets[:-1], offsets[1:]):

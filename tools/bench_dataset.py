@@ -76,6 +76,7 @@ if rank == 0:
                                     "parallelism": f"trajectories partitioned over {world} rank(s), fused likelihood batches"},
         "frame_steps": summary[1], "frame_steps_per_s": summary[1] / summary[0], "profiles": summary[2],
         "fused_rounds_max": summary[3], "launches_rank0": int(launches), "trajectories": int(summary[4]),
-        "truth_recovered_exactly": int(summary[5]), "check": check, "data": "synthetic", "dtype": "f64"}), flush=True)
+        "truth_recovered_exactly": int(summary[5]), "check": check,
+        "rank0_wall_split_s": {k: round(stats[k], 3) for k in ("t_host_lanes", "t_pack", "t_gpu")}, "data": "synthetic", "dtype": "f64"}), flush=True)
 if world > 1:
     dist.destroy_process_group()
