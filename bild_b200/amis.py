@@ -275,15 +275,30 @@ class FixedkSampler:
         return Loopingprofile(states)
 
     def log_proposal(self, parameters, ss, thetas):
-        return self.dirichlet.logpdf(parameters[0], ss) + self.cfc.logpmf(parameters[1], thetas)
+        return self.log_proposal_multi([parameters], ss, thetas)[0]
 
     def log_proposal_multi(self, parameters, ss, thetas):
-        """``(len(parameters), N)``: the samples under every proposal of the list, in one vectorised pass (the
-        reference evaluates past proposals one by one, amis.py:836-839 - O(steps) scipy constructions per step)."""
-        if len(parameters) == 0:
-            return np.empty((0, len(ss)))
-        return (self.dirichlet.logpdf_multi(np.array([par[0] for par in parameters]), ss)
-                + self.cfc.logpmf_multi(np.array([par[1] for par in parameters]), thetas))
+        """
+        ``(len(parameters), N)``: the samples under every proposal of the list in one pass of the native helper
+        ``bildk_amis_log_proposal`` (the reference evaluates proposals one by one through scipy distribution
+        objects, amis.py:697-715, 836-839 - O(steps) constructions per step).  `Dirichlet.logpdf_multi` +
+        `CFC.logpmf_multi` are the numpy statement of the same arithmetic (tests compare the two).
+        """
+        from . import _lib
+        n_par, n = len(parameters), len(ss)
+        out = np.empty((n_par, n))
+        if n_par == 0 or n == 0:
+            return out
+        A = np.ascontiguousarray([par[0] for par in parameters], dtype=np.float64)
+        L = np.ascontiguousarray([par[1] for par in parameters], dtype=np.float64)
+        ss = np.ascontiguousarray(ss, dtype=np.float64)
+        thetas = np.ascontiguousarray(thetas, dtype=np.int64)
+        trans = np.ascontiguousarray(self.cfc.transitions, dtype=np.uint8)
+        _lib.check(_lib.load().bildk_amis_log_proposal(
+            n_par, n, ss.shape[1], self.cfc.n, _lib.ptr(A, _lib.c_double_p), _lib.ptr(L, _lib.c_double_p),
+            _lib.ptr(trans, _lib.c_uint8_p), _lib.ptr(ss, _lib.c_double_p),
+            thetas.ctypes.data_as(_lib.ctypes.POINTER(_lib.ctypes.c_int64)), _lib.ptr(out, _lib.c_double_p)))
+        return out
 
     def logL(self, ss, thetas):
         """Model likelihood of a batch of samples -> (N,) float64.  One GPU launch when the model can."""

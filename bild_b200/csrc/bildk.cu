@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -1162,6 +1163,69 @@ extern "C" int bildk_amis_weights(int n, const double* logL, const double* logde
         return fail(BILDK_ECUDA, "weights kernel failed: %s", cudaGetErrorString(e));
     if (log_w) std::memcpy(log_w, sc.host.data(), nn * 8);
     std::memcpy(stats, sc.host.data() + (log_w ? nn : 0), 4 * 8);
+    return BILDK_OK;
+}
+
+// Host-side AMIS bookkeeping: proposal densities of n samples under n_par proposals (see include/bild_b200.h).
+extern "C" int bildk_amis_log_proposal(int n_par, int n, int K1, int S, const double* A, const double* logp,
+                                       const uint8_t* transitions, const double* ss, const int64_t* thetas, double* out) {
+    if (n_par < 0 || n < 0 || K1 < 1 || S < 1 || S > 255) return fail(BILDK_EINVAL, "bad sizes (n_par=%d n=%d K1=%d S=%d)", n_par, n, K1, S);
+    if (n_par == 0 || n == 0) return BILDK_OK;
+    if (!A || !logp || !transitions || !ss || !thetas || !out) return fail(BILDK_EINVAL, "NULL array argument");
+    for (size_t i = 0; i < static_cast<size_t>(n) * K1; ++i)
+        if (thetas[i] < 0 || thetas[i] >= S) return fail(BILDK_EINVAL, "state %lld out of range [0,%d)", static_cast<long long>(thetas[i]), S);
+    const double inf = std::numeric_limits<double>::infinity();
+    // log-sum-exp over the entries selected by `allowed`; -inf for an empty selection (amis.py uses scipy's logsumexp)
+    auto lse = [&](const double* v, int stride, const uint8_t* allowed) {
+        double top = -inf;
+        for (int m = 0; m < S; ++m)
+            if (!allowed || allowed[m]) top = std::max(top, v[m * stride]);
+        if (!std::isfinite(top)) top = 0.0;
+        double acc = 0.0;
+        for (int m = 0; m < S; ++m)
+            if (!allowed || allowed[m]) acc += std::exp(v[m * stride] - top);
+        return std::log(acc) + top;
+    };
+    std::vector<double> logs(static_cast<size_t>(n) * K1);   // log(s), shared by all proposals
+    std::vector<uint8_t> bad0(n), haszero(n);
+    for (int i = 0; i < n; ++i) {
+        double sum = 0.0;
+        bool bad = false, z = false;
+        for (int c = 0; c < K1; ++c) {
+            const double v = ss[static_cast<size_t>(i) * K1 + c];
+            sum += v;
+            if (!(v >= 0.0) || v > 1.0) bad = true;
+            if (v == 0.0) z = true;
+            logs[static_cast<size_t>(i) * K1 + c] = v > 0.0 ? std::log(v) : -inf;
+        }
+        if (std::fabs(sum - 1.0) > 1e-9 || std::isnan(sum)) bad = true;
+        bad0[i] = bad; haszero[i] = z;
+    }
+    std::vector<double> reach(static_cast<size_t>(S) * K1);   // per proposal: LSE over the states reachable from m at slot c
+    for (int j = 0; j < n_par; ++j) {
+        const double* a = A + static_cast<size_t>(j) * K1;
+        const double* lp = logp + static_cast<size_t>(j) * S * K1;   // [S][K1]
+        double asum = 0.0, lg = 0.0;
+        for (int c = 0; c < K1; ++c) { asum += a[c]; lg += std::lgamma(a[c]); }
+        const double lognorm = std::lgamma(asum) - lg;
+        const double norm0 = lse(lp, K1, nullptr);
+        for (int m = 0; m < S; ++m)
+            for (int c = 1; c < K1; ++c) reach[static_cast<size_t>(m) * K1 + c] = lse(lp + c, K1, transitions + static_cast<size_t>(m) * S);
+        double* o = out + static_cast<size_t>(j) * n;
+        for (int i = 0; i < n; ++i) {
+            const double* ls = logs.data() + static_cast<size_t>(i) * K1;
+            const int64_t* th = thetas + static_cast<size_t>(i) * K1;
+            double dir = lognorm;
+            bool bad = bad0[i];
+            for (int c = 0; c < K1; ++c) {
+                if (a[c] != 1.0) dir += (a[c] - 1.0) * ls[c];            // xlogy(a - 1, s): zero when a == 1, even at s == 0
+                if (haszero[i] && ls[c] == -inf && a[c] < 1.0) bad = true;
+            }
+            double cat = lp[th[0] * K1] - norm0;
+            for (int c = 1; c < K1; ++c) cat += lp[th[c] * K1 + c] - reach[static_cast<size_t>(th[c - 1]) * K1 + c];
+            o[i] = (bad ? inf : dir) + cat;
+        }
+    }
     return BILDK_OK;
 }
 

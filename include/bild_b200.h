@@ -117,6 +117,20 @@ int bildk_amis_weights(int n, const double *logL, const double *logdelta,
                        const double *cur_log_proposal, double log_nsteps,
                        double *log_w, double stats[4], int device);
 
+/*
+ * AMIS proposal densities (amis.py:83-108 `Dirichlet.logpdf`, amis.py:258-281 `CFC.logpmf`, combined as
+ * `FixedkSampler.log_proposal`, amis.py:697-715) of n samples under n_par proposals at once:
+ *   out[j][i] = log Dirichlet(ss[i]; A[j]) + log CFC(thetas[i]; logp[j])
+ * A (n_par, K1) concentrations; logp (n_par, S, K1) CFC log-weights; transitions (S, S), non-zero = allowed;
+ * ss (n, K1) interval lengths; thetas (n, K1) state traces; out (n_par, n).  Host arrays, row-major.
+ * Conventions of the reference: a sample with an s_i == 0 whose a_i < 1, entries outside [0, 1] or a sum off by
+ * more than 1e-9 gets +inf (its importance weight vanishes, amis.py:98-108).  Host-side bookkeeping of the AMIS
+ * loop - it replaces O(steps) scipy distribution constructions per step; it does
+ * not touch the GPU and consumes no random numbers.
+ */
+int bildk_amis_log_proposal(int n_par, int n, int K1, int S, const double *A, const double *logp,
+                            const uint8_t *transitions, const double *ss, const int64_t *thetas, double *out);
+
 /* Device-resident variant of bildk_amis_weights: device pointers (d_log_w may be NULL, d_stats has
  * room for 4 doubles), asynchronous on `stream`. */
 int bildk_amis_weights_device(int n, const double *d_logL, const double *d_logdelta,

@@ -109,6 +109,56 @@ def test_cfc_matches_scipy_formulation():
     np.testing.assert_allclose(cfc.estimate(thetas, lw), cfc.logp_from_marginals(lm), rtol=1e-10, atol=1e-12)
 
 
+def test_native_log_proposal_matches_numpy_and_scipy():
+    """bildk_amis_log_proposal (C ABI, host) == Dirichlet.logpdf + CFC.logpmf == the vectorised numpy statement,
+    including the reference's boundary conventions (amis.py:98-108): +inf for s_i == 0 with a_i < 1, -inf for
+    s_i == 0 with a_i > 1, nothing for a_i == 1; -inf for a trace through a forbidden (-inf weight) state."""
+    rng = np.random.default_rng(3)
+
+    class Model:
+        transitions = np.array([[0, 1, 1], [1, 0, 1], [1, 1, 0]], dtype=bool)
+        nStates = 3
+
+        def logL(self, profile, traj):
+            return 0.0
+
+    np.random.seed(2)
+    fs = amis.FixedkSampler(np.zeros((50, 1)), Model(), k=4)
+    K1 = 5
+    pars = [(rng.uniform(0.5, 5, K1), rng.normal(size=(3, K1))) for _ in range(6)]
+    pars.append((np.ones(K1), fs.cfc.logp_uniform(4)))
+    lp = pars[0][1].copy()
+    lp[1, 2] = -np.inf
+    pars.append((np.array([0.5, 1.0, 1.0, 2.0, 3.0]), lp))
+    ss = rng.dirichlet(np.ones(K1), 60)
+    thetas = fs.cfc.sample(pars[0][1], 60)
+    for row, col in ((3, 2), (4, 0), (5, 1)):            # exact zeros in columns with a == 1, a < 1, a == 1
+        ss[row, col] = 0
+        ss[row] /= ss[row].sum()
+    ss[6] = ss[6] * 1.1                                   # does not sum to one
+    one_by_one = np.array([fs.dirichlet.logpdf(a, ss) + fs.cfc.logpmf(lq, thetas) for a, lq in pars])
+    native = fs.log_proposal_multi(pars, ss, thetas)
+    assert np.array_equal(np.isinf(one_by_one), np.isinf(native))
+    assert np.array_equal(np.sign(one_by_one[np.isinf(one_by_one)]), np.sign(native[np.isinf(native)]))
+    fin = np.isfinite(one_by_one)
+    assert np.max(np.abs(one_by_one[fin] - native[fin])) < 1e-12
+    assert np.array_equal(fs.log_proposal(pars[2], ss, thetas), native[2])
+    # the vectorised numpy statement of the same arithmetic
+    A = np.array([p[0] for p in pars])
+    L = np.array([p[1] for p in pars])
+    vec = fs.dirichlet.logpdf_multi(A, ss) + fs.cfc.logpmf_multi(L, thetas)
+    assert np.max(np.abs(vec[fin] - native[fin])) < 1e-12
+    # scipy on the interior rows
+    for j in (1, 4):
+        want = scipy.stats.dirichlet(pars[j][0]).logpdf(ss[10:].T)
+        assert np.max(np.abs(fs.dirichlet.logpdf(pars[j][0], ss[10:]) - want)) < 1e-12
+    # error behaviour: state out of range
+    bad = thetas.copy()
+    bad[0, 0] = 7
+    with pytest.raises(ValueError):
+        fs.log_proposal_multi(pars, ss, bad)
+
+
 def test_fixedk_sampler_basics():
     model = bild.models.FactorizedModel([scipy.stats.maxwell(scale=1), scipy.stats.maxwell(scale=4)], d=1)
     traj = bild.Trajectory(np.array([0.5, 0.7, 3.0, 5.0, 4.0, 0.8]))
