@@ -1140,7 +1140,9 @@ extern "C" int bildk_amis_weights(int n, const double* logL, const double* logde
     CU(cudaSetDevice(device));
     // one grow-only scratch buffer per device and thread, one packed copy in, one out (a cudaMalloc / cudaFree pair
     // and five small copies per call used to cost more than the reduction itself: the AMIS loop calls this every step)
-    struct Scratch { DevBuf<double> dev; std::vector<double> host; };
+    // ... on a private non-blocking stream: a call from one host thread never queues behind a filter launch that
+    // another thread has in flight on the default stream
+    struct Scratch { DevBuf<double> dev; std::vector<double> host; cudaStream_t st = nullptr; };
     static thread_local std::vector<Scratch> scratch;
     if (scratch.size() < static_cast<size_t>(ndev)) scratch.resize(ndev);
     Scratch& sc = scratch[device];
@@ -1148,18 +1150,21 @@ extern "C" int bildk_amis_weights(int n, const double* logL, const double* logde
     int rc = sc.dev.reserve(4 * nn + 4);
     if (rc) return rc;
     if (sc.host.size() < 3 * nn + 4) sc.host.resize(2 * (3 * nn + 4));
+    if (!sc.st) CU(cudaStreamCreateWithFlags(&sc.st, cudaStreamNonBlocking));
     double* d = sc.dev.p;
     std::memcpy(sc.host.data(), logL, nn * 8);
     std::memcpy(sc.host.data() + nn, logdelta, nn * 8);
     std::memcpy(sc.host.data() + 2 * nn, curlp, nn * 8);
     cudaError_t e;
-    if ((e = cudaMemcpy(d, sc.host.data(), 3 * nn * 8, cudaMemcpyHostToDevice)) != cudaSuccess)
+    if ((e = cudaMemcpyAsync(d, sc.host.data(), 3 * nn * 8, cudaMemcpyHostToDevice, sc.st)) != cudaSuccess)
         return fail(BILDK_ECUDA, "copy failed: %s", cudaGetErrorString(e));
-    k_amis_weights<<<1, 1024>>>(n, d, d + nn, d + 2 * nn, log_nsteps, log_w ? d + 3 * nn : nullptr, d + 4 * nn);
+    k_amis_weights<<<1, 1024, 0, sc.st>>>(n, d, d + nn, d + 2 * nn, log_nsteps, log_w ? d + 3 * nn : nullptr, d + 4 * nn);
     g_launches++;
     // log_w (n) and the four statistics are contiguous on the device: [3n, 4n + 4)
     const size_t off = log_w ? 3 * nn : 4 * nn, cnt = log_w ? nn + 4 : 4;
-    if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaMemcpy(sc.host.data(), d + off, cnt * 8, cudaMemcpyDeviceToHost)) != cudaSuccess)
+    if ((e = cudaGetLastError()) != cudaSuccess ||
+        (e = cudaMemcpyAsync(sc.host.data(), d + off, cnt * 8, cudaMemcpyDeviceToHost, sc.st)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(sc.st)) != cudaSuccess)
         return fail(BILDK_ECUDA, "weights kernel failed: %s", cudaGetErrorString(e));
     if (log_w) std::memcpy(log_w, sc.host.data(), nn * 8);
     std::memcpy(stats, sc.host.data() + (log_w ? nn : 0), 4 * 8);

@@ -15,6 +15,11 @@ so trajectory ``i`` consumes exactly the random numbers it would consume in
 the sequential runs, independent of how many trajectories share a launch or a GPU.
 
 Multi-GPU: trajectories are partitioned across ranks (`rank`, `world`); no communication during sampling.
+
+Measured and dropped: two groups of state machines taking turns, so that the fused launch of one group (a worker
+thread inside the GIL-free C call) overlaps the host code of the other.  On the B200 box the launch time was
+hidden, but the lane threads lost as much to GIL hand-overs as was gained (64 trajectories: 11.9 s without,
+13.2 s with overlap); the remaining host time is AMIS bookkeeping in numpy (`stats['t_host_lanes']`).
 """
 import threading
 import time
