@@ -7,6 +7,7 @@
 #include "bildk_kernels.cuh"
 #include "bildk_mma.cuh"
 #include "bildk_mmar.cuh"
+#include "bildk_mmag2.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -403,6 +404,7 @@ struct Plan {
     bool mma = false;      // tensor-core kernel, one warp per filter
     bool mmac = false;     // tensor-core kernel, one CTA per filter, one warp per tile column
     bool mmag = false;     // same, covariance in an L2 workspace (N > 112)
+    int mmag_nc = 1;       // ... tile columns per warp (2, 4: k_mmag2)
     bool mma2 = false;     // tensor-core kernel, two warps per filter (GT 5..7)
     bool mmar = false;     // tensor-core kernel, one warp per filter, T chained through registers (GT <= 4)
     int nb = 0;            // ... its variant: resident 4-warp CTAs per SM it is compiled for
@@ -608,6 +610,29 @@ static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
             pl.smem = (static_cast<size_t>(2) * m->NPm + 2) * 8;
             pl.threads = 32 * GT;
             pl.FPC = 1;
+            const int ncw_env = env_int("BILDK_MMAG2", 3);   // tile columns per warp: 3 (default, measured best at N = 150, 200), 2, 4, or 0/1 = k_mmag
+            if (ncw_env >= 2) {
+                // NC adjacent tile columns per warp (k_mmag2): group j = columns [NC j, NC j + NC) of the GTC columns of
+                // [C | M]; groups -> warps longest-processing-time first onto the four schedulers (warp i runs on scheduler i % 4)
+                const int NC = ncw_env >= 4 ? 4 : ncw_env;
+                const int GTC = GT + (m->mma_mx ? 1 : 0);
+                const int ngrp = (GTC + NC - 1) / NC;
+                pl.mmag_nc = NC;
+                pl.threads = 32 * ngrp;
+                double load2[4] = {0, 0, 0, 0};
+                int slots2[4], used2[4] = {0, 0, 0, 0};
+                for (int k = 0; k < 4; ++k) slots2[k] = (ngrp - k + 3) / 4;
+                for (int j = ngrp - 1; j >= 0; --j) {   // P2 work grows with the group index
+                    int best = -1;
+                    for (int k = 0; k < 4; ++k)
+                        if (used2[k] < slots2[k] && (best < 0 || load2[k] < load2[best])) best = k;
+                    pl.colmap[best + 4 * used2[best]] = static_cast<unsigned char>(j);
+                    const int cA = NC * j, ncw = std::min(NC, GTC - cA), ncu = std::max(0, std::min(NC, GT - cA));
+                    load2[best] += ncw * GT + ncu * (cA + ncu);
+                    ++used2[best];
+                }
+                return pl;
+            }
             double load[4] = {0, 0, 0, 0};
             int slots[4], used[4] = {0, 0, 0, 0};
             for (int k = 0; k < 4; ++k) slots[k] = (GT - k + 3) / 4;
@@ -788,8 +813,8 @@ static std::string plan_string(const bildk_model* m, const Plan& pl) {
         snprintf(buf, sizeof buf, "mma2 (DMMA m8n8k4) GT=%d %s two-warps-per-filter FPC=%d threads=%d smem=%zu", m->GT,
                  m->mma_mx ? "mean-in-extra-tile" : "mean-in-padding", pl.FPC, pl.threads, pl.smem);
     else if (pl.mmag)
-        snprintf(buf, sizeof buf, "mmag (DMMA m8n8k4) GT=%d %s cta-per-filter warp-per-tile-column covariance-in-L2-workspace threads=%d", m->GT,
-                 m->mma_mx ? "mean-in-extra-tile" : "mean-in-padding", pl.threads);
+        snprintf(buf, sizeof buf, "mmag (DMMA m8n8k4) GT=%d %s cta-per-filter %s covariance-in-L2-workspace threads=%d", m->GT,
+                 m->mma_mx ? "mean-in-extra-tile" : "mean-in-padding", pl.mmag_nc == 4 ? "warp-per-four-tile-columns" : pl.mmag_nc == 3 ? "warp-per-three-tile-columns" : pl.mmag_nc == 2 ? "warp-per-two-tile-columns" : "warp-per-tile-column", pl.threads);
     else if (pl.mmac)
         snprintf(buf, sizeof buf, "mmac (DMMA m8n8k4) GT=%d %s cta-per-filter warp-per-tile-column B=%s threads=%d smem=%zu", m->GT,
                  m->mma_mx ? "mean-in-extra-tile" : "mean-in-padding", pl.b_all ? "all" : "one", pl.threads, pl.smem);
@@ -881,7 +906,7 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
                 CU(cudaMemcpy(m->meta2.p, pt.data(), P * sizeof(int), cudaMemcpyHostToDevice));
                 gp.prof_traj = m->meta2.p;
             }
-            const int nc = std::min(P, 2 * m->n_sm);
+            const int nc = std::min(P, ((pl.mmag_nc == 4 && env_int("BILDK_MMAG2_MINB", 2) >= 3) ? 3 : 2) * m->n_sm);
             const size_t wsz = static_cast<size_t>(2) * m->NPm * m->LDCm;
             int rc = m->work.reserve(wsz * nc * dstar);
             if (rc) return rc;
@@ -889,6 +914,18 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
             // row-chunk size by the registers the warp count leaves (registers are allocated per scheduler)
             auto waste = [&](int chv) { return ((m->GT + chv - 1) / chv) * chv; };   // padded tile rows per column
             const int ch = env_int("BILDK_MMAG_CH", m->GT <= 16 ? 8 : ((m->GT <= 28 && waste(6) <= waste(4)) ? 6 : 4));
+            if (pl.mmag_nc == 4) {        // <= 8 warps per CTA
+                if (env_int("BILDK_MMAG2_MINB", 2) >= 3) k_mmag2<4, 4, 256, 3><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);
+                else k_mmag2<4, 4, 256, 2><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);
+            } else if (pl.mmag_nc == 3) {   // <= 11 warps per CTA
+                if (pl.threads <= 288) k_mmag2<4, 3, 288, 2><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);
+                else k_mmag2<4, 3, 352, 2><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);
+            } else if (pl.mmag_nc == 2 && env_int("BILDK_MMAG2_CH", 4) >= 8) {
+                k_mmag2<8, 2, 512, 1><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);
+            } else if (pl.mmag_nc == 2) {
+                if (pl.threads <= 448) k_mmag2<4, 2, 448, 2><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);
+                else k_mmag2<4, 2, 512, 2><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);
+            } else
             if (ch >= 8 && m->GT <= 16) k_mmag<8, 512><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);
             else if (ch >= 6 && m->GT <= 28) k_mmag<6, 896><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);
             else k_mmag<4, 1024><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);

@@ -71,12 +71,15 @@ def test_against_c_oracle(N, d, T, P, p_nan, noise, loops, kmax):
     assert np.array_equal(got_st, got_states)          # same filters, same arithmetic
 
 
-@pytest.mark.parametrize("kernel", ["tile", "mmag"])
+@pytest.mark.parametrize("kernel", ["tile", "mmag", "mmag-one-column"])
 @pytest.mark.parametrize("N", [20, 60, 100])
 def test_kernel_variants_agree(kernel, N, monkeypatch):
     """Every kernel family that can run a shape gives the oracle's answer (BILDK_KERNEL forces the family)."""
-    if kernel == "mmag" and N < 57:
+    if kernel.startswith("mmag") and N < 57:
         pytest.skip("the L2-workspace tensor-core kernel starts at GT = 8")
+    if kernel == "mmag-one-column":      # k_mmag (one tile column per warp) instead of k_mmag2 (two)
+        monkeypatch.setenv("BILDK_MMAG2", "0")
+        kernel = "mmag"
     rng = np.random.default_rng(N)
     mod = oracle_model(N, d=3)
     T, P = 25, 5
