@@ -405,6 +405,7 @@ struct Plan {
     bool mmac = false;     // tensor-core kernel, one CTA per filter, one warp per tile column
     bool mmag = false;     // same, covariance in an L2 workspace (N > 112)
     int mmag_nc = 1;       // ... tile columns per warp (2, 4: k_mmag2)
+    int nhelp = 0;         // mmac: helper warps that balance P1 across the schedulers
     bool mma2 = false;     // tensor-core kernel, two warps per filter (GT 5..7)
     bool mmar = false;     // tensor-core kernel, one warp per filter, T chained through registers (GT <= 4)
     int nb = 0;            // ... its variant: resident 4-warp CTAs per SM it is compiled for
@@ -533,7 +534,7 @@ static cudaError_t mmac_launch(const CParams& cp, dim3 grid, size_t smem, cudaSt
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    k_mmac<GT, MX><<<grid, 32 * GT, smem, st>>>(cp);
+    k_mmac<GT, MX><<<grid, 32 * (GT + cp.nhelp), smem, st>>>(cp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         cudaFuncAttributes a{};
@@ -656,16 +657,20 @@ static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
             pl.smem = 16 + matb * (pl.b_all ? m->S : 1) + fbytes;
             pl.threads = 32 * GT;
             pl.FPC = 1;
+            // GT = 4k + 1 columns: three helper warps balance P1 across the schedulers (see k_mmac), so the column map
+            // only has to balance P2 (weight c + 1); otherwise it balances P1 + P2 (weight GT + c + 1)
+            pl.nhelp = (GT % 4 == 1 && GT >= 9 && !m->mma_mx && env_int("BILDK_MMAC_HELPERS", 1)) ? 3 : 0;
+            pl.threads = 32 * (GT + pl.nhelp);
             // column -> warp: longest-processing-time first onto the four schedulers (warp i runs on scheduler i % 4)
             double load[4] = {0, 0, 0, 0};
             int slots[4], used[4] = {0, 0, 0, 0};
             for (int k = 0; k < 4; ++k) slots[k] = (GT - k + 3) / 4;
-            for (int c = GT - 1; c >= 0; --c) {   // weight GT (P1) + c + 1 (P2) decreases with c
+            for (int c = GT - 1; c >= 0; --c) {   // the weight decreases with c
                 int best = -1;
                 for (int k = 0; k < 4; ++k)
                     if (used[k] < slots[k] && (best < 0 || load[k] < load[best])) best = k;
                 pl.colmap[best + 4 * used[best]] = static_cast<unsigned char>(c);
-                load[best] += GT + c + 1 + ((c == 0 && m->mma_mx) ? GT : 0);
+                load[best] += (pl.nhelp ? 0 : GT) + c + 1 + ((c == 0 && m->mma_mx) ? GT : 0);
                 ++used[best];
             }
             return pl;
@@ -816,8 +821,8 @@ static std::string plan_string(const bildk_model* m, const Plan& pl) {
         snprintf(buf, sizeof buf, "mmag (DMMA m8n8k4) GT=%d %s cta-per-filter %s covariance-in-L2-workspace threads=%d", m->GT,
                  m->mma_mx ? "mean-in-extra-tile" : "mean-in-padding", pl.mmag_nc == 4 ? "warp-per-four-tile-columns" : pl.mmag_nc == 3 ? "warp-per-three-tile-columns" : pl.mmag_nc == 2 ? "warp-per-two-tile-columns" : "warp-per-tile-column", pl.threads);
     else if (pl.mmac)
-        snprintf(buf, sizeof buf, "mmac (DMMA m8n8k4) GT=%d %s cta-per-filter warp-per-tile-column B=%s threads=%d smem=%zu", m->GT,
-                 m->mma_mx ? "mean-in-extra-tile" : "mean-in-padding", pl.b_all ? "all" : "one", pl.threads, pl.smem);
+        snprintf(buf, sizeof buf, "mmac (DMMA m8n8k4) GT=%d %s cta-per-filter warp-per-tile-column%s B=%s threads=%d smem=%zu", m->GT,
+                 m->mma_mx ? "mean-in-extra-tile" : "mean-in-padding", pl.nhelp ? " +3-P1-helper-warps" : "", pl.b_all ? "all" : "one", pl.threads, pl.smem);
     else if (pl.mmar)
         snprintf(buf, sizeof buf, "mmar (DMMA m8n8k4) GT=%d register-chained warp-per-filter WPC=%d CTAs/SM=%d threads=%d smem=%zu", m->GT,
                  pl.WPC, pl.nb, pl.threads, pl.smem);
@@ -956,6 +961,7 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
                 CParams cp{};
                 cp.m = mp;
                 cp.b_all = pl.b_all;
+                cp.nhelp = pl.nhelp;
                 for (int i = 0; i < 16; ++i) cp.colmap[i] = pl.colmap[i];   // GT <= 14
                 CU(mmac_launch_for(m->GT, m->mma_mx, cp, grid, pl.smem, st));
             } else

@@ -432,7 +432,24 @@ struct CParams {
     MParams m;
     unsigned char colmap[16];   // warp -> tile column
     int b_all;                  // all S propagators resident
+    int nhelp;                  // helper warps (GT % 4 == 1, no extra mean column): warps GT .. GT + nhelp - 1, see k_mmac
 };
+
+// P1 of one tile column for the tile rows [LO, HI): acc[ti] = sum_k B_s[ti][k] C[k][cc]
+template <int GT, int LO, int HI, int LDA, int LDBB>
+__device__ __forceinline__ void mmac_p1(double (&acc)[GT][2], const double* __restrict__ Ap, const double* __restrict__ Bp, int NK) {
+#pragma unroll
+    for (int ti = LO; ti < HI; ++ti) acc[ti][0] = acc[ti][1] = 0.0;
+#pragma unroll 1
+    for (int k0 = 0; k0 < NK; k0 += 4) {
+        double a[HI - LO];
+#pragma unroll
+        for (int ti = LO; ti < HI; ++ti) a[ti - LO] = Ap[8 * ti * LDA + k0];
+        const double b = Bp[k0 * LDBB];
+#pragma unroll
+        for (int ti = LO; ti < HI; ++ti) dmma884(acc[ti], a[ti - LO], b);
+    }
+}
 
 template <int GT, bool MX>
 // registers are allocated per scheduler (16 K each): ceil(GT / 4) warps share one
@@ -451,9 +468,18 @@ __global__ void __maxnreg__((16384 / (32 * ((GT + 3) / 4))) / 8 * 8 > 240 ? 240 
     const int g = lane >> 2, c4 = lane & 3;
     const int e_sub = blockIdx.y;
     const int N = p.N, D = p.D, NK = mp.NK;
-    const int c = cp.colmap[wid];                 // this warp's tile column
-    const bool mown = (c == GT - 1);              // ... which also carries the mean columns
-    const bool mxw = MX && (c == 0);              // ... or computes the extra mean tile column of T
+    // Warps 0 .. GT-1 own one tile column each.  With GT = 4k + 1 columns one scheduler (warps 0, 4, 8, ...) carries
+    // k + 1 column warps and the others k, and P1 - the same GT tiles for every column, between two CTA barriers -
+    // would run at the pace of that scheduler (13 columns: 52 vs 39 tiles, a fifth of the P1 phase idle).  Three helper
+    // warps (GT, GT+1, GT+2 -> schedulers 1, 2, 3) therefore take the first HR = GT / 4 tile rows of P1 of the columns of
+    // warps 0, 4, 8: 43 / 42 / 42 / 42 tiles per scheduler.  Helper and owner read the whole column before either
+    // overwrites it (T is produced in place), so the pair meets at a named barrier between the product and the store.
+    constexpr int HR = GT / 4;
+    const bool helper = wid >= GT;                // helpers run their own compact frame loop (below) and own no column
+    const bool helped = HR > 0 && !helper && (wid & 3) == 0 && (wid >> 2) < cp.nhelp;   // pair (wid >> 2) with warp GT + (wid >> 2)
+    const int c = cp.colmap[helper ? 4 * (wid - GT) : wid];   // this warp's tile column (helper: the column it helps with)
+    const bool mown = !helper && (c == GT - 1);   // ... which also carries the mean columns
+    const bool mxw = MX && !helper && (c == 0);   // ... or computes the extra mean tile column of T
 
     const int tj = p.cta_traj ? p.cta_traj[blockIdx.x] : 0;
     const int pidx = p.cta_first ? p.cta_first[blockIdx.x] : blockIdx.x;
@@ -505,6 +531,35 @@ __global__ void __maxnreg__((16384 / (32 * ((GT + 3) / 4))) / 8 * 8 > 240 ? 240 
 
     if (cp.b_all) mbar_wait(mbar, 0);
 
+    if (HR > 0 && helper) {
+        // ---------------- helper warp: tile rows [0, HR) of P1 of column c, and every CTA-wide synchronisation of
+        //                  the main loop below (propagator re-staging wait, three barriers per frame)
+        for (int t = 0; t < T; ++t) {
+            while (t >= next_sw) {
+                ++r_cur;
+                s = p.run_states[static_cast<size_t>(pidx) * p.K1 + r_cur];
+                next_sw = (r_cur + 1 < p.K1) ? p.run_starts[static_cast<size_t>(pidx) * p.K1 + r_cur + 1] : 0x7fffffff;
+            }
+            if (!cp.b_all && t > 0 && s != s_loaded) {
+                mbar_wait(mbar, bphase);
+                bphase ^= 1;
+                s_loaded = s;
+            }
+            if (t > 0) {
+                const double* Bs = Bsm + (cp.b_all ? s * MATB : 0);
+                mmac_p1<GT, 0, (HR > 0 ? HR : 1), LDB, LDC>(acc, Bs + g * LDB + c4, Cb + c4 * LDC + 8 * c + g, NK);
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + wid - GT) : "memory");   // owner and helper have read column c
+#pragma unroll
+                for (int ti = 0; ti < HR; ++ti)
+                    *reinterpret_cast<double2*>(myC + 8 * ti * LDC + 8 * c) = make_double2(acc[ti][0], acc[ti][1]);
+                __syncthreads();   // T complete
+            }
+            __syncthreads();       // published columns visible
+            __syncthreads();       // C+ complete
+        }
+        return;
+    }
+
     for (int t = 0; t < T; ++t) {
         while (t >= next_sw) {
             ++r_cur;
@@ -533,25 +588,23 @@ __global__ void __maxnreg__((16384 / (32 * ((GT + 3) / 4))) / 8 * 8 > 240 ? 240 
         if (t > 0) {
             // ---------------- P1: T[:, cc] = B_s Caug[:, cc], in place
             auto p1_column = [&](int cc) {
-#pragma unroll
-                for (int ti = 0; ti < GT; ++ti) acc[ti][0] = acc[ti][1] = 0.0;
                 const double* Ap = Bs + g * LDB + c4;
                 const double* Bp = Cb + c4 * LDC + 8 * cc + g;
-#pragma unroll 1
-                for (int k0 = 0; k0 < NK; k0 += 4) {
-                    double a[GT];
-#pragma unroll
-                    for (int ti = 0; ti < GT; ++ti) a[ti] = Ap[8 * ti * LDB + k0];
-                    const double b = Bp[k0 * LDC];
-#pragma unroll
-                    for (int ti = 0; ti < GT; ++ti) dmma884(acc[ti], a[ti], b);
-                }
+                mmac_p1<GT, 0, GT, LDB, LDC>(acc, Ap, Bp, NK);
                 __syncwarp();   // this warp is the only reader of column cc
 #pragma unroll
                 for (int ti = 0; ti < GT; ++ti)
                     *reinterpret_cast<double2*>(myC + 8 * ti * LDC + 8 * cc) = make_double2(acc[ti][0], acc[ti][1]);
             };
-            p1_column(c);
+            if (helped) {      // tile rows [HR, GT); the helper warp GT + (wid >> 2) does [0, HR)
+                mmac_p1<GT, HR, GT, LDB, LDC>(acc, Bs + g * LDB + c4, Cb + c4 * LDC + 8 * c + g, NK);
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + (wid >> 2)) : "memory");   // both warps have read column c
+#pragma unroll
+                for (int ti = HR; ti < GT; ++ti)
+                    *reinterpret_cast<double2*>(myC + 8 * ti * LDC + 8 * c) = make_double2(acc[ti][0], acc[ti][1]);
+            } else {
+                p1_column(c);
+            }
             if (mxw) p1_column(GT);
         }
         // upper tiles of this column start at Sig (t > 0) / hold C0 (t = 0)
