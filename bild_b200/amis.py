@@ -457,6 +457,10 @@ class FixedkSampler:
             log_w = np.concatenate([smp["log_weights"] for smp in self.samples])
         except KeyError:                              # exhaustive sampling: weights are the likelihoods
             log_w = np.concatenate([smp["logLs"] for smp in self.samples])
+        if hasattr(self.model, "marginal_posterior"):      # weighted per-frame state histogram on the device
+            ss = np.concatenate([smp["ss"] for smp in self.samples])
+            thetas = np.concatenate([smp["thetas"] for smp in self.samples])
+            return self.model.marginal_posterior(ss, thetas, len(self.traj), log_w)
         states = self._ensemble_states()
         n = self.model.nStates
         onehot = states[:, None, :] == np.arange(n)[None, :, None]

@@ -1214,6 +1214,39 @@ extern "C" int bildk_amis_weights(int n, const double* logL, const double* logde
     return BILDK_OK;
 }
 
+extern "C" int bildk_marginal_posterior(int n, int K1, int T, int S, const int32_t* run_starts, const uint8_t* run_states,
+                                        const double* log_w, double* out, int device) {
+    if (n < 1 || K1 < 1 || T < 1 || S < 1 || S > 255 || !run_starts || !run_states || !log_w || !out) return fail(BILDK_EINVAL, "bad argument");
+    int ndev = bildk_device_count();
+    if (ndev == 0) return fail(BILDK_ECUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(BILDK_EINVAL, "device %d out of range", device);
+    const size_t nn = static_cast<size_t>(n), nr = nn * K1;
+    for (size_t i = 0; i < nr; ++i) if (run_states[i] >= S) return fail(BILDK_EINVAL, "state %d out of range [0,%d)", run_states[i], S);
+    CU(cudaSetDevice(device));
+    int32_t* d_starts = nullptr;
+    uint8_t* d_states = nullptr;
+    double *d_w = nullptr, *d_out = nullptr;
+    int rc = BILDK_OK;
+    cudaError_t e = cudaSuccess;
+    if ((e = cudaMalloc(&d_starts, nr * sizeof(int32_t))) != cudaSuccess || (e = cudaMalloc(&d_states, nr)) != cudaSuccess ||
+        (e = cudaMalloc(&d_w, nn * 8)) != cudaSuccess || (e = cudaMalloc(&d_out, static_cast<size_t>(S) * T * 8)) != cudaSuccess)
+        rc = fail(BILDK_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(e));
+    if (rc == BILDK_OK &&
+        ((e = cudaMemcpy(d_starts, run_starts, nr * sizeof(int32_t), cudaMemcpyHostToDevice)) != cudaSuccess ||
+         (e = cudaMemcpy(d_states, run_states, nr, cudaMemcpyHostToDevice)) != cudaSuccess ||
+         (e = cudaMemcpy(d_w, log_w, nn * 8, cudaMemcpyHostToDevice)) != cudaSuccess))
+        rc = fail(BILDK_ECUDA, "copy failed: %s", cudaGetErrorString(e));
+    if (rc == BILDK_OK) {
+        k_marginal_posterior<<<T, 256>>>(n, K1, T, S, d_starts, d_states, d_w, d_out);
+        g_launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess ||
+            (e = cudaMemcpy(out, d_out, static_cast<size_t>(S) * T * 8, cudaMemcpyDeviceToHost)) != cudaSuccess)
+            rc = fail(BILDK_ECUDA, "marginal posterior kernel failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d_starts); cudaFree(d_states); cudaFree(d_w); cudaFree(d_out);
+    return rc;
+}
+
 // Host-side AMIS bookkeeping: proposal densities of n samples under n_par proposals (see include/bild_b200.h).
 extern "C" int bildk_amis_log_proposal(int n_par, int n, int K1, int S, const double* A, const double* logp,
                                        const uint8_t* transitions, const double* ss, const int64_t* thetas, double* out) {

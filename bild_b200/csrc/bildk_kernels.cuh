@@ -658,6 +658,67 @@ __global__ void __launch_bounds__(1024) k_amis_weights(int n, const double* __re
 }
 
 // ------------------------------------------------------------------------------------------------
+// Marginal posterior of the state at every frame from a weighted ensemble of run-length profiles
+// (FixedkSampler.log_marginal_posterior, /root/reference/bild/amis.py:942-972, which materialises an
+// (n, S, T) boolean tensor on the host): out[s][t] = log sum_{i: state_i(t) = s} w_i, normalised over s.
+// One CTA per frame; for every state a fixed-order (thread-strided, warp-shuffle, cross-warp) sum, so the
+// result does not depend on the launch geometry of other frames and is reproducible.
+__global__ void __launch_bounds__(256) k_marginal_posterior(int n, int K1, int T, int S, const int32_t* __restrict__ starts,
+                                                            const uint8_t* __restrict__ states, const double* __restrict__ log_w,
+                                                            double* __restrict__ out) {
+    __shared__ double red[8];
+    __shared__ double bc;
+    __shared__ double lse[256];
+    const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    auto state_at = [&](int i) {
+        const int32_t* rs = starts + static_cast<size_t>(i) * K1;
+        int r = 0;
+        for (int q = 1; q < K1; ++q) r = (rs[q] <= t) ? q : r;   // last run that has started (empty runs vanish)
+        return static_cast<int>(states[static_cast<size_t>(i) * K1 + r]);
+    };
+    for (int s = 0; s < S; ++s) {
+        // log-sum-exp of the weights of the samples that are in state s at frame t, shifted by THEIR maximum (a state
+        // whose samples are all e-800 below the best one still has a finite log posterior, as in the reference)
+        double mx = -INFINITY;
+        for (int i = tid; i < n; i += blockDim.x)
+            if (state_at(i) == s) mx = fmax(mx, log_w[i]);
+        mx = warp_max(mx);
+        if (lane == 0) red[wid] = mx;
+        __syncthreads();
+        if (tid == 0) {
+            double v = -INFINITY;
+            for (int k = 0; k < nw; ++k) v = fmax(v, red[k]);
+            bc = v;
+        }
+        __syncthreads();
+        mx = bc;
+        double acc = 0.0;
+        if (mx > -INFINITY && mx < INFINITY)
+            for (int i = tid; i < n; i += blockDim.x)
+                if (state_at(i) == s) acc += exp(log_w[i] - mx);
+        acc = warp_sum(acc);
+        __syncthreads();
+        if (lane == 0) red[wid] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double v = 0.0;
+            for (int k = 0; k < nw; ++k) v += red[k];
+            lse[s] = (mx > -INFINITY && mx < INFINITY) ? log(v) + mx : mx;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {   // normalise over the states (amis.py:972)
+        double top = -INFINITY;
+        for (int s = 0; s < S; ++s) top = fmax(top, lse[s]);
+        double all = 0.0;
+        if (top > -INFINITY && top < INFINITY)
+            for (int s = 0; s < S; ++s) all += exp(lse[s] - top);
+        const double norm = (top > -INFINITY && top < INFINITY) ? log(all) + top : top;
+        for (int s = 0; s < S; ++s) out[static_cast<size_t>(s) * T + t] = lse[s] - norm;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // FP64 peak probes (roofline denominators; MEASURED_PEAKS.json has no FP64 entry): independent
 // register-resident DFMA chains, and DMMA m8n8k4 chains.  Same kernels as tools/fp64_peak.cu.
 __global__ void __launch_bounds__(256) k_peak_dfma(double* out, int iters, double a, double b) {

@@ -232,6 +232,23 @@ class MultiStateRouse(MultiStateModel):
                                                   _lib.ptr(log_w, dp), _lib.ptr(st, dp), self.engine.device))
         return log_w, tuple(st)
 
+    def marginal_posterior(self, ss, thetas, T, log_weights):
+        """
+        ``(n_states, T)`` normalised log posterior probability of each state at each frame from the weighted
+        ensemble ``(ss, thetas, log_weights)`` (amis.py:942-972), reduced on the device from the run-length profiles
+        (the reference builds an ``(n, S, T)`` boolean tensor on the host).
+        """
+        from . import _lib
+        from .engine import st_to_runs
+        starts, states = st_to_runs(ss, thetas, T)
+        lw = _lib.as_f64(log_weights)
+        out = np.empty((self.nStates, T))
+        _lib.check(_lib.load().bildk_marginal_posterior(len(lw), starts.shape[1], T, self.nStates,
+                                                        _lib.ptr(starts, _lib.c_int32_p), _lib.ptr(states, _lib.c_uint8_p),
+                                                        _lib.ptr(lw, _lib.c_double_p), _lib.ptr(out, _lib.c_double_p),
+                                                        self.engine.device))
+        return out
+
     # ------------------------------------------------------------------ helpers shared with the reference API
     def initial_loopingprofile(self, traj):
         return self.toFactorized().initial_loopingprofile(traj)

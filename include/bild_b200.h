@@ -118,6 +118,17 @@ int bildk_amis_weights(int n, const double *logL, const double *logdelta,
                        double *log_w, double stats[4], int device);
 
 /*
+ * Marginal posterior of the state at every frame from a weighted ensemble of run-length profiles
+ * (FixedkSampler.log_marginal_posterior, amis.py:942-972; SamplingResults.log_marginal_posterior, core.py:345-372):
+ *   out[s][t] = log sum_{i : state_i(t) = s} exp(log_w[i])  -  log sum_i exp(log_w[i])
+ * run_starts (n, K1) / run_states (n, K1) as for bildk_logl_runs (first run starts at 0, empty runs allowed,
+ * padding runs start at T); log_w (n) the AMIS log-weights (or log-likelihoods for an exhaustive sample);
+ * out (S, T) row-major.  Host pointers.  The reference materialises an (n, S, T) boolean tensor on the host for this.
+ */
+int bildk_marginal_posterior(int n, int K1, int T, int S, const int32_t *run_starts, const uint8_t *run_states,
+                             const double *log_w, double *out, int device);
+
+/*
  * AMIS proposal densities (amis.py:83-108 `Dirichlet.logpdf`, amis.py:258-281 `CFC.logpmf`, combined as
  * `FixedkSampler.log_proposal`, amis.py:697-715) of n samples under n_par proposals at once:
  *   out[j][i] = log Dirichlet(ss[i]; A[j]) + log CFC(thetas[i]; logp[j])

@@ -49,6 +49,51 @@ def test_sample_config1_matches_reference_run(runs):
     assert _lib.load().bildk_launch_count() >= int(runs["c1_n_logl_batches"])
 
 
+def test_marginal_posterior_kernel(runs):
+    """Device marginal posterior (amis.py:942-972 replacement) vs the host tensor formulation, and vs the reference run."""
+    model = bild.models.MultiStateRouse(20, 1, 5, d=3, localization_error=0.3)
+    traj = bild.Trajectory(runs["c1_x"], localization_error=[0.3] * 3)
+    np.random.seed(1234)
+    res = bild.sample(traj, model)
+    np.testing.assert_allclose(np.exp(res.log_marginal_posterior()), np.exp(runs["c1_post"]), atol=1e-4)   # as in test_amis_host
+    for smp in res.samplers:
+        if not smp.samples:
+            continue
+        dev = smp.log_marginal_posterior()
+        # host formulation: hide the device method from the sampler
+        class HostOnly:
+            nStates = model.nStates
+        keep, smp.model = smp.model, HostOnly()
+        try:
+            host = smp.log_marginal_posterior()
+        finally:
+            smp.model = keep
+        assert dev.shape == host.shape == (2, len(traj))
+        both = np.isfinite(host)
+        assert np.array_equal(both, np.isfinite(dev))
+        assert np.max(np.abs(dev[both] - host[both])) < 1e-10
+    # evidence-averaged posterior goes through the same kernel
+    avg = res.log_marginal_posterior(dE="average")
+    np.testing.assert_allclose(np.exp(avg).sum(axis=0), 1.0, atol=1e-12)
+    # synthetic ensemble with empty runs, padding runs and -inf weights, three states
+    rng = np.random.default_rng(5)
+    n, K1, T = 777, 6, 41
+    ss = rng.dirichlet(np.ones(K1), n)
+    ss[::7, 2] = 0
+    ss /= ss.sum(axis=1, keepdims=True)
+    thetas = rng.integers(0, 2, size=(n, K1))
+    lw = rng.normal(-50, 8, n)
+    lw[::11] = -np.inf
+    got = model.marginal_posterior(ss, thetas, T, lw)
+    switches = np.floor(np.cumsum(ss, axis=1)[:, :-1] * (T - 1)).astype(int) + 1
+    run = np.sum(np.arange(T)[None, :, None] >= switches[:, None, :], axis=2)
+    st = np.take_along_axis(thetas, run, axis=1)
+    w = np.exp(lw - lw[np.isfinite(lw)].max())
+    want = np.array([[w[st[:, t] == s].sum() for t in range(T)] for s in range(2)])
+    want = np.log(want / want.sum(axis=0, keepdims=True))
+    assert np.max(np.abs(got - want)) < 1e-10
+
+
 def test_amis_weights_kernel():
     rng = np.random.default_rng(0)
     model = bild.models.MultiStateRouse(8, 1, 5, d=1, localization_error=0.5)
