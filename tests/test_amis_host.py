@@ -249,10 +249,10 @@ class OracleBackedRouse(bild.models.MultiStateRouse):
             out[lo:hi] = ko.logl_c(*arrs, self.measurement, tr[:], s2, cind, st)
         return out
 
-    amis_weights = None    # host numpy weights
+    amis_weights = None    # host numpy weights, host marginal posterior: no device in the CPU suite
 
     def __getattribute__(self, name):
-        if name == "amis_weights":
+        if name in ("amis_weights", "marginal_posterior"):
             raise AttributeError(name)
         return super().__getattribute__(name)
 
