@@ -8,6 +8,7 @@
 #include "bildk_mma.cuh"
 #include "bildk_mmar.cuh"
 #include "bildk_mmag2.cuh"
+#include "bildk_mmact.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -406,6 +407,7 @@ struct Plan {
     bool mmag = false;     // same, covariance in an L2 workspace (N > 112)
     int mmag_nc = 1;       // ... tile columns per warp (2, 4: k_mmag2)
     int nhelp = 0;         // mmac: helper warps that balance P1 across the schedulers
+    bool mmact = false;    // ... and P2 / update / write-back dealt out as tile slots (k_mmact)
     bool mma2 = false;     // tensor-core kernel, two warps per filter (GT 5..7)
     bool mmar = false;     // tensor-core kernel, one warp per filter, T chained through registers (GT <= 4)
     int nb = 0;            // ... its variant: resident 4-warp CTAs per SM it is compiled for
@@ -544,6 +546,69 @@ static cudaError_t mmac_launch(const CParams& cp, dim3 grid, size_t smem, cudaSt
     }
     return e;
 }
+template <int GT>
+static cudaError_t mmact_launch(const CTParams& ct, dim3 grid, size_t smem, cudaStream_t st) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_mmact<GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    k_mmact<GT><<<grid, 32 * (GT + 3), smem, st>>>(ct);
+    return cudaGetLastError();
+}
+// slot table of k_mmact: the upper tiles (ti <= c), last column first, rows ascending, dealt out to the GT + 3 warps in
+// order as SEGMENTS (consecutive tile rows of one column), at most two per warp; the first (total mod warps) warps may
+// take one slot more.  Pieces that would have been a third segment go to the lightest single-segment warps.
+// Warp w runs on scheduler w % 4.
+static bool mmact_slots(int GT, CTParams& ct) {
+    const int nw = GT + 3, total = GT * (GT + 1) / 2, base = total / nw, rem = total % nw;
+    struct Seg { int c, lo, n; };
+    std::vector<std::vector<Seg>> warps(1);
+    std::vector<Seg> extra;
+    auto cap = [&](int w) { return base + (w < rem ? 1 : 0); };
+    auto load = [](const std::vector<Seg>& v) { int x = 0; for (const Seg& sg : v) x += sg.n; return x; };
+    for (int c = GT - 1; c >= 0; --c) {
+        int ti = 0;
+        while (ti <= c) {
+            const int w = static_cast<int>(warps.size()) - 1;
+            if (w >= nw) { extra.push_back({c, ti, c + 1 - ti}); break; }
+            const int room = cap(w) - load(warps.back());
+            if (room == 0 || warps.back().size() == 2) { warps.emplace_back(); continue; }
+            const int n = std::min(room, c + 1 - ti);
+            warps.back().push_back({c, ti, n});
+            ti += n;
+        }
+    }
+    while (static_cast<int>(warps.size()) > nw) {   // pieces of warps beyond the last one
+        for (const Seg& sg : warps.back()) extra.push_back(sg);
+        warps.pop_back();
+    }
+    warps.resize(nw);
+    for (const Seg& sg : extra) {
+        int best = -1;
+        for (int w = 0; w < nw; ++w)
+            if (warps[w].size() < 2 && load(warps[w]) + sg.n <= 6 && (best < 0 || load(warps[w]) < load(warps[best]))) best = w;
+        if (best < 0) return false;
+        warps[best].push_back(sg);
+    }
+    for (int w = 0; w < 16; ++w) { ct.nslot[w] = 0; ct.nsegA[w] = 0; }
+    for (int w = 0; w < nw; ++w) {
+        int k = 0;
+        for (size_t sgi = 0; sgi < warps[w].size(); ++sgi) {
+            const Seg& sg = warps[w][sgi];
+            for (int i = 0; i < sg.n; ++i, ++k) {
+                ct.slot_ti[w][k] = static_cast<unsigned char>(sg.lo + i);
+                ct.slot_c[w][k] = static_cast<unsigned char>(sg.c);
+            }
+            if (sgi == 0) ct.nsegA[w] = static_cast<unsigned char>(sg.n);
+        }
+        ct.nslot[w] = static_cast<unsigned char>(k);
+        if (k == 0 || k > 6) return false;
+    }
+    return ct.slot_ti[0][0] == 0 && ct.slot_c[0][0] == GT - 1;
+}
+
 static cudaError_t mmac_launch_for(int GT, bool MX, const CParams& cp, dim3 grid, size_t smem, cudaStream_t st) {
     switch (GT * 2 + (MX ? 1 : 0)) {
         case 10: return mmac_launch<5, false>(cp, grid, smem, st);   case 11: return mmac_launch<5, true>(cp, grid, smem, st);
@@ -661,6 +726,7 @@ static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
             // only has to balance P2 (weight c + 1); otherwise it balances P1 + P2 (weight GT + c + 1)
             pl.nhelp = (GT % 4 == 1 && GT >= 9 && !m->mma_mx && env_int("BILDK_MMAC_HELPERS", 1)) ? 3 : 0;
             pl.threads = 32 * (GT + pl.nhelp);
+            pl.mmact = pl.nhelp == 3 && (GT == 9 || GT == 13) && env_int("BILDK_MMACT", 1);
             // column -> warp: longest-processing-time first onto the four schedulers (warp i runs on scheduler i % 4)
             double load[4] = {0, 0, 0, 0};
             int slots[4], used[4] = {0, 0, 0, 0};
@@ -821,8 +887,9 @@ static std::string plan_string(const bildk_model* m, const Plan& pl) {
         snprintf(buf, sizeof buf, "mmag (DMMA m8n8k4) GT=%d %s cta-per-filter %s covariance-in-L2-workspace threads=%d", m->GT,
                  m->mma_mx ? "mean-in-extra-tile" : "mean-in-padding", pl.mmag_nc == 4 ? "warp-per-four-tile-columns" : pl.mmag_nc == 3 ? "warp-per-three-tile-columns" : pl.mmag_nc == 2 ? "warp-per-two-tile-columns" : "warp-per-tile-column", pl.threads);
     else if (pl.mmac)
-        snprintf(buf, sizeof buf, "mmac (DMMA m8n8k4) GT=%d %s cta-per-filter warp-per-tile-column%s B=%s threads=%d smem=%zu", m->GT,
-                 m->mma_mx ? "mean-in-extra-tile" : "mean-in-padding", pl.nhelp ? " +3-P1-helper-warps" : "", pl.b_all ? "all" : "one", pl.threads, pl.smem);
+        snprintf(buf, sizeof buf, "%s (DMMA m8n8k4) GT=%d %s cta-per-filter %s%s B=%s threads=%d smem=%zu", pl.mmact ? "mmact" : "mmac", m->GT,
+                 m->mma_mx ? "mean-in-extra-tile" : "mean-in-padding", pl.mmact ? "tile-slots-per-warp" : "warp-per-tile-column",
+                 pl.nhelp ? " +3-P1-helper-warps" : "", pl.b_all ? "all" : "one", pl.threads, pl.smem);
     else if (pl.mmar)
         snprintf(buf, sizeof buf, "mmar (DMMA m8n8k4) GT=%d register-chained warp-per-filter WPC=%d CTAs/SM=%d threads=%d smem=%zu", m->GT,
                  pl.WPC, pl.nb, pl.threads, pl.smem);
@@ -962,8 +1029,16 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
                 cp.m = mp;
                 cp.b_all = pl.b_all;
                 cp.nhelp = pl.nhelp;
-                for (int i = 0; i < 16; ++i) cp.colmap[i] = pl.colmap[i];   // GT <= 14
-                CU(mmac_launch_for(m->GT, m->mma_mx, cp, grid, pl.smem, st));
+                if (pl.mmact) {   // every phase balanced over GT + 3 warps
+                    CTParams ct{};
+                    ct.m = mp;
+                    ct.b_all = pl.b_all;
+                    if (!mmact_slots(m->GT, ct)) return fail(BILDK_EINVAL, "internal: slot table for GT=%d", m->GT);
+                    CU(m->GT == 9 ? mmact_launch<9>(ct, grid, pl.smem, st) : mmact_launch<13>(ct, grid, pl.smem, st));
+                } else {
+                    for (int i = 0; i < 16; ++i) cp.colmap[i] = pl.colmap[i];   // GT <= 14
+                    CU(mmac_launch_for(m->GT, m->mma_mx, cp, grid, pl.smem, st));
+                }
             } else
             CU(mma_launch_for(m->GT, m->mma_mx, mp, grid, pl.threads, pl.smem, st));
         } else {

@@ -45,6 +45,7 @@ CASES = [
     (64, 3, 20, 3, 0.0, 0.3, (None, [(0, -1)]), 3),             # GT=8, no padding room: mean in an extra tile column
     (70, 3, 24, 4, 0.1, 0.3, (None, [(0, -1)]), 3),             # GT=9 = 4k+1: three helper warps share P1 of the busiest scheduler's columns
     (96, 2, 16, 3, 0.2, 0.3, (None, [(0, -1)], [(10, 50)]), 3), # GT=12, 3 states: single resident propagator, TMA swaps
+    (100, 2, 14, 3, 0.2, [0.2, 0.4], (None, [(0, -1)], [(10, 50)]), 3),   # GT=13 = 4k+1 (k_mmact: slots), 3 states, d*=2
     (110, 3, 12, 2, 0.0, 0.3, (None, [(0, -1)]), 2),            # GT=14
     (120, 2, 12, 3, 0.1, 0.3, (None, [(0, -1)]), 2),            # GT=15, no padding room: tensor cores with the covariance in L2
     (130, 2, 12, 3, 0.0, 0.3, (None, [(0, -1)]), 2),            # GT=17: beyond the shared-memory limit
@@ -72,7 +73,7 @@ def test_against_c_oracle(N, d, T, P, p_nan, noise, loops, kmax):
     assert np.array_equal(got_st, got_states)          # same filters, same arithmetic
 
 
-@pytest.mark.parametrize("kernel", ["tile", "mmag", "mmag-one-column"])
+@pytest.mark.parametrize("kernel", ["tile", "mmag", "mmag-one-column", "mmac-column-warps"])
 @pytest.mark.parametrize("N", [20, 60, 100])
 def test_kernel_variants_agree(kernel, N, monkeypatch):
     """Every kernel family that can run a shape gives the oracle's answer (BILDK_KERNEL forces the family)."""
@@ -81,6 +82,11 @@ def test_kernel_variants_agree(kernel, N, monkeypatch):
     if kernel == "mmag-one-column":      # k_mmag (one tile column per warp) instead of k_mmag2 (two)
         monkeypatch.setenv("BILDK_MMAG2", "0")
         kernel = "mmag"
+    if kernel == "mmac-column-warps":    # k_mmac with helper warps instead of k_mmact (slots) where GT = 4k + 1
+        if N < 57:
+            pytest.skip("one CTA per filter starts at GT = 8")
+        monkeypatch.setenv("BILDK_MMACT", "0")
+        kernel = "mmac"
     rng = np.random.default_rng(N)
     mod = oracle_model(N, d=3)
     T, P = 25, 5
@@ -184,7 +190,7 @@ def test_dense_measurement_vector():
     assert rel_err(got, want) < TOL
 
 
-@pytest.mark.parametrize("N", [15, 19])   # 15: k_mma; 19: k_mmar (G added to the chained mean)
+@pytest.mark.parametrize("N", [15, 19, 100])   # 15: k_mma; 19: k_mmar (G added to the chained mean); 100: k_mmact
 def test_external_force_mean_offset(N):
     """G != 0 (pyx:209): constant force on the chain ends."""
     rng = np.random.default_rng(6)

@@ -19,9 +19,10 @@ import bench  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--quick", action="store_true")
 ap.add_argument("--cpu-seconds", type=float, default=4.0, help="CPU work per point (core-seconds) for the reference sample")
+ap.add_argument("--only-N", type=int, nargs="*", default=None, help="restrict the sweep to these polymer sizes")
 a = ap.parse_args()
 
-Ns = [10, 25, 50, 100, 200]
+Ns = [10, 25, 50, 100, 200] if not a.only_N else list(a.only_N)
 Ts = [100, 1000]
 Ps = [1024, 65536]
 points = [(N, T, P) for N in Ns for T in Ts for P in Ps]
