@@ -17,3 +17,5 @@ done
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_c2_$TAG.csv python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/ncu_launches_$TAG.log 2>&1
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_mmar -c 1 -f -o gpurun_out/prof_c2_mmar_$TAG python tools/run_kernel.py --workload c2 --reps 2 > gpurun_out/ncu_full_$TAG.log 2>&1
 tail -2 gpurun_out/ncu_full_$TAG.log
+timeout 900 python tools/sweep.py --only-N 100 > gpurun_out/sweep_n100_$TAG.jsonl 2> gpurun_out/sweep_n100_$TAG.md
+tail -6 gpurun_out/sweep_n100_$TAG.md
