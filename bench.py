@@ -414,7 +414,8 @@ def run_gpu_arm(args, wl, rank, world, local_rank):
         "gpu_launches": int(launches),
         "wall_s_timed_region": wall,
         "clocks": clocks,
-        "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+        # "tensor": the bounding unit is the FP64 tensor pipe (DMMA m8n8k4) - the peak below is ITS measured rate, not bf16
+        "roofline": {"bound": "tensor", "pipe": "fp64 DMMA m8n8k4 (no tcgen05 kind for f64)", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
                      "traffic": _ncu_traffic(args.workload if not args.profiles else None), "kernel": th.describe_plan(P).split(" FPC")[0].split(" WPC")[0], "kernel_ms": kavg_ms,
                      "flop_per_launch": fl, "flop_model": "4N^3 d* per frame-step + lower-order terms (SURVEY.md 8d); the DMMA kernels execute "
                                                           "3N^3 (symmetric output) on 8x8 tiles - achieved counts ALGORITHMIC flops only",
