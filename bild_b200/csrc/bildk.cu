@@ -546,23 +546,39 @@ static cudaError_t mmac_launch(const CParams& cp, dim3 grid, size_t smem, cudaSt
     }
     return e;
 }
-template <int GT>
+template <int GT, int NH, int NW>
 static cudaError_t mmact_launch(const CTParams& ct, dim3 grid, size_t smem, cudaStream_t st) {
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_mmact<GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        cudaError_t e = cudaFuncSetAttribute(k_mmact<GT, NH, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    k_mmact<GT><<<grid, 32 * (GT + 3), smem, st>>>(ct);
+    k_mmact<GT, NH, NW><<<grid, 32 * NW, smem, st>>>(ct);
     return cudaGetLastError();
+}
+// warps of k_mmact per GT: GT column warps (+ 3 P1 helpers when GT = 4k + 1), topped up to a multiple of four so that
+// the upper tiles of P2 can be dealt out evenly over the four schedulers
+static int mmact_warps(int GT) { return GT <= 8 ? 8 : (GT <= 9 ? 12 : 16); }
+static int mmact_helpers(int GT) { return (GT % 4 == 1 && GT >= 9) ? 3 : 0; }
+static cudaError_t mmact_launch_for(int GT, const CTParams& ct, dim3 grid, size_t smem, cudaStream_t st) {
+    switch (GT) {
+        case 8: return mmact_launch<8, 0, 8>(ct, grid, smem, st);
+        case 9: return mmact_launch<9, 3, 12>(ct, grid, smem, st);
+        case 10: return mmact_launch<10, 0, 16>(ct, grid, smem, st);
+        case 11: return mmact_launch<11, 0, 16>(ct, grid, smem, st);
+        case 12: return mmact_launch<12, 0, 16>(ct, grid, smem, st);
+        case 13: return mmact_launch<13, 3, 16>(ct, grid, smem, st);
+        case 14: return mmact_launch<14, 0, 16>(ct, grid, smem, st);
+    }
+    return cudaErrorInvalidValue;
 }
 // slot table of k_mmact: the upper tiles (ti <= c), last column first, rows ascending, dealt out to the GT + 3 warps in
 // order as SEGMENTS (consecutive tile rows of one column), at most two per warp; the first (total mod warps) warps may
 // take one slot more.  Pieces that would have been a third segment go to the lightest single-segment warps.
 // Warp w runs on scheduler w % 4.
 static bool mmact_slots(int GT, CTParams& ct) {
-    const int nw = GT + 3, total = GT * (GT + 1) / 2, base = total / nw, rem = total % nw;
+    const int nw = mmact_warps(GT), total = GT * (GT + 1) / 2, base = total / nw, rem = total % nw;
     struct Seg { int c, lo, n; };
     std::vector<std::vector<Seg>> warps(1);
     std::vector<Seg> extra;
@@ -588,7 +604,7 @@ static bool mmact_slots(int GT, CTParams& ct) {
     for (const Seg& sg : extra) {
         int best = -1;
         for (int w = 0; w < nw; ++w)
-            if (warps[w].size() < 2 && load(warps[w]) + sg.n <= 6 && (best < 0 || load(warps[w]) < load(warps[best]))) best = w;
+            if (warps[w].size() < 2 && load(warps[w]) + sg.n <= MMACT_MAXS && (best < 0 || load(warps[w]) < load(warps[best]))) best = w;
         if (best < 0) return false;
         warps[best].push_back(sg);
     }
@@ -604,7 +620,7 @@ static bool mmact_slots(int GT, CTParams& ct) {
             if (sgi == 0) ct.nsegA[w] = static_cast<unsigned char>(sg.n);
         }
         ct.nslot[w] = static_cast<unsigned char>(k);
-        if (k == 0 || k > 6) return false;
+        if (k == 0 || k > MMACT_MAXS) return false;
     }
     return ct.slot_ti[0][0] == 0 && ct.slot_c[0][0] == GT - 1;
 }
@@ -726,7 +742,10 @@ static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
             // only has to balance P2 (weight c + 1); otherwise it balances P1 + P2 (weight GT + c + 1)
             pl.nhelp = (GT % 4 == 1 && GT >= 9 && !m->mma_mx && env_int("BILDK_MMAC_HELPERS", 1)) ? 3 : 0;
             pl.threads = 32 * (GT + pl.nhelp);
-            pl.mmact = pl.nhelp == 3 && (GT == 9 || GT == 13) && env_int("BILDK_MMACT", 1);
+            // slots need the mean in the padding columns; measured against k_mmac (T=300, 2960 filters): GT=13 +7 %, GT=14 +13 %,
+            // GT=8/10/11/12 -3..-14 % (their column warps are already balanced four-by-four)
+            pl.mmact = !m->mma_mx && (GT == 9 || GT == 13 || GT == 14) && env_int("BILDK_MMACT", 1);
+            if (pl.mmact) { pl.nhelp = mmact_helpers(GT); pl.threads = 32 * mmact_warps(GT); }
             // column -> warp: longest-processing-time first onto the four schedulers (warp i runs on scheduler i % 4)
             double load[4] = {0, 0, 0, 0};
             int slots[4], used[4] = {0, 0, 0, 0};
@@ -978,7 +997,7 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
                 CU(cudaMemcpy(m->meta2.p, pt.data(), P * sizeof(int), cudaMemcpyHostToDevice));
                 gp.prof_traj = m->meta2.p;
             }
-            const int nc = std::min(P, ((pl.mmag_nc == 4 && env_int("BILDK_MMAG2_MINB", 2) >= 3) ? 3 : 2) * m->n_sm);
+            const int nc = std::min(P, 2 * m->n_sm);
             const size_t wsz = static_cast<size_t>(2) * m->NPm * m->LDCm;
             int rc = m->work.reserve(wsz * nc * dstar);
             if (rc) return rc;
@@ -987,13 +1006,10 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
             auto waste = [&](int chv) { return ((m->GT + chv - 1) / chv) * chv; };   // padded tile rows per column
             const int ch = env_int("BILDK_MMAG_CH", m->GT <= 16 ? 8 : ((m->GT <= 28 && waste(6) <= waste(4)) ? 6 : 4));
             if (pl.mmag_nc == 4) {        // <= 8 warps per CTA
-                if (env_int("BILDK_MMAG2_MINB", 2) >= 3) k_mmag2<4, 4, 256, 3><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);
-                else k_mmag2<4, 4, 256, 2><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);
+                k_mmag2<4, 4, 256, 2><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);
             } else if (pl.mmag_nc == 3) {   // <= 11 warps per CTA
                 if (pl.threads <= 288) k_mmag2<4, 3, 288, 2><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);
                 else k_mmag2<4, 3, 352, 2><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);
-            } else if (pl.mmag_nc == 2 && env_int("BILDK_MMAG2_CH", 4) >= 8) {
-                k_mmag2<8, 2, 512, 1><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);
             } else if (pl.mmag_nc == 2) {
                 if (pl.threads <= 448) k_mmag2<4, 2, 448, 2><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);
                 else k_mmag2<4, 2, 512, 2><<<dim3(nc, dstar), pl.threads, pl.smem, st>>>(gp, m->GT, m->mma_mx ? 1 : 0);
@@ -1034,7 +1050,7 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
                     ct.m = mp;
                     ct.b_all = pl.b_all;
                     if (!mmact_slots(m->GT, ct)) return fail(BILDK_EINVAL, "internal: slot table for GT=%d", m->GT);
-                    CU(m->GT == 9 ? mmact_launch<9>(ct, grid, pl.smem, st) : mmact_launch<13>(ct, grid, pl.smem, st));
+                    CU(mmact_launch_for(m->GT, ct, grid, pl.smem, st));
                 } else {
                     for (int i = 0; i < 16; ++i) cp.colmap[i] = pl.colmap[i];   // GT <= 14
                     CU(mmac_launch_for(m->GT, m->mma_mx, cp, grid, pl.smem, st));

@@ -1,11 +1,12 @@
-// k_mmact - k_mmac (one CTA per filter, covariance in shared memory, 56 < N <= 112) for GT = 4k + 1 tile columns
-// (N = 65..72 and 97..104: BASELINE configs[2], N = 100) with the work of EVERY phase balanced over 16 warps.
+// k_mmact - k_mmac (one CTA per filter, covariance in shared memory, 56 < N <= 112, mean in the padding columns) with
+// the work of EVERY phase balanced over the warps (BASELINE configs[2], N = 100: GT = 13 tile columns, 16 warps).
 //
 // ncu of k_mmac<13> on configs[2] (profiles/r01_ncu_c3_mmac_v9.txt): the tensor pipe is 65 % active and 37 % of the
 // stall samples are CTA barriers.  Per frame the phases are separated by barriers, so each phase must be balanced on
 // its own, and with one warp per tile column it is not:
-//   P1   every column costs GT tiles, but 13 column warps sit 4/3/3/3 on the four schedulers  -> helper warps (as in
-//        k_mmac): warps 13, 14, 15 take the first GT/4 tile rows of the columns of warps 0, 4, 8: 43/42/42/42 tiles;
+//   P1   every column costs GT tiles, but 13 column warps sit 4/3/3/3 on the four schedulers  -> for GT = 4k + 1 helper
+//        warps (as in k_mmac): warps 13, 14, 15 take the first GT/4 tile rows of the columns of warps 0, 4, 8:
+//        43/42/42/42 tiles (NH = 3; other GT run without helpers, NH = 0);
 //   P2   column c has c + 1 upper tiles: the warp of the last column works 13 x longer than that of the first and
 //        runs alone at the end of the phase; the rank-1 update and the write-back inherit the same imbalance while
 //        the tensor pipe idles.  Every upper tile (ti, c) is independent given the published columns of C', so here
@@ -20,10 +21,12 @@
 
 namespace bildk {
 
+constexpr int MMACT_MAXS = 7;   // most slots (upper tiles) one warp can hold
+
 struct CTParams {
     MParams m;
     int b_all;                    // all S propagators resident
-    unsigned char nslot[16];      // slots of every warp (<= 6): segment A = slots [0, nsegA), segment B the rest
+    unsigned char nslot[16];      // slots of every warp (<= MMACT_MAXS): segment A = slots [0, nsegA), segment B the rest
     unsigned char nsegA[16];      // ... each segment = consecutive tile rows of one tile column
     unsigned char slot_ti[16][8]; // tile row / column of every slot; slot 0 of warp 0 is tile (0, GT-1)
     unsigned char slot_c[16][8];
@@ -33,7 +36,7 @@ struct CTParams {
 // a segment share their B fragment.  (One A and one B fragment per DMMA - independent slots - saturates the
 // shared-memory pipe: 4 wavefronts per DMMA is exactly the tensor pipe's rate; measured 0.51 instead of 0.80.)
 template <int NA, int NB, int LDA, int LDBB>
-__device__ __forceinline__ void mmact_p2(double (&acc)[6][2], const double* __restrict__ ApA, const double* __restrict__ BpA,
+__device__ __forceinline__ void mmact_p2(double (&acc)[MMACT_MAXS][2], const double* __restrict__ ApA, const double* __restrict__ BpA,
                                          const double* __restrict__ ApB, const double* __restrict__ BpB, int NK) {
 #pragma unroll 1
     for (int k0 = 0; k0 < NK; k0 += 4) {
@@ -51,13 +54,16 @@ __device__ __forceinline__ void mmact_p2(double (&acc)[6][2], const double* __re
     }
 }
 
-template <int GT>
-__global__ void __maxnreg__(128) k_mmact(const __grid_constant__ CTParams cp) {
-    static_assert(GT % 4 == 1 && GT >= 9, "k_mmact is the GT = 4k + 1 variant");
+// NW warps in total: GT column warps for P1 (+ NH helpers); warps beyond GT + NH only join P2 / update / write-back
+template <int GT, int NH, int NW>
+__global__ void __maxnreg__((16384 / (32 * ((NW + 3) / 4))) / 8 * 8 > 160 ? 160 : (16384 / (32 * ((NW + 3) / 4))) / 8 * 8)
+k_mmact(const __grid_constant__ CTParams cp) {
+    static_assert(NW >= GT + NH && NW <= 16, "warp budget");
+    static_assert(NH == 0 || (NH == 3 && GT % 4 == 1 && GT >= 9), "helper warps are the GT = 4k + 1 variant");
     constexpr int TJM = GT - 1;                   // the mean rides in the padding columns of the last tile column
     constexpr int NPm = 8 * GT, LDB = NPm + 4, LDC = 8 * GT + 4;
     constexpr int MATB = NPm * LDB, MATG = NPm * NPm;
-    constexpr int HR = GT / 4;
+    constexpr int HR = NH ? GT / 4 : 0;
     const MParams& mp = cp.m;
     const KParams& p = mp.k;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -69,16 +75,17 @@ __global__ void __maxnreg__(128) k_mmact(const __grid_constant__ CTParams cp) {
     const int e_sub = blockIdx.y;
     const int N = p.N, D = p.D, NK = mp.NK;
     // P1 roles: warps 0..GT-1 own column wid; warps 0, 4, 8 are helped by warps GT, GT+1, GT+2
-    const bool helper = wid >= GT;
-    const bool helped = !helper && (wid & 3) == 0 && (wid >> 2) < 3;
+    const bool helper = NH > 0 && wid >= GT && wid < GT + NH;
+    const bool p1idle = wid >= GT + NH;                      // no P1 work: barriers only
+    const bool helped = NH > 0 && !helper && (wid & 3) == 0 && (wid >> 2) < NH;
     const int pc = helper ? 4 * (wid - GT) : wid;           // P1 column
     const int pair_id = 1 + (helper ? wid - GT : (wid >> 2));
     // P2 / update / write-back slots
     const int nt = cp.nslot[wid], nA = cp.nsegA[wid];
-    int sti[6], sc[6];
+    int sti[MMACT_MAXS], sc[MMACT_MAXS];
     bool meanw = false;                                     // holds a tile of the last column: carries part of the mean
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
+    for (int i = 0; i < MMACT_MAXS; ++i) {
         sti[i] = cp.slot_ti[wid][i];
         sc[i] = cp.slot_c[wid][i];
         meanw |= (i < nt) && sc[i] == GT - 1;
@@ -154,13 +161,13 @@ __global__ void __maxnreg__(128) k_mmact(const __grid_constant__ CTParams cp) {
         const double* Bs = Bsm + (cp.b_all ? s * MATB : 0);
         const double* Gsrc = ((t == 0) ? mp.C0m : mp.Sigm) + static_cast<size_t>(MATG) * s + g * NPm + 2 * c4;
 
-        if (t > 0) {
+        if (t > 0 && !p1idle) {
             // ---------------- P1: T[:, pc] = B_s Caug[:, pc], in place (MSRouse_logL.pyx:206-241, first product)
             double acc[GT][2];
             const double* Ap = Bs + g * LDB + c4;
             const double* Bp = Cb + c4 * LDC + 8 * pc + g;
             if (helper) {
-                mmac_p1<GT, 0, HR, LDB, LDC>(acc, Ap, Bp, NK);
+                mmac_p1<GT, 0, (HR > 0 ? HR : 1), LDB, LDC>(acc, Ap, Bp, NK);
                 asm volatile("bar.sync %0, 64;" ::"r"(pair_id) : "memory");   // owner and helper have read column pc
 #pragma unroll
                 for (int ti = 0; ti < HR; ++ti)
@@ -180,9 +187,9 @@ __global__ void __maxnreg__(128) k_mmact(const __grid_constant__ CTParams cp) {
             }
         }
         // slots start at Sig (t > 0) / hold C0 (t = 0); the global loads overlap the barrier
-        double acc[6][2];
+        double acc[MMACT_MAXS][2];
 #pragma unroll
-        for (int i = 0; i < 6; ++i)
+        for (int i = 0; i < MMACT_MAXS; ++i)
             if (i < nt) {
                 const double2 v = __ldg(reinterpret_cast<const double2*>(Gsrc + 8 * sti[i] * NPm + 8 * sc[i]));
                 acc[i][0] = v.x;
@@ -205,12 +212,13 @@ __global__ void __maxnreg__(128) k_mmact(const __grid_constant__ CTParams cp) {
             const double* BpB = Bs + c4 * LDB + 8 * cp.slot_c[wid][sB] + g;
             switch (nA * 8 + (nt - nA)) {   // instantiated per shape: no predicates in the hot loop
 #define P2S(A_, B_) case A_ * 8 + B_: mmact_p2<A_, B_, LDC, LDB>(acc, ApA, BpA, ApB, BpB, NK); break;
-                P2S(1, 0) P2S(1, 1) P2S(1, 2) P2S(1, 3) P2S(1, 4) P2S(1, 5)
-                P2S(2, 0) P2S(2, 1) P2S(2, 2) P2S(2, 3) P2S(2, 4)
-                P2S(3, 0) P2S(3, 1) P2S(3, 2) P2S(3, 3)
-                P2S(4, 0) P2S(4, 1) P2S(4, 2)
-                P2S(5, 0) P2S(5, 1)
-                P2S(6, 0)
+                P2S(1, 0) P2S(1, 1) P2S(1, 2) P2S(1, 3) P2S(1, 4) P2S(1, 5) P2S(1, 6)
+                P2S(2, 0) P2S(2, 1) P2S(2, 2) P2S(2, 3) P2S(2, 4) P2S(2, 5)
+                P2S(3, 0) P2S(3, 1) P2S(3, 2) P2S(3, 3) P2S(3, 4)
+                P2S(4, 0) P2S(4, 1) P2S(4, 2) P2S(4, 3)
+                P2S(5, 0) P2S(5, 1) P2S(5, 2)
+                P2S(6, 0) P2S(6, 1)
+                P2S(7, 0)
 #undef P2S
                 default: break;
             }
@@ -255,9 +263,9 @@ __global__ void __maxnreg__(128) k_mmact(const __grid_constant__ CTParams cp) {
             }
         };
         // prior mean of the slots in the last column: read before the publish barrier as well (tile (ti, GT-1) of T)
-        double mp0[6], mp1[6];
+        double mp0[MMACT_MAXS], mp1[MMACT_MAXS];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
+        for (int i = 0; i < MMACT_MAXS; ++i) {
             mp0[i] = mp1[i] = 0.0;
             if (i < nt && sc[i] == GT - 1) mean_prior(sti[i], mp0[i], mp1[i]);
         }
@@ -270,7 +278,7 @@ __global__ void __maxnreg__(128) k_mmact(const __grid_constant__ CTParams cp) {
                 const int jz = z ? j1 : j0;
                 const int tjz = jz >> 3, cj = jz & 7;
 #pragma unroll
-                for (int i = 0; i < 6; ++i)
+                for (int i = 0; i < MMACT_MAXS; ++i)
                     if (i < nt) {
                         if (sc[i] == tjz && c4 == (cj >> 1)) colb[z * NPm + 8 * sti[i] + g] = (cj & 1) ? acc[i][1] : acc[i][0];
                         if (sc[i] > tjz && sti[i] == tjz && g == cj)
@@ -279,14 +287,14 @@ __global__ void __maxnreg__(128) k_mmact(const __grid_constant__ CTParams cp) {
             }
         }
         __syncthreads();   // T no longer needed; published columns visible
-        double kr[6];
+        double kr[MMACT_MAXS];
         if (is_valid) {
             const double cw_j0 = fma(w1, colb[NPm + j0], w0 * colb[j0]);
             const double cw_j1 = fma(w1, colb[NPm + j1], w0 * colb[j1]);
             const double S = fma(w1, cw_j1, fma(w0, cw_j0, s2));
             const double Sinv = __drcp_rn(S);                               // pyx:63
 #pragma unroll
-            for (int i = 0; i < 6; ++i)
+            for (int i = 0; i < MMACT_MAXS; ++i)
                 if (i < nt) {
                     kr[i] = fma(w1, colb[NPm + 8 * sti[i] + g], w0 * colb[8 * sti[i] + g]) * Sinv;   // pyx:66-67
                     const double2 u = *reinterpret_cast<const double2*>(colb + 8 * sc[i] + 2 * c4);
@@ -311,7 +319,7 @@ __global__ void __maxnreg__(128) k_mmact(const __grid_constant__ CTParams cp) {
         // ---------------- C+ written back: upper pairs, mirrored below the diagonal; M+ in the padding of the last column
         if (t + 1 < T) {
 #pragma unroll
-            for (int i = 0; i < 6; ++i)
+            for (int i = 0; i < MMACT_MAXS; ++i)
                 if (i < nt) {
                     const int ti = sti[i], c = sc[i];
                     double v0 = acc[i][0], v1 = acc[i][1];

@@ -43,7 +43,9 @@ CASES = [
     (2, 3, 25, 6, 0.1, 0.5, (None, [(0, -1, 0.5)]), 2),         # N < d: catch-all kernel
     (60, 3, 30, 4, 0.1, 0.3, (None, [(0, -1)]), 4),             # GT=8: one CTA per filter, one warp per tile column
     (64, 3, 20, 3, 0.0, 0.3, (None, [(0, -1)]), 3),             # GT=8, no padding room: mean in an extra tile column
-    (70, 3, 24, 4, 0.1, 0.3, (None, [(0, -1)]), 3),             # GT=9 = 4k+1: three helper warps share P1 of the busiest scheduler's columns
+    (68, 3, 24, 4, 0.1, 0.3, (None, [(0, -1)]), 3),             # GT=9 = 4k+1 (k_mmact: 12 warps, three P1 helper warps, tile segments)
+    (70, 3, 24, 4, 0.1, 0.3, (None, [(0, -1)]), 3),             # GT=9, no padding room for the mean: k_mmac with an extra tile column
+    (108, 3, 12, 2, 0.1, 0.3, (None, [(0, -1)]), 2),            # GT=14 (k_mmact without helpers, 7 slots per warp)
     (96, 2, 16, 3, 0.2, 0.3, (None, [(0, -1)], [(10, 50)]), 3), # GT=12, 3 states: single resident propagator, TMA swaps
     (100, 2, 14, 3, 0.2, [0.2, 0.4], (None, [(0, -1)], [(10, 50)]), 3),   # GT=13 = 4k+1 (k_mmact: slots), 3 states, d*=2
     (110, 3, 12, 2, 0.0, 0.3, (None, [(0, -1)]), 2),            # GT=14
