@@ -45,6 +45,7 @@ SYMBOLS = {
     "bildk_measure_fp64_peak": (ctypes.c_int, [ctypes.c_int, c_double_p, c_double_p]),
     "bildk_launch_count": (ctypes.c_longlong, []),
     "bildk_describe_plan": (ctypes.c_char_p, [ctypes.c_void_p, ctypes.c_int]),
+    "bildk_debug_tables": (ctypes.c_int, [ctypes.c_int] * 4 + [c_uint8_p]),
 }
 
 _lib = None

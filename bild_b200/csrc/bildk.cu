@@ -930,6 +930,27 @@ extern "C" const char* bildk_describe_plan(bildk_traj_t t, int P) {
     return t->plan.c_str();
 }
 
+extern "C" int bildk_debug_tables(int kernel, int GT, int r, int ncols, unsigned char* out) {
+    if (!out) return fail(BILDK_EINVAL, "out is NULL");
+    if (kernel == 0) {
+        if (GT < 1 || GT > 4 || r < 1 || r > 4 || ncols < 1 || ncols > 4) return fail(BILDK_EINVAL, "k_mmar tables need GT in 1..4, r in 1..4, ncols in 1..4");
+        mmar_tables(GT, r, ncols, out, out + 8);
+        return 12;
+    }
+    if (kernel == 1) {
+        if (GT < 8 || GT > 14) return fail(BILDK_EINVAL, "k_mmact tables need GT in 8..14");
+        CTParams ct{};
+        if (!mmact_slots(GT, ct)) return fail(BILDK_EINVAL, "internal: slot table for GT=%d", GT);
+        for (int w = 0; w < 16; ++w) {
+            out[18 * w] = ct.nslot[w];
+            out[18 * w + 1] = ct.nsegA[w];
+            for (int i = 0; i < 8; ++i) { out[18 * w + 2 + 2 * i] = ct.slot_ti[w][i]; out[18 * w + 3 + 2 * i] = ct.slot_c[w][i]; }
+        }
+        return 288;
+    }
+    return fail(BILDK_EINVAL, "unknown kernel %d", kernel);
+}
+
 // Core launcher on device-resident profile arrays.  Trajectory metadata arrays are device pointers.
 static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const double* const* d_x,
                          const uint8_t* const* d_valid, const int* d_T, const int* d_first,

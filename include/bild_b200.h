@@ -156,6 +156,16 @@ int bildk_measure_fp64_peak(int device, double *dfma_tflops, double *dmma_tflops
 long long   bildk_launch_count(void);
 const char *bildk_describe_plan(bildk_traj_t traj, int P);
 
+/* Diagnostics (host only, no GPU needed): the work-distribution tables two of the kernels are launched with, so that
+ * their invariants can be tested on a CPU.
+ *   kernel 0 (k_mmar, GT <= 4 tile columns, r = N - 8 (GT - 1) in 1..4 covariance rows in the last row block, ncols mean
+ *     columns): out[0..7] = buffer row read by B-fragment lane g for the last tile column, out[8..11] = buffer row of
+ *     mean column q (unused entries repeat the zero row).
+ *   kernel 1 (k_mmact, GT in 8..14): for each of 16 warps w: out[18 w] = number of slots, out[18 w + 1] = slots in the
+ *     first segment, out[18 w + 2 + 2 i] / out[18 w + 3 + 2 i] = tile row / tile column of slot i (i < 8).
+ * Returns the number of bytes written (12 or 288), or a negative error code. */
+int bildk_debug_tables(int kernel, int GT, int r, int ncols, unsigned char *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -164,3 +164,71 @@ def test_models_host_side():
     fm.clear_memo()
     assert fm.logL(Loopingprofile([1, 1, 0, 0]), traj) == v
     assert len(fm.trajectory_from_loopingprofile(Loopingprofile([0, 0, 0, 1, 1, 1]))) == 6
+
+
+def test_register_chained_kernel_tables():
+    """Host tables of k_mmar (bildk_debug_tables, no GPU): for every admissible (GT, r, ncols) the mean rows and the
+    zero row are distinct spare rows of the last tile-row block, the covariance rows sit in the even B-fragment slots,
+    and the placement keeps the 128-bit (lane pairs: rows of different parity) and 64-bit (lane quads: rows distinct
+    mod 4) fragment loads free of bank conflicts for the d = 3 shapes of the BASELINE workloads (with fewer mean columns
+    several unused slots share the single zero row, which cannot differ in parity from all of their partners)."""
+    from bild_b200 import _lib
+    lib = _lib.load()
+    out = np.zeros(12, dtype=np.uint8)
+    for GT in (1, 2, 3, 4):
+        base = 8 * (GT - 1)
+        for r in (1, 2, 3, 4):
+            for ncols in (1, 2, 3, 4):
+                assert lib.bildk_debug_tables(0, GT, r, ncols, _lib.ptr(out, _lib.c_uint8_p)) == 12
+                lastrow, mrow = out[:8].astype(int), out[8:].astype(int)
+                spare = set(range(base + r, base + 8))
+                m = list(mrow[:ncols])
+                assert len(set(m)) == ncols and set(m) <= spare                      # mean rows: distinct spare rows
+                for i in range(4):
+                    assert lastrow[2 * i + 1] == (m[i] if i < ncols else lastrow[2 * i + 1])
+                    if i < r:
+                        assert lastrow[2 * i] == base + i                             # covariance rows in the even slots
+                unused = [lastrow[2 * i] for i in range(r, 4)] + [lastrow[2 * i + 1] for i in range(ncols, 4)]
+                if unused:
+                    z = set(unused)
+                    assert len(z) == 1 and z <= spare and not (z & set(m))          # one zero row, never a mean row
+                # bank conflicts (row stride == 8 mod 16 doubles, column bit 2 flipped by (row >> 1) & 1)
+                pair_conf = sum(1 for i in range(4) if lastrow[2 * i] != lastrow[2 * i + 1] and (lastrow[2 * i] - lastrow[2 * i + 1]) % 2 == 0)
+                quad_conf = sum(1 for h in range(2) for a in range(4) for b in range(a + 1, 4)
+                                if lastrow[4 * h + a] != lastrow[4 * h + b] and (lastrow[4 * h + a] - lastrow[4 * h + b]) % 4 == 0)
+                if (r, ncols) in ((4, 3), (2, 3), (1, 3)):    # shapes of the BASELINE workloads (d = 3; N = 20, 10 / 50, 25)
+                    assert pair_conf == 0 and quad_conf == 0, (GT, r, ncols, lastrow)
+    assert lib.bildk_debug_tables(0, 5, 1, 1, _lib.ptr(out, _lib.c_uint8_p)) < 0      # out of the kernel's range
+
+
+def test_tile_slot_tables():
+    """Host tables of k_mmact: every upper tile (ti <= c) exactly once, at most MAXS = 7 slots and two segments
+    (consecutive tile rows of one column) per warp, tile (0, GT-1) first on warp 0, the four schedulers (warp % 4)
+    within three tiles of each other."""
+    from bild_b200 import _lib
+    lib = _lib.load()
+    out = np.zeros(288, dtype=np.uint8)
+    for GT in range(8, 15):
+        assert lib.bildk_debug_tables(1, GT, 0, 0, _lib.ptr(out, _lib.c_uint8_p)) == 288
+        t = out.reshape(16, 18).astype(int)
+        nw = 8 if GT == 8 else (12 if GT == 9 else 16)
+        seen = set()
+        sched = [0, 0, 0, 0]
+        for w in range(16):
+            n, na = t[w, 0], t[w, 1]
+            if w >= nw:
+                assert n == 0
+                continue
+            assert 1 <= n <= 7 and 1 <= na <= n
+            slots = [(t[w, 2 + 2 * i], t[w, 3 + 2 * i]) for i in range(n)]
+            for seg in (slots[:na], slots[na:]):
+                if seg:
+                    assert len({c for _, c in seg}) == 1                              # one column per segment
+                    assert [ti for ti, _ in seg] == list(range(seg[0][0], seg[0][0] + len(seg)))   # consecutive rows
+            for ti, c in slots:
+                assert 0 <= ti <= c < GT and (ti, c) not in seen
+                seen.add((ti, c))
+            sched[w % 4] += n
+        assert len(seen) == GT * (GT + 1) // 2
+        assert (t[0, 2], t[0, 3]) == (0, GT - 1)
+        assert max(sched) - min(sched) <= 3, (GT, sched)      # e.g. GT = 13: 24 / 23 / 23 / 21 of 91 tiles
