@@ -23,7 +23,7 @@ from scipy.special import gammaln, xlogy
 
 from .util import Loopingprofile
 
-__all__ = ["Dirichlet", "CFC", "FixedkSampler"]
+__all__ = ["Dirichlet", "CFC", "FixedkSampler", "drive"]
 
 
 def _lse(a, axis=None, mask=None, keepdims=False):
@@ -38,6 +38,21 @@ def _lse(a, axis=None, mask=None, keepdims=False):
     if not keepdims:
         out = np.squeeze(out, axis=axis) if axis is not None else out.reshape(())
     return out
+
+
+def drive(gen, evaluate):
+    """
+    Run a likelihood-requesting generator to completion: every ``(ss, thetas)`` it yields is answered with
+    ``evaluate(ss, thetas)``; returns the generator's return value.  The AMIS code is written as generators that
+    *yield* their likelihood batches, so that one driver can serve many trajectories from one fused GPU launch
+    (`bild_b200.dataset.sample_many`) without threads; the public, synchronous methods drive them with this.
+    """
+    try:
+        request = next(gen)
+        while True:
+            request = gen.send(evaluate(*request))
+    except StopIteration as stop:
+        return stop.value
 
 
 # ------------------------------------------------------------------------------------------------ Dirichlet
@@ -237,16 +252,19 @@ class FixedkSampler:
         pass
 
     def __init__(self, traj, model, k, N=100, concentration_brake=1e-2, polarization_brake=1e-3,
-                 max_fev=20000, max_fcomplete=1000):
+                 max_fev=20000, max_fcomplete=1000, _defer=False):
+        # _defer (internal): do not evaluate the exhaustive sample here; the caller runs `start_gen()` itself
         self.k, self.N = k, N
         self.brakes = (concentration_brake, polarization_brake)
         self.max_fev, self.max_fcomplete = max_fev, max_fcomplete
         self.exhausted = False
         self.traj, self.model = traj, model
 
+        self._started = False
         if self.k >= len(self.traj):      # more switches than frames: unidentifiable by construction
             self.evidences = [(-np.inf, 1e-10, np.inf)]
             self.exhausted = True
+            self._started = True
             return
 
         self.dirichlet = Dirichlet()
@@ -256,8 +274,16 @@ class FixedkSampler:
         self.logprior = np.sum(np.log(np.arange(self.k) + 1)) - self.cfc.N_total(self.k, log=True)
         self.samples = []       # dicts with 'ss', 'thetas', 'logLs' [, 'logδs', 'log_weights', 'cur_log_proposal']
         self.evidences = []     # (logev, dlogev, KL) per step
+        if not _defer:
+            drive(self.start_gen(), self.logL)
+
+    def start_gen(self):
+        """Generator form of the construction-time work: the exhaustive evaluation if the space is small enough."""
+        if self._started:
+            return
+        self._started = True
         try:
-            self.fix_exhaustive()
+            yield from self.fix_exhaustive_gen()
         except FixedkSampler.ExhaustionImpractical:
             pass
 
@@ -310,6 +336,9 @@ class FixedkSampler:
 
     # ------------------------------------------------------------------ exhaustive evaluation for tiny spaces
     def fix_exhaustive(self):
+        return drive(self.fix_exhaustive_gen(), self.logL)
+
+    def fix_exhaustive_gen(self):
         """
         If there are at most ``min(max_fcomplete, max_fev)`` profiles with ``k`` switches, evaluate all of
         them (one batch) and compute the evidence exactly as the mean likelihood under the uniform prior;
@@ -333,7 +362,7 @@ class FixedkSampler:
         thetas = np.repeat(thetas, n_ss, axis=0)
 
         sample = {"ss": ss, "thetas": thetas}
-        sample["logLs"] = self.logL(ss, thetas)
+        sample["logLs"] = yield (ss, thetas)              # the one likelihood batch of this sampler
         self.samples.append(sample)
 
         top = np.max(sample["logLs"])
@@ -348,6 +377,10 @@ class FixedkSampler:
     # ------------------------------------------------------------------ one AMIS iteration
     def step(self):
         """Returns False (and does nothing) if the sampler is exhausted, True otherwise."""
+        return drive(self.step_gen(), self.logL)
+
+    def step_gen(self):
+        """Generator form of `step`: yields the ``(ss, thetas)`` batch whose likelihoods it needs."""
         if self.exhausted:
             return False
         cur = self.parameters[-1]
@@ -364,7 +397,7 @@ class FixedkSampler:
 
         # new sample: RNG order Dirichlet -> CFC, as the reference
         new = {"ss": self.dirichlet.sample(cur[0], self.N), "thetas": self.cfc.sample(cur[1], self.N)}
-        new["logLs"] = self.logL(new["ss"], new["thetas"])
+        new["logLs"] = yield (new["ss"], new["thetas"])
         all_lp = self.log_proposal_multi(self.parameters, new["ss"], new["thetas"])   # past proposals and the current one
         new["cur_log_proposal"] = all_lp[-1]
         new["logδs"] = _lse(all_lp, axis=0)

@@ -8,11 +8,11 @@ each `FixedkSampler` go to the GPU when the model is a `bild_b200.models.MultiSt
 import numpy as np
 from tqdm.auto import tqdm
 
-from .amis import FixedkSampler, _lse
+from .amis import FixedkSampler, _lse, drive
 from .choicesampler import ChoiceSampler
 from .trajectory import make_Trajectory
 
-__all__ = ["sample", "SamplingResults"]
+__all__ = ["sample", "sample_gen", "SamplingResults"]
 
 
 def sample(traj, model, dE=0, init_runs=20, certainty_in_k=0.99, k_lookahead=2, k_max=20,
@@ -44,6 +44,21 @@ def sample(traj, model, dE=0, init_runs=20, certainty_in_k=0.99, k_lookahead=2, 
     -------
     SamplingResults
     """
+    traj = make_Trajectory(traj)
+    # every likelihood batch of the run goes through FixedkSampler.logL of a throw-away sampler bound to (traj, model)
+    probe = FixedkSampler.__new__(FixedkSampler)
+    probe.traj, probe.model = traj, model
+    return drive(sample_gen(traj, model, dE=dE, init_runs=init_runs, certainty_in_k=certainty_in_k, k_lookahead=k_lookahead,
+                            k_max=k_max, sampler_kw=sampler_kw, choice_kw=choice_kw, show_progress=show_progress), probe.logL)
+
+
+def sample_gen(traj, model, dE=0, init_runs=20, certainty_in_k=0.99, k_lookahead=2, k_max=20,
+               sampler_kw={}, choice_kw={}, show_progress=False):
+    """
+    Generator form of `sample` (same arguments): yields every ``(ss, thetas)`` batch whose likelihoods the run needs
+    and expects them to be sent back; returns the `SamplingResults`.  `sample` drives it with the model's own batched
+    likelihood; `bild_b200.dataset.sample_many` drives many of them and fuses their batches into one launch.
+    """
     bar = tqdm(disable=not show_progress)
     traj = make_Trajectory(traj)
     samplers = []
@@ -51,7 +66,7 @@ def sample(traj, model, dE=0, init_runs=20, certainty_in_k=0.99, k_lookahead=2, 
     state = {"fresh": False}
 
     def take_step(k):
-        if samplers[k].step():            # no-op for exhausted samplers
+        if (yield from samplers[k].step_gen()):            # no-op for exhausted samplers
             bar.update()
             for key in log:
                 log[key].append(None)
@@ -60,9 +75,11 @@ def sample(traj, model, dE=0, init_runs=20, certainty_in_k=0.99, k_lookahead=2, 
 
     def new_sampler(k):
         assert k == len(samplers)
-        samplers.append(FixedkSampler(traj, model, k=k, **sampler_kw))
+        fresh = FixedkSampler(traj, model, k=k, _defer=True, **sampler_kw)
+        yield from fresh.start_gen()
+        samplers.append(fresh)
         for _ in range(init_runs):
-            take_step(k)
+            yield from take_step(k)
 
     def next_k():
         k_new = len(samplers)
@@ -95,9 +112,9 @@ def sample(traj, model, dE=0, init_runs=20, certainty_in_k=0.99, k_lookahead=2, 
     try:
         while running:
             if k_next < len(samplers):
-                take_step(k_next)
+                yield from take_step(k_next)
             elif k_next == len(samplers):
-                new_sampler(k_next)
+                yield from new_sampler(k_next)
             else:  # pragma: no cover
                 raise RuntimeError("Trying to sample outside of existing range; this is a bug")
             k_next = next_k()

@@ -8,11 +8,12 @@ per step - far too few to fill a B200.  `sample_many` runs all state machines co
 pending batches of all trajectories into ONE multi-trajectory launch per round (C ABI
 ``bildk_logl_runs_multi``): SURVEY.md section 8(f) rank 2, BASELINE.json configs[3].
 
-Determinism: every trajectory owns its numpy RNG stream.  The state machines are cooperative (exactly one
-runs at a time, fixed round-robin order) and the global ``np.random`` state is swapped at every hand-over,
-so trajectory ``i`` consumes exactly the random numbers it would consume in
-``np.random.seed(seeds[i]); sample(trajs[i], model, ...)`` run on its own - the results are identical to
-the sequential runs, independent of how many trajectories share a launch or a GPU.
+Determinism: every trajectory owns its numpy RNG stream.  The state machines are generators (`core.sample_gen`
+yields every likelihood batch it needs); exactly one runs at a time, in a fixed round-robin order, and the global
+``np.random`` state is swapped at every hand-over, so trajectory ``i`` consumes exactly the random numbers it would
+consume in ``np.random.seed(seeds[i]); sample(trajs[i], model, ...)`` run on its own - the results are identical to
+the sequential runs, independent of how many trajectories share a launch or a GPU.  (A first version ran every
+`sample` in its own thread and handed over with semaphores: the hand-overs cost as much as the AMIS bookkeeping.)
 
 Multi-GPU: trajectories are partitioned across ranks (`rank`, `world`); no communication during sampling.
 
@@ -21,12 +22,11 @@ thread inside the GIL-free C call) overlaps the host code of the other.  On the 
 hidden, but the lane threads lost as much to GIL hand-overs as was gained (64 trajectories: 11.9 s without,
 13.2 s with overlap); the remaining host time is AMIS bookkeeping in numpy (`stats['t_host_lanes']`).
 """
-import threading
 import time
 
 import numpy as np
 
-from .core import sample
+from .core import sample_gen
 from .engine import st_to_runs
 from .trajectory import make_Trajectory
 
@@ -34,42 +34,33 @@ __all__ = ["sample_many"]
 
 
 class _Lane:
-    """One trajectory's state machine, running `sample` in its own thread, one step at a time."""
+    """One trajectory's state machine: the `sample_gen` generator, its pending request and its private RNG state."""
 
     def __init__(self, idx, traj, seed):
         self.idx, self.traj, self.seed = idx, traj, seed
-        self.go = threading.Semaphore(0)        # scheduler -> lane: run until your next likelihood request
+        self.gen = None
         self.request = None                      # (ss, thetas) waiting for evaluation
         self.answer = None
         self.result = None
-        self.error = None
         self.done = False
         self.rng_state = None
 
-
-class _FusingModel:
-    """
-    Per-lane proxy of the shared model: everything is forwarded, except that ``logL_st_batch`` parks the
-    request, hands control back to the scheduler and returns the answer it is given.
-    """
-
-    def __init__(self, model, lane, sched):
-        object.__setattr__(self, "_m", model)
-        object.__setattr__(self, "_lane", lane)
-        object.__setattr__(self, "_sched", sched)
-
-    def __getattr__(self, name):
-        return getattr(self._m, name)
-
-    def logL_st_batch(self, ss, thetas, traj):
-        lane = self._lane
-        lane.request = (np.asarray(ss, dtype=float), np.asarray(thetas))
-        lane.rng_state = np.random.get_state()
-        self._sched.release()                    # back to the scheduler
-        lane.go.acquire()                        # ... until the fused batch has been evaluated
-        np.random.set_state(lane.rng_state)
-        ans, lane.answer = lane.answer, None
-        return ans
+    def advance(self, model, sample_kw):
+        """Run until the next likelihood request (stored in `request`) or the end (`result`, `done`)."""
+        if self.gen is None:
+            np.random.seed(self.seed)
+            self.gen = sample_gen(self.traj, model, **sample_kw)
+            send = None
+        else:
+            np.random.set_state(self.rng_state)
+            send, self.answer = self.answer, None
+        try:
+            ss, thetas = self.gen.send(send)
+            self.request = (np.asarray(ss, dtype=float), np.asarray(thetas))
+        except StopIteration as stop:
+            self.result = stop.value
+            self.done = True
+        self.rng_state = np.random.get_state()
 
 
 def sample_many(trajs, model, seeds=None, rank=0, world=1, max_active=None, **sample_kw):
@@ -97,40 +88,22 @@ def sample_many(trajs, model, seeds=None, rank=0, world=1, max_active=None, **sa
     if seeds is None:
         seeds = list(range(len(trajs)))
     mine = list(range(rank, len(trajs), world))
-    sched = threading.Semaphore(0)
     outer_rng = np.random.get_state()
     stats = {"launches": 0, "profiles": 0, "frame_steps": 0, "rounds": 0,
              "t_host_lanes": 0.0, "t_pack": 0.0, "t_gpu": 0.0}      # wall seconds: AMIS host code / run-length packing / fused launches
-
-    def body(lane):
-        lane.go.acquire()
-        try:
-            np.random.seed(lane.seed)
-            lane.result = sample(lane.traj, _FusingModel(model, lane, sched), **sample_kw)
-        except BaseException as err:  # noqa: BLE001 - reported by the scheduler thread
-            lane.error = err
-        lane.done = True
-        lane.rng_state = np.random.get_state()
-        sched.release()
-
     pending = [_Lane(i, trajs[i], seeds[i]) for i in mine]
     limit = max_active or len(pending) or 1
     active, results = [], {}
     while pending or active:
         while pending and len(active) < limit:
-            lane = pending.pop(0)
-            threading.Thread(target=body, args=(lane,), daemon=True).start()
-            active.append(lane)
+            active.append(pending.pop(0))
         # let every active lane run (one at a time, fixed order) until it asks for likelihoods or finishes
         tic = time.perf_counter()
         for lane in active:
             if lane.request is None and not lane.done:
-                lane.go.release()
-                sched.acquire()
+                lane.advance(model, sample_kw)
         stats["t_host_lanes"] += time.perf_counter() - tic
         for lane in [ln for ln in active if ln.done]:
-            if lane.error is not None:
-                raise lane.error
             results[lane.idx] = lane.result
             active.remove(lane)
         waiting = [ln for ln in active if ln.request is not None]
