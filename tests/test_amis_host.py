@@ -326,3 +326,40 @@ def test_sample_many_equals_sequential_runs():
     # bounded concurrency gives the same answers
     r2, _ = sample_many(trajs, model, seeds=seeds, max_active=2, **kw)
     assert all(np.array_equal(r2[i].evidence, res[i].evidence) for i in range(4))
+
+
+def test_generator_api_equals_synchronous_api():
+    """`sample_gen` / `FixedkSampler.step_gen` yield exactly the batches `sample` / `step` evaluate: driving them by hand
+    with the model's own batched likelihood reproduces the synchronous run bit for bit, and the requests are the
+    (ss, thetas) batches of `FixedkSampler.logL` (amis.py:717-739)."""
+    from bild_b200.amis import drive
+    from bild_b200.core import sample_gen
+    model = OracleBackedRouse(8, 1, 5, d=2, localization_error=0.3)
+    np.random.seed(3)
+    traj = model.trajectory_from_loopingprofile(bild.Loopingprofile([0] * 9 + [1] * 10 + [0] * 8))
+    kw = dict(init_runs=3, sampler_kw={"N": 15, "max_fcomplete": 40}, k_max=3, certainty_in_k=0.9)
+    np.random.seed(11)
+    ref = bild.sample(traj, model, **kw)
+    seen = []
+
+    def evaluate(ss, thetas):
+        seen.append((np.shape(ss), np.shape(thetas)))
+        return model.logL_st_batch(ss, thetas, traj)
+
+    np.random.seed(11)
+    res = drive(sample_gen(traj, model, **kw), evaluate)
+    assert np.array_equal(res.evidence, ref.evidence) and np.array_equal(res.log["k"], ref.log["k"])
+    assert res.best_profile() == ref.best_profile()
+    assert len(seen) == sum(len(s.samples) for s in res.samplers) and all(a == b for a, b in seen)
+    # one sampler by hand: the deferred constructor evaluates nothing until start_gen is driven
+    np.random.seed(12)
+    smp = amis.FixedkSampler(traj, model, k=3, N=15, max_fcomplete=40, _defer=True)
+    assert smp.samples == []
+    drive(smp.start_gen(), evaluate)
+    assert smp.step() is True and len(smp.samples) == 1
+    gen = smp.step_gen()
+    ss, thetas = next(gen)
+    assert ss.shape == thetas.shape == (15, 4)
+    with pytest.raises(StopIteration) as stop:
+        gen.send(model.logL_st_batch(ss, thetas, traj))
+    assert stop.value.value is True and len(smp.samples) == 2
