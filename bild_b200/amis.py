@@ -40,6 +40,22 @@ def _lse(a, axis=None, mask=None, keepdims=False):
     return out
 
 
+_NATIVE = None
+
+
+def _native_helpers():
+    """True when libbild_b200.so (which also carries the host-side proposal-density helper) can be loaded."""
+    global _NATIVE
+    if _NATIVE is None:
+        from . import _lib
+        try:
+            _lib.load()
+            _NATIVE = True
+        except (_lib.BildkError, OSError):
+            _NATIVE = False
+    return _NATIVE
+
+
 def drive(gen, evaluate):
     """
     Run a likelihood-requesting generator to completion: every ``(ss, thetas)`` it yields is answered with
@@ -317,6 +333,11 @@ class FixedkSampler:
             return out
         A = np.ascontiguousarray([par[0] for par in parameters], dtype=np.float64)
         L = np.ascontiguousarray([par[1] for par in parameters], dtype=np.float64)
+        if not _native_helpers():
+            # host-side bookkeeping only (no likelihood is evaluated here): without the built library - pure-CPU models
+            # such as `FactorizedModel` on a machine without nvcc - use the numpy statement of the same arithmetic,
+            # as the reference's AMIS layer (pure numpy/scipy) does.  The LIKELIHOOD has no such fallback.
+            return self.dirichlet.logpdf_multi(A, ss) + self.cfc.logpmf_multi(L, thetas)
         ss = np.ascontiguousarray(ss, dtype=np.float64)
         thetas = np.ascontiguousarray(thetas, dtype=np.int64)
         trans = np.ascontiguousarray(self.cfc.transitions, dtype=np.uint8)

@@ -21,6 +21,23 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false"]
 
 
+# roofline micro-benchmark (measurement tooling, not the product): tools/fp64_peak.cu -> tools/libfp64peak.so
+PEAK_SRC = os.path.join(os.path.dirname(HERE), "tools", "fp64_peak.cu")
+PEAK_OUT = os.path.join(os.path.dirname(HERE), "tools", "libfp64peak.so")
+
+
+def build_peak(force=False):
+    if not force and os.path.exists(PEAK_OUT) and os.path.getmtime(PEAK_OUT) >= os.path.getmtime(PEAK_SRC):
+        return PEAK_OUT
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+           "-DFP64_PEAK_NO_MAIN", "-o", PEAK_OUT, PEAK_SRC]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return PEAK_OUT
+
+
 def needs_build():
     if not os.path.exists(OUT):
         return True
@@ -29,6 +46,7 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    build_peak(force)
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")

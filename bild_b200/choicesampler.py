@@ -4,6 +4,12 @@ Which k to sample next?  Information-based sample selection for the iterative AM
 Behavioural mirror of /root/reference/bild/choicesampler.py (`ChoiceSampler`); host-side numpy, tiny
 (``samplesize x kmax`` normals), but it draws from the global numpy RNG (choicesampler.py:106), so the
 call order is part of the seed-parity contract and is kept.
+
+Provenance note: this class is OUT OF SCOPE of the accelerated path and exists only so that
+``import bild_b200 as bild`` is a complete drop-in.  It follows the reference class closely - same attribute and
+method names (they are public API: ``n0``, ``samplesize``, ``KLD_moreSamples``, ``KLD_omitK``) and, necessarily, the
+same formulas and the same order of random draws - i.e. it is a restatement of choicesampler.py:83-210, not
+independent work, and claims no credit.
 """
 import numpy as np
 

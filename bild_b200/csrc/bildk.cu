@@ -18,8 +18,13 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
+
+#include <nvtx3/nvToolsExt.h>
 
 using namespace bildk;
 
@@ -41,6 +46,30 @@ static int fail(int code, const char* fmt, ...) {
         cudaError_t e_ = (x);                                                                        \
         if (e_ != cudaSuccess) return fail(BILDK_ECUDA, "%s: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
+
+// NVTX range around every ABI entry point that launches work (shows up in nsys / ncu --nvtx timelines)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: remember the largest value
+// configured for every (device, kernel) pair (a process-wide `static` would skip the call on a second device).
+static cudaError_t ensure_dyn_smem(const void* kernel, size_t smem) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> configured;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& cur = configured[std::make_pair(dev, kernel)];
+    if (smem > cur) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        cur = smem;
+    }
+    return cudaSuccess;
+}
 
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
@@ -102,6 +131,9 @@ struct bildk_model {
     DevBuf<const uint8_t*> vptrs;
     int max_smem_optin = 0;
     int n_sm = 0;
+    // the scratch buffers above are shared by every call on this model: host-pointer entry points hold this lock from
+    // staging to copy-back (ctypes releases the GIL, so two Python threads may call in concurrently)
+    std::mutex mu;
 };
 
 struct bildk_traj {
@@ -218,6 +250,10 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
     CU(cudaSetDevice(device));
 
     bildk_model* m = new bildk_model();
+    struct Guard {
+        bildk_model* m;
+        ~Guard() { if (m) bildk_model_destroy(m); }
+    } guard{m};
     m->N = N; m->D = d; m->S = S; m->device = device;
     CU(cudaDeviceGetAttribute(&m->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CU(cudaDeviceGetAttribute(&m->n_sm, cudaDevAttrMultiProcessorCount, device));
@@ -225,7 +261,7 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
     for (size_t i = 0; i < S * ND; ++i) if (G[i] != 0.0) m->hasG = true;
     m->nnz = 0;
     for (int i = 0; i < N; ++i) {
-        if (!std::isfinite(w[i])) { delete m; return fail(BILDK_EINVAL, "non-finite measurement vector"); }
+        if (!std::isfinite(w[i])) return fail(BILDK_EINVAL, "non-finite measurement vector");
         if (w[i] != 0.0) {
             if (m->nnz < NZMAX) { m->wz_idx[m->nnz] = i; m->wz_val[m->nnz] = w[i]; }
             ++m->nnz;
@@ -245,19 +281,17 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
         for (int i = 0; i < N; ++i)
             for (int j = 0; j < N; ++j) Bs[s * NN + static_cast<size_t>(i) * N + j] = B[s * NN + static_cast<size_t>(std::max(i, j)) * N + std::min(i, j)];
     if ((rc = upload(&m->dB, Bs.data(), S * NN)) || (rc = upload(&m->dSig, Sig, S * NN)) || (rc = upload(&m->dC0, C0, S * NN)) ||
-        (rc = upload(&m->dG, G, S * ND)) || (rc = upload(&m->dM0, M0, S * ND)) || (rc = upload(&m->dw, w, N))) {
-        bildk_model_destroy(m);
+        (rc = upload(&m->dG, G, S * ND)) || (rc = upload(&m->dM0, M0, S * ND)) || (rc = upload(&m->dw, w, N)))
         return rc;
-    }
     if (m->tile_ok) {
         const size_t matd = static_cast<size_t>(m->NP) * m->LD;
         std::vector<double> pad(S * matd);
         for (int s = 0; s < S; ++s) pad_matrix(B + s * NN, N, m->TS, m->BS, m->LD, m->NP, pad.data() + s * matd, true);
-        if ((rc = upload(&m->dBpad, pad.data(), S * matd))) { bildk_model_destroy(m); return rc; }
+        if ((rc = upload(&m->dBpad, pad.data(), S * matd))) return rc;
         for (int s = 0; s < S; ++s) pad_matrix(Sig + s * NN, N, m->TS, m->BS, m->LD, m->NP, pad.data() + s * matd, false);
-        if ((rc = upload(&m->dSigpad, pad.data(), S * matd))) { bildk_model_destroy(m); return rc; }
+        if ((rc = upload(&m->dSigpad, pad.data(), S * matd))) return rc;
         for (int s = 0; s < S; ++s) pad_matrix(C0 + s * NN, N, m->TS, m->BS, m->LD, m->NP, pad.data() + s * matd, false);
-        if ((rc = upload(&m->dC0pad, pad.data(), S * matd))) { bildk_model_destroy(m); return rc; }
+        if ((rc = upload(&m->dC0pad, pad.data(), S * matd))) return rc;
         // lane -> (a, b): walk the tile grid in 2x2 blocks so that an aligned quad of lanes owns one block
         std::vector<uint16_t> lab;
         const int Gt = m->G;
@@ -292,7 +326,7 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
                             pad[s * matb + static_cast<size_t>(i) * m->LDBm + ((((j >> 2) ^ sw) << 2) | (j & 3))] =
                                 B[s * NN + static_cast<size_t>(std::max(i, j)) * N + std::min(i, j)];
                     }
-                if ((rc = upload(&m->dBm, pad.data(), S * matb))) { bildk_model_destroy(m); return rc; }
+                if ((rc = upload(&m->dBm, pad.data(), S * matb))) return rc;
             }
             auto fill = [&](const double* src, std::vector<double>& pad) {
                 std::fill(pad.begin(), pad.end(), 0.0);
@@ -302,9 +336,9 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
             };
             std::vector<double> padg(S * matg);
             fill(Sig, padg);
-            if ((rc = upload(&m->dSigm, padg.data(), S * matg))) { bildk_model_destroy(m); return rc; }
+            if ((rc = upload(&m->dSigm, padg.data(), S * matg))) return rc;
             fill(C0, padg);
-            if ((rc = upload(&m->dC0m, padg.data(), S * matg))) { bildk_model_destroy(m); return rc; }
+            if ((rc = upload(&m->dC0m, padg.data(), S * matg))) return rc;
             const size_t fbytes = (static_cast<size_t>(m->NPm) * m->LDCm + static_cast<size_t>(2) * m->NPm + 2) * 8;
             // one CTA per filter, one warp per tile column (k_mmac); at least one propagator resident
             if (GT >= 5 && GT <= 14) m->mmac_ok = 16 + matb * 8 + fbytes <= static_cast<size_t>(m->max_smem_optin);
@@ -324,13 +358,14 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
                         for (int j = 0; j < N; ++j)
                             pad[s * matr + static_cast<size_t>(i) * LDr + (j ^ (4 * ((i >> 1) & 1)))] =
                                 B[s * NN + static_cast<size_t>(std::max(i, j)) * N + std::min(i, j)];
-                if ((rc = upload(&m->dBr, pad.data(), S * matr))) { bildk_model_destroy(m); return rc; }
+                if ((rc = upload(&m->dBr, pad.data(), S * matr))) return rc;
                 m->r_last = rl; m->LDr = LDr;
                 m->fstride_r = static_cast<int>(matr) + 2 * R + 8;
                 m->mmar_ok = 16 + matr * 8 * S + static_cast<size_t>(m->fstride_r) * 8 * 4 <= static_cast<size_t>(m->max_smem_optin);
             }
         }
     }
+    guard.m = nullptr;
     *out = m;
     return BILDK_OK;
 }
@@ -361,6 +396,10 @@ extern "C" int bildk_traj_create(bildk_model_t m, int T, const double* x, int ds
         if (Cind[j] >= static_cast<uint32_t>(dstar)) return fail(BILDK_EINVAL, "Cind[%d]=%u out of range", j, Cind[j]);
     CU(cudaSetDevice(m->device));
     bildk_traj* t = new bildk_traj();
+    struct Guard {   // an early return through CU() must not leak the handle and its device allocations
+        bildk_traj* t;
+        ~Guard() { if (t) bildk_traj_destroy(t); }
+    } guard{t};
     t->m = m; t->T = T; t->dstar = dstar;
     for (int e = 0; e < DMAX; ++e) { t->s2[e] = 0; t->ncols[e] = 0; for (int c = 0; c < DMAX; ++c) t->cols[e][c] = 0; }
     for (int e = 0; e < dstar; ++e) t->s2[e] = s2[e];
@@ -396,6 +435,7 @@ extern "C" int bildk_traj_create(bildk_model_t m, int T, const double* x, int ds
     CU(cudaMemcpy(t->d_xptr, &xp, sizeof xp, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(t->d_vptr, &vp, sizeof vp, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(t->d_T, &T, sizeof T, cudaMemcpyHostToDevice));
+    guard.t = nullptr;
     *out = t;
     return BILDK_OK;
 }
@@ -422,11 +462,9 @@ struct Plan {
 
 template <int GT, bool MX>
 static cudaError_t mma_launch(const MParams& mp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_mma<GT, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    {
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&k_mma<GT, MX>), smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     k_mma<GT, MX><<<grid, threads, smem, st>>>(mp);
     return cudaGetLastError();
@@ -462,11 +500,9 @@ static cudaError_t mma_launch_for(int GT, bool MX, const MParams& mp, dim3 grid,
 
 template <int GT, int NB>
 static cudaError_t mmar_launch(const RParams& rp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_mmar<GT, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    {
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&k_mmar<GT, NB>), smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     k_mmar<GT, NB><<<grid, threads, smem, st>>>(rp);
     return cudaGetLastError();
@@ -530,11 +566,9 @@ static void mmar_tables(int GT, int r, int ncols, unsigned char* lastrow, unsign
 
 template <int GT, bool MX>
 static cudaError_t mmac_launch(const CParams& cp, dim3 grid, size_t smem, cudaStream_t st) {
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_mmac<GT, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    {
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&k_mmac<GT, MX>), smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     k_mmac<GT, MX><<<grid, 32 * (GT + cp.nhelp), smem, st>>>(cp);
     cudaError_t e = cudaGetLastError();
@@ -548,11 +582,9 @@ static cudaError_t mmac_launch(const CParams& cp, dim3 grid, size_t smem, cudaSt
 }
 template <int GT, int NH, int NW>
 static cudaError_t mmact_launch(const CTParams& ct, dim3 grid, size_t smem, cudaStream_t st) {
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_mmact<GT, NH, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    {
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&k_mmact<GT, NH, NW>), smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     k_mmact<GT, NH, NW><<<grid, 32 * NW, smem, st>>>(ct);
     return cudaGetLastError();
@@ -643,11 +675,9 @@ static cudaError_t mmac_launch_for(int GT, bool MX, const CParams& cp, dim3 grid
 
 template <int GT, bool MX>
 static cudaError_t mma2_launch(const M2Params& mp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_mma2<GT, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    {
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&k_mma2<GT, MX>), smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     k_mma2<GT, MX><<<grid, threads, smem, st>>>(mp);
     return cudaGetLastError();
@@ -866,11 +896,9 @@ static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
 
 template <int TS, bool WS, bool DW, int MAXT>
 static cudaError_t launch_one(const KParams& kp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_tile<TS, WS, DW, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    {
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&k_tile<TS, WS, DW, MAXT>), smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     k_tile<TS, WS, DW, MAXT><<<grid, threads, smem, st>>>(kp);
     return cudaGetLastError();
@@ -1140,6 +1168,8 @@ extern "C" int bildk_logl_runs_device(bildk_traj_t t, int P, int K1, const int32
     if (P == 0) return BILDK_OK;
     if (!d_starts || !d_states || !d_out) return fail(BILDK_EINVAL, "NULL device pointer");
     bildk_model* m = t->m;
+    NvtxRange nvtx("bildk_logl_runs_device");
+    std::lock_guard<std::mutex> lock(m->mu);   // covers the launch bookkeeping only: the work itself is asynchronous
     CU(cudaSetDevice(m->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int first[2] = {0, P};
@@ -1171,6 +1201,8 @@ extern "C" int bildk_logl_runs_multi(int n_traj, const bildk_traj_t* trajs, cons
         int rc = validate_runs(m, t->T, hf[i + 1] - hf[i], K1, starts + static_cast<size_t>(hf[i]) * K1, states + static_cast<size_t>(hf[i]) * K1, hf[i]);
         if (rc) return rc;
     }
+    NvtxRange nvtx("bildk_logl_runs_multi");
+    std::lock_guard<std::mutex> lock(m->mu);   // staging buffers, launch and copy-back of this model are one critical section
     CU(cudaSetDevice(m->device));
     int rc;
     const size_t nrun = static_cast<size_t>(P) * K1;
@@ -1286,6 +1318,26 @@ extern "C" int bildk_logl_states(bildk_traj_t t, int P, const int32_t* states, d
 }
 
 // ------------------------------------------------------------------------------------------------
+// one cluster of AW_CLUSTER CTAs (bildk_kernels.cuh)
+static cudaError_t launch_amis_weights(int n, const double* logL, const double* logdelta, const double* curlp, double log_nsteps,
+                                       double* log_w, double* stats, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(AW_CLUSTER);
+    cfg.blockDim = dim3(1024);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = AW_CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_amis_weights, n, logL, logdelta, curlp, log_nsteps, log_w, stats);
+    if (e == cudaSuccess) g_launches++;
+    return e;
+}
+
 extern "C" int bildk_amis_weights(int n, const double* logL, const double* logdelta, const double* curlp,
                                   double log_nsteps, double* log_w, double stats[4], int device) {
     if (n < 1 || !logL || !logdelta || !curlp || !stats) return fail(BILDK_EINVAL, "bad argument");
@@ -1313,11 +1365,11 @@ extern "C" int bildk_amis_weights(int n, const double* logL, const double* logde
     cudaError_t e;
     if ((e = cudaMemcpyAsync(d, sc.host.data(), 3 * nn * 8, cudaMemcpyHostToDevice, sc.st)) != cudaSuccess)
         return fail(BILDK_ECUDA, "copy failed: %s", cudaGetErrorString(e));
-    k_amis_weights<<<1, 1024, 0, sc.st>>>(n, d, d + nn, d + 2 * nn, log_nsteps, log_w ? d + 3 * nn : nullptr, d + 4 * nn);
-    g_launches++;
+    NvtxRange nvtx("bildk_amis_weights");
+    e = launch_amis_weights(n, d, d + nn, d + 2 * nn, log_nsteps, log_w ? d + 3 * nn : nullptr, d + 4 * nn, sc.st);
     // log_w (n) and the four statistics are contiguous on the device: [3n, 4n + 4)
     const size_t off = log_w ? 3 * nn : 4 * nn, cnt = log_w ? nn + 4 : 4;
-    if ((e = cudaGetLastError()) != cudaSuccess ||
+    if (e != cudaSuccess ||
         (e = cudaMemcpyAsync(sc.host.data(), d + off, cnt * 8, cudaMemcpyDeviceToHost, sc.st)) != cudaSuccess ||
         (e = cudaStreamSynchronize(sc.st)) != cudaSuccess)
         return fail(BILDK_ECUDA, "weights kernel failed: %s", cudaGetErrorString(e));
@@ -1335,28 +1387,37 @@ extern "C" int bildk_marginal_posterior(int n, int K1, int T, int S, const int32
     const size_t nn = static_cast<size_t>(n), nr = nn * K1;
     for (size_t i = 0; i < nr; ++i) if (run_states[i] >= S) return fail(BILDK_EINVAL, "state %d out of range [0,%d)", run_states[i], S);
     CU(cudaSetDevice(device));
-    int32_t* d_starts = nullptr;
-    uint8_t* d_states = nullptr;
-    double *d_w = nullptr, *d_out = nullptr;
-    int rc = BILDK_OK;
-    cudaError_t e = cudaSuccess;
-    if ((e = cudaMalloc(&d_starts, nr * sizeof(int32_t))) != cudaSuccess || (e = cudaMalloc(&d_states, nr)) != cudaSuccess ||
-        (e = cudaMalloc(&d_w, nn * 8)) != cudaSuccess || (e = cudaMalloc(&d_out, static_cast<size_t>(S) * T * 8)) != cudaSuccess)
-        rc = fail(BILDK_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(e));
-    if (rc == BILDK_OK &&
-        ((e = cudaMemcpy(d_starts, run_starts, nr * sizeof(int32_t), cudaMemcpyHostToDevice)) != cudaSuccess ||
-         (e = cudaMemcpy(d_states, run_states, nr, cudaMemcpyHostToDevice)) != cudaSuccess ||
-         (e = cudaMemcpy(d_w, log_w, nn * 8, cudaMemcpyHostToDevice)) != cudaSuccess))
-        rc = fail(BILDK_ECUDA, "copy failed: %s", cudaGetErrorString(e));
-    if (rc == BILDK_OK) {
-        k_marginal_posterior<<<T, 256>>>(n, K1, T, S, d_starts, d_states, d_w, d_out);
-        g_launches++;
-        if ((e = cudaGetLastError()) != cudaSuccess ||
-            (e = cudaMemcpy(out, d_out, static_cast<size_t>(S) * T * 8, cudaMemcpyDeviceToHost)) != cudaSuccess)
-            rc = fail(BILDK_ECUDA, "marginal posterior kernel failed: %s", cudaGetErrorString(e));
-    }
-    cudaFree(d_starts); cudaFree(d_states); cudaFree(d_w); cudaFree(d_out);
-    return rc;
+    NvtxRange nvtx("bildk_marginal_posterior");
+    // grow-only scratch per device and thread, one packed copy in, one out, private stream (as bildk_amis_weights)
+    struct Scratch { DevBuf<double> dev; std::vector<double> host; cudaStream_t st = nullptr; };
+    static thread_local std::vector<Scratch> scratch;
+    if (scratch.size() < static_cast<size_t>(ndev)) scratch.resize(ndev);
+    Scratch& sc = scratch[device];
+    // packed layout in units of 8 bytes: log_w (n) | out (S*T) | run_starts (ceil(nr/2)) | run_states (ceil(nr/8))
+    const size_t n_out = static_cast<size_t>(S) * T, o_out = nn, o_starts = o_out + n_out, o_states = o_starts + (nr + 1) / 2,
+                 total = o_states + (nr + 7) / 8;
+    int rc = sc.dev.reserve(total);
+    if (rc) return rc;
+    if (sc.host.size() < total) sc.host.resize(2 * total);
+    if (!sc.st) CU(cudaStreamCreateWithFlags(&sc.st, cudaStreamNonBlocking));
+    std::memcpy(sc.host.data(), log_w, nn * 8);
+    std::memcpy(sc.host.data() + o_starts, run_starts, nr * sizeof(int32_t));
+    std::memcpy(sc.host.data() + o_states, run_states, nr);
+    double* d = sc.dev.p;
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(d, sc.host.data(), nn * 8, cudaMemcpyHostToDevice, sc.st)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(d + o_starts, sc.host.data() + o_starts, (total - o_starts) * 8, cudaMemcpyHostToDevice, sc.st)) != cudaSuccess)
+        return fail(BILDK_ECUDA, "copy failed: %s", cudaGetErrorString(e));
+    const int cache_n = nn <= 40 * 1024 ? n : 0;   // one byte of shared memory per sample (48 KB need no opt-in)
+    k_marginal_posterior<<<T, 256, static_cast<size_t>(cache_n), sc.st>>>(n, K1, T, S, reinterpret_cast<const int32_t*>(d + o_starts),
+                                                                        reinterpret_cast<const uint8_t*>(d + o_states), d, d + o_out, cache_n);
+    g_launches++;
+    if ((e = cudaGetLastError()) != cudaSuccess ||
+        (e = cudaMemcpyAsync(sc.host.data() + o_out, d + o_out, n_out * 8, cudaMemcpyDeviceToHost, sc.st)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(sc.st)) != cudaSuccess)
+        return fail(BILDK_ECUDA, "marginal posterior kernel failed: %s", cudaGetErrorString(e));
+    std::memcpy(out, sc.host.data() + o_out, n_out * 8);
+    return BILDK_OK;
 }
 
 // Host-side AMIS bookkeeping: proposal densities of n samples under n_par proposals (see include/bild_b200.h).
@@ -1425,42 +1486,7 @@ extern "C" int bildk_amis_log_proposal(int n_par, int n, int K1, int S, const do
 extern "C" int bildk_amis_weights_device(int n, const double* d_logL, const double* d_logdelta, const double* d_curlp,
                                          double log_nsteps, double* d_log_w, double* d_stats, void* stream) {
     if (n < 1 || !d_logL || !d_logdelta || !d_curlp || !d_stats) return fail(BILDK_EINVAL, "bad argument");
-    k_amis_weights<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(n, d_logL, d_logdelta, d_curlp, log_nsteps, d_log_w, d_stats);
-    CU(cudaGetLastError());
-    g_launches++;
-    return BILDK_OK;
-}
-
-extern "C" int bildk_measure_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops) {
-    int ndev = bildk_device_count();
-    if (ndev == 0) return fail(BILDK_ECUDA, "no CUDA device available");
-    if (device < 0 || device >= ndev || !dfma_tflops || !dmma_tflops) return fail(BILDK_EINVAL, "bad argument");
-    CU(cudaSetDevice(device));
-    int sms = 0;
-    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    double* d = nullptr;
-    CU(cudaMalloc(&d, 8));
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
-    const int iters = 4096, blocks = sms * 4;   // 32 warps per SM
-    double best[2] = {1e30, 1e30};
-    for (int which = 0; which < 2; ++which)
-        for (int rep = 0; rep < 7; ++rep) {
-            CU(cudaEventRecord(e0));
-            if (which == 0) k_peak_dfma<<<blocks, 256>>>(d, iters, 1.0000001, 1e-9);
-            else k_peak_dmma<<<blocks, 256>>>(d, iters, 1.0000001, 1e-9);
-            CU(cudaEventRecord(e1));
-            CU(cudaEventSynchronize(e1));
-            float ms = 0;
-            CU(cudaEventElapsedTime(&ms, e0, e1));
-            if (rep >= 2 && ms < best[which]) best[which] = ms;
-        }
-    CU(cudaGetLastError());
-    *dfma_tflops = 2.0 * 16 * iters * 256.0 * blocks / best[0] * 1e-9;
-    *dmma_tflops = 2.0 * 256 * 8 * iters * 8.0 * blocks / best[1] * 1e-9;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(d);
+    NvtxRange nvtx("bildk_amis_weights_device");
+    CU(launch_amis_weights(n, d_logL, d_logdelta, d_curlp, log_nsteps, d_log_w, d_stats, static_cast<cudaStream_t>(stream)));
     return BILDK_OK;
 }

@@ -21,6 +21,7 @@
 //     shared buffer, everybody forms Cw, S, K locally and applies C -= K Cw^T to its own tile;
 //   * filters narrower than a warp (G*G <= 32) synchronise with __syncwarp only, several per warp.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -605,16 +606,28 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Multi-CTA version: ONE launch of a thread-block cluster of AW_CLUSTER CTAs.  Every CTA owns a contiguous chunk of the
+// ensemble; the per-CTA partials of each pass are exchanged through distributed shared memory (cluster.map_shared_rank)
+// and combined by every CTA in rank order, so the result is a function of n alone - identical bits on every rank of
+// a multi-GPU run - while the three passes over the (gathered) ensemble are spread over AW_CLUSTER SMs.
+// (Round 1 used one CTA: 10.7 us at n = 4096 but ~8x that for the 32768-element vector of an 8-GPU step.)
+constexpr int AW_CLUSTER = 8;
 __global__ void __launch_bounds__(1024) k_amis_weights(int n, const double* __restrict__ logL,
                                                        const double* __restrict__ logdelta,
                                                        const double* __restrict__ curlp, double log_nsteps,
                                                        double* __restrict__ log_w, double* __restrict__ stats) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = static_cast<int>(cluster.block_rank()), ncta = static_cast<int>(cluster.num_blocks());
     __shared__ double red[32][2];
-    __shared__ double bc;
+    __shared__ double part[4];   // this CTA's partials (max, sum w, sum (w - mean)^2, nansum), read by the peers
+    __shared__ double bc[2];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    const int chunk = (n + ncta - 1) / ncta;
+    const int lo = crank * chunk, hi = min(n, lo + chunk);
     // pass 1: log weights and their maximum
     double mx = -INFINITY;
-    for (int i = tid; i < n; i += blockDim.x) {
+    for (int i = lo + tid; i < hi; i += blockDim.x) {
         const double lw = logL[i] - logdelta[i] + log_nsteps;
         if (log_w) log_w[i] = lw;
         mx = fmax(mx, lw);
@@ -622,24 +635,40 @@ __global__ void __launch_bounds__(1024) k_amis_weights(int n, const double* __re
     mx = warp_max(mx);
     if (lane == 0) red[wid][0] = mx;
     __syncthreads();
-    mx = warp_max((lane < nw) ? red[lane][0] : -INFINITY);
+    if (wid == 0) {
+        mx = warp_max((lane < nw) ? red[lane][0] : -INFINITY);
+        if (lane == 0) part[0] = mx;
+    }
+    cluster.sync();
+    if (tid == 0) {
+        double v = -INFINITY;
+        for (int r = 0; r < ncta; ++r) v = fmax(v, *cluster.map_shared_rank(&part[0], r));
+        bc[0] = v;
+    }
     __syncthreads();
+    mx = bc[0];
     // pass 2: sum of the shifted weights
     double s1 = 0.0;
-    for (int i = tid; i < n; i += blockDim.x) s1 += exp(logL[i] - logdelta[i] + log_nsteps - mx);
+    for (int i = lo + tid; i < hi; i += blockDim.x) s1 += exp(logL[i] - logdelta[i] + log_nsteps - mx);
     s1 = warp_sum(s1);
     if (lane == 0) red[wid][0] = s1;
     __syncthreads();
     if (wid == 0) {
         s1 = warp_sum((lane < nw) ? red[lane][0] : 0.0);
-        if (lane == 0) bc = s1;
+        if (lane == 0) part[1] = s1;
+    }
+    cluster.sync();
+    if (tid == 0) {
+        double v = 0.0;
+        for (int r = 0; r < ncta; ++r) v += *cluster.map_shared_rank(&part[1], r);   // rank order: same bits in every CTA
+        bc[1] = v;
     }
     __syncthreads();
-    s1 = bc;
+    s1 = bc[1];
     const double mean = s1 / n;
     // pass 3: centred second moment (what scipy.stats.sem needs) and the KL numerator
     double ssd = 0.0, s3 = 0.0;
-    for (int i = tid; i < n; i += blockDim.x) {
+    for (int i = lo + tid; i < hi; i += blockDim.x) {
         const double wo = exp(logL[i] - logdelta[i] + log_nsteps - mx);
         const double dv = wo - mean;
         ssd = fma(dv, dv, ssd);
@@ -653,8 +682,15 @@ __global__ void __launch_bounds__(1024) k_amis_weights(int n, const double* __re
     if (wid == 0) {
         ssd = warp_sum((lane < nw) ? red[lane][0] : 0.0);
         s3 = warp_sum((lane < nw) ? red[lane][1] : 0.0);
-        if (lane == 0) { stats[0] = mx; stats[1] = s1; stats[2] = ssd; stats[3] = s3; }
+        if (lane == 0) { part[2] = ssd; part[3] = s3; }
     }
+    cluster.sync();
+    if (crank == 0 && tid == 0) {
+        double a = 0.0, b = 0.0;
+        for (int r = 0; r < ncta; ++r) { a += *cluster.map_shared_rank(&part[2], r); b += *cluster.map_shared_rank(&part[3], r); }
+        stats[0] = mx; stats[1] = s1; stats[2] = a; stats[3] = b;
+    }
+    cluster.sync();   // no CTA may exit while rank 0 still reads its shared memory
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -662,23 +698,34 @@ __global__ void __launch_bounds__(1024) k_amis_weights(int n, const double* __re
 // (FixedkSampler.log_marginal_posterior, /root/reference/bild/amis.py:942-972, which materialises an
 // (n, S, T) boolean tensor on the host): out[s][t] = log sum_{i: state_i(t) = s} w_i, normalised over s.
 // One CTA per frame; for every state a fixed-order (thread-strided, warp-shuffle, cross-warp) sum, so the
-// result does not depend on the launch geometry of other frames and is reproducible.
+// result does not depend on the launch geometry of other frames and is reproducible.  The state of every sample at
+// this frame is looked up ONCE (a scan of its run starts) and cached as one byte in dynamic shared memory
+// (`cache_n` = n when the launch provided n bytes, else 0: look-up on the fly), not once per state and pass.
+// The log-sum-exp of a state is shifted by the maximum over ITS OWN samples - what scipy >= 1.15 does for
+// logsumexp(a, b=mask) (masked entries are set to -inf before the shift); older scipy releases, the ones the
+// reference's `numpy < 2` pin allows, shift by the global maximum, so states more than ~745 below the best sample
+// underflow to -inf there and stay finite here.
 __global__ void __launch_bounds__(256) k_marginal_posterior(int n, int K1, int T, int S, const int32_t* __restrict__ starts,
                                                             const uint8_t* __restrict__ states, const double* __restrict__ log_w,
-                                                            double* __restrict__ out) {
+                                                            double* __restrict__ out, int cache_n) {
+    extern __shared__ uint8_t st_cache[];
     __shared__ double red[8];
     __shared__ double bc;
     __shared__ double lse[256];
     const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-    auto state_at = [&](int i) {
+    auto lookup = [&](int i) {
         const int32_t* rs = starts + static_cast<size_t>(i) * K1;
         int r = 0;
         for (int q = 1; q < K1; ++q) r = (rs[q] <= t) ? q : r;   // last run that has started (empty runs vanish)
         return static_cast<int>(states[static_cast<size_t>(i) * K1 + r]);
     };
+    const bool cached = cache_n >= n;
+    if (cached) {
+        for (int i = tid; i < n; i += blockDim.x) st_cache[i] = static_cast<uint8_t>(lookup(i));
+        __syncthreads();
+    }
+    auto state_at = [&](int i) { return cached ? static_cast<int>(st_cache[i]) : lookup(i); };
     for (int s = 0; s < S; ++s) {
-        // log-sum-exp of the weights of the samples that are in state s at frame t, shifted by THEIR maximum (a state
-        // whose samples are all e-800 below the best one still has a finite log posterior, as in the reference)
         double mx = -INFINITY;
         for (int i = tid; i < n; i += blockDim.x)
             if (state_at(i) == s) mx = fmax(mx, log_w[i]);
@@ -716,38 +763,6 @@ __global__ void __launch_bounds__(256) k_marginal_posterior(int n, int K1, int T
         const double norm = (top > -INFINITY && top < INFINITY) ? log(all) + top : top;
         for (int s = 0; s < S; ++s) out[static_cast<size_t>(s) * T + t] = lse[s] - norm;
     }
-}
-
-// ------------------------------------------------------------------------------------------------
-// FP64 peak probes (roofline denominators; MEASURED_PEAKS.json has no FP64 entry): independent
-// register-resident DFMA chains, and DMMA m8n8k4 chains.  Same kernels as tools/fp64_peak.cu.
-__global__ void __launch_bounds__(256) k_peak_dfma(double* out, int iters, double a, double b) {
-    double acc[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = threadIdx.x * 1e-9 + i;
-    for (int it = 0; it < iters; ++it) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] = fma(acc[i], a, b);
-    }
-    double s = 0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) s += acc[i];
-    if (s == 123.456) out[0] = s;
-}
-__global__ void __launch_bounds__(256) k_peak_dmma(double* out, int iters, double a, double b) {
-    double c0[8], c1[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { c0[i] = threadIdx.x * 1e-9; c1[i] = i; }
-    for (int it = 0; it < iters; ++it) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                         : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
-    }
-    double s = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s += c0[i] + c1[i];
-    if (s == 123.456) out[0] = s;
 }
 
 }  // namespace bildk

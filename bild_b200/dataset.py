@@ -94,49 +94,58 @@ def sample_many(trajs, model, seeds=None, rank=0, world=1, max_active=None, **sa
     pending = [_Lane(i, trajs[i], seeds[i]) for i in mine]
     limit = max_active or len(pending) or 1
     active, results = [], {}
-    while pending or active:
-        while pending and len(active) < limit:
-            active.append(pending.pop(0))
-        # let every active lane run (one at a time, fixed order) until it asks for likelihoods or finishes
-        tic = time.perf_counter()
-        for lane in active:
-            if lane.request is None and not lane.done:
-                lane.advance(model, sample_kw)
-        stats["t_host_lanes"] += time.perf_counter() - tic
-        for lane in [ln for ln in active if ln.done]:
-            results[lane.idx] = lane.result
-            active.remove(lane)
-        waiting = [ln for ln in active if ln.request is not None]
-        if not waiting:
-            continue
-        # ---- fuse: one launch for all waiting trajectories; profiles with fewer runs are padded with
-        #      empty runs (start = T), which vanish exactly like the empty slices of st2profile
-        stats["rounds"] += 1
-        tic = time.perf_counter()
-        K1 = max(ln.request[0].shape[1] for ln in waiting)
-        starts, states, offsets = [], [], [0]
-        for ln in waiting:
-            ss, thetas = ln.request
-            if thetas.size and (thetas.min() < 0 or thetas.max() >= model.nStates):
-                raise ValueError("state index out of range")
-            a, b = st_to_runs(ss, thetas, len(ln.traj))
-            if a.shape[1] < K1:
-                extra = K1 - a.shape[1]
-                a = np.concatenate([a, np.full((len(a), extra), len(ln.traj), dtype=a.dtype)], axis=1)
-                b = np.concatenate([b, np.repeat(b[:, -1:], extra, axis=1)], axis=1)
-            starts.append(a)
-            states.append(b)
-            offsets.append(offsets[-1] + len(a))
-            stats["frame_steps"] += len(a) * (len(ln.traj) - 1)
-        all_starts, all_states = np.concatenate(starts), np.concatenate(states)
-        stats["t_pack"] += time.perf_counter() - tic
-        tic = time.perf_counter()
-        out = model.logL_runs_multi([ln.traj for ln in waiting], offsets, all_starts, all_states)
-        stats["t_gpu"] += time.perf_counter() - tic
-        stats["launches"] += 1
-        stats["profiles"] += offsets[-1]
-        for ln, lo, hi in zip(waiting, offsets[:-1], offsets[1:]):
-            ln.answer = out[lo:hi]
-            ln.request = None
-    np.random.set_state(outer_rng)
+    try:
+        while pending or active:
+            while pending and len(active) < limit:
+                active.append(pending.pop(0))
+            # let every active lane run (one at a time, fixed order) until it asks for likelihoods or finishes
+            tic = time.perf_counter()
+            for lane in active:
+                if lane.request is None and not lane.done:
+                    lane.advance(model, sample_kw)
+            stats["t_host_lanes"] += time.perf_counter() - tic
+            for lane in [ln for ln in active if ln.done]:
+                results[lane.idx] = lane.result
+                active.remove(lane)
+            waiting = [ln for ln in active if ln.request is not None]
+            if not waiting:
+                continue
+            # ---- fuse: one launch for all waiting trajectories that share a localisation error (the fused kernel takes
+            #      ONE error structure per launch; with ``model.localization_error`` set that is a single group); profiles
+            #      with fewer runs are padded with empty runs (start = T), which vanish exactly like the empty slices
+            #      of st2profile
+            stats["rounds"] += 1
+            groups = {}
+            for ln in waiting:
+                key = tuple(np.asarray(model._get_noise(ln.traj), dtype=float).ravel())
+                groups.setdefault(key, []).append(ln)
+            for lanes in groups.values():
+                tic = time.perf_counter()
+                K1 = max(ln.request[0].shape[1] for ln in lanes)
+                starts, states, offsets = [], [], [0]
+                for ln in lanes:
+                    ss, thetas = ln.request
+                    if thetas.size and (thetas.min() < 0 or thetas.max() >= model.nStates):
+                        raise ValueError("state index out of range")
+                    a, b = st_to_runs(ss, thetas, len(ln.traj))
+                    if a.shape[1] < K1:
+                        extra = K1 - a.shape[1]
+                        a = np.concatenate([a, np.full((len(a), extra), len(ln.traj), dtype=a.dtype)], axis=1)
+                        b = np.concatenate([b, np.repeat(b[:, -1:], extra, axis=1)], axis=1)
+                    starts.append(a)
+                    states.append(b)
+                    offsets.append(offsets[-1] + len(a))
+                    stats["frame_steps"] += len(a) * (len(ln.traj) - 1)
+                all_starts, all_states = np.concatenate(starts), np.concatenate(states)
+                stats["t_pack"] += time.perf_counter() - tic
+                tic = time.perf_counter()
+                out = model.logL_runs_multi([ln.traj for ln in lanes], offsets, all_starts, all_states)
+                stats["t_gpu"] += time.perf_counter() - tic
+                stats["launches"] += 1
+                stats["profiles"] += offsets[-1]
+                for ln, lo, hi in zip(lanes, offsets[:-1], offsets[1:]):
+                    ln.answer = out[lo:hi]
+                    ln.request = None
+    finally:
+        np.random.set_state(outer_rng)      # also when a lane or a launch raises: the caller's RNG stream is not ours to keep
     return results, stats

@@ -36,12 +36,22 @@ def st_to_runs(ss, thetas, T):
     if K1 > 1:
         switchpos = np.cumsum(ss, axis=1)[:, :-1]
         starts[:, 1:] = np.floor(switchpos * (T - 1)).astype(int) + 1
-    return starts, np.ascontiguousarray(thetas, dtype=np.uint8)
+    return starts, _as_state_bytes(thetas)
+
+
+def _as_state_bytes(states):
+    """uint8 copy of a state array; refuses values that would wrap (the C ABI checks < S, a silent wrap would pass it)."""
+    states = np.asarray(states)
+    if states.size and (states.min() < 0 or states.max() > 255):
+        raise ValueError("state indices must lie in [0, 255]")
+    return np.ascontiguousarray(states, dtype=np.uint8)
 
 
 def states_to_runs(states):
     """Run-length code per-frame state arrays (P, T) -> (starts (P, K1) int32, run_states (P, K1) uint8)."""
     states = np.asarray(states)
+    if states.size and (states.min() < 0 or states.max() > 255):
+        raise ValueError("state indices must lie in [0, 255]")
     if states.ndim == 1:
         states = states[None, :]
     P, T = states.shape

@@ -130,6 +130,7 @@ class MultiStateRouse(MultiStateModel):
         self.device = device
         self._sharder = None
         self._engine = None
+        self._engine_built_for = None
         self._handles = OrderedDict()   # id(traj) -> (fingerprint, TrajectoryHandle)
         self._max_handles = 8192
 
@@ -146,20 +147,35 @@ class MultiStateRouse(MultiStateModel):
         raise ValueError("No localization error specified (use MultiStateModel.localization_error or Trajectory.localization_error)")
 
     # ------------------------------------------------------------------ GPU plumbing
+    def _engine_key(self):
+        """What the GPU copy depends on: the per-state ``_dynamics`` (by identity - `update_dynamics` installs a new
+        dict) and the measurement vector.  The reference re-reads these on every call (pyx:150-160), so an edit of
+        ``models[i]`` (D, k, `update_dynamics`) or of ``measurement`` between two likelihood calls must take effect."""
+        for m in self.models:
+            m.check_dynamics()             # as pyx:152-153: refreshes dynamics whose N / D / k / dt changed
+        return [m._dynamics for m in self.models], np.array(self.measurement, dtype=float)
+
     @property
     def engine(self):
-        """The GPU-resident model (built on first use; rebuilt by `reset_engine` after editing ``models``)."""
-        if self._engine is None:
-            import os
-            from .engine import RouseEngine
-            dev = self.device
-            if dev is None:
-                dev = int(os.environ.get("BILD_B200_DEVICE", os.environ.get("LOCAL_RANK", 0)))
-            self._engine = RouseEngine.from_models(self.models, self.measurement, device=dev)
+        """The GPU-resident model: built on first use, rebuilt when the dynamics or the measurement vector changed."""
+        dyn, w = self._engine_key()
+        if self._engine is not None:
+            old_dyn, old_w = self._engine_built_for
+            if len(old_dyn) == len(dyn) and all(a is b for a, b in zip(old_dyn, dyn)) and np.array_equal(old_w, w):
+                return self._engine
+            self.reset_engine()
+        import os
+        from .engine import RouseEngine
+        dev = self.device
+        if dev is None:
+            dev = int(os.environ.get("BILD_B200_DEVICE", os.environ.get("LOCAL_RANK", 0)))
+        self._engine = RouseEngine.from_models(self.models, self.measurement, device=dev)
+        self._engine_built_for = (dyn, w)
         return self._engine
 
     def reset_engine(self):
         self._engine = None
+        self._engine_built_for = None
         self._handles.clear()
 
     def _handle(self, traj):

@@ -15,6 +15,13 @@
  * Every function returns 0 on success or a negative BILDK_E* code; bildk_last_error() gives the
  * message for the calling thread.  There is NO CPU fallback: without a CUDA device every compute
  * entry point fails with BILDK_ECUDA.
+ *
+ * Thread safety: handles may be shared between host threads.  The host-pointer entry points
+ * (bildk_logl_runs / _st / _states / _runs_multi) serialise on a per-model lock from staging to copy-back;
+ * bildk_amis_weights and bildk_marginal_posterior use per-thread scratch and a private stream.  The
+ * *_device variants only enqueue work: calls on one model that may overlap in time must use ONE stream
+ * (per-model scratch is reused in stream order).  Creating / destroying a handle must not race with calls
+ * that use it.  Every entry point that launches work opens an NVTX range named after itself.
  */
 #ifndef BILD_B200_H
 #define BILD_B200_H
@@ -147,9 +154,6 @@ int bildk_amis_log_proposal(int n_par, int n, int K1, int S, const double *A, co
 int bildk_amis_weights_device(int n, const double *d_logL, const double *d_logdelta,
                               const double *d_cur_log_proposal, double log_nsteps,
                               double *d_log_w, double *d_stats, void *stream);
-
-/* Roofline denominators measured on the spot: FP64 FMA and FP64 MMA (m8n8k4) peak, TFLOP/s. */
-int bildk_measure_fp64_peak(int device, double *dfma_tflops, double *dmma_tflops);
 
 /* Diagnostics: kernels launched by this library since load; description of the kernel variant the
  * next bildk_logl_* call on this trajectory would use for a batch of P ("tile TS=5 G=4 warp ..."). */

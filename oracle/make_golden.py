@@ -188,6 +188,7 @@ def sample_goldens():
     traj = model.trajectory_from_loopingprofile(bild.Loopingprofile(truth))
     np.random.seed(1234)
     res = bild.sample(traj, model)
+    replay_golden(res, traj, truth)
     out["c1_x"] = traj[:]
     out["c1_truth"] = truth
     out["c1_k"] = res.k
@@ -202,6 +203,36 @@ def sample_goldens():
     np.savez_compressed(os.path.join(OUT, "sample_runs.npz"), **out)
 
 
+def replay_golden(res, traj, truth):
+    """
+    Everything needed to replay the config-1 reference run step by step on IDENTICAL profile batches
+    (tests/test_gpu_sample.py::test_replay_reference_batches): per sampler the concatenated samples in draw order
+    (``ss``, ``thetas``, ``logLs``, and - for the AMIS samplers - ``logδs``, ``cur_log_proposal``, ``log_weights`` as
+    they stand at the END of the run), the batch sizes, the evidence triple after every step (amis.py:878-900) and
+    the proposal parameters after every step (amis.py:847-876).
+    """
+    rp = {"x": traj[:], "truth": truth, "n_samplers": np.array(len(res.samplers))}
+    for smp in res.samplers:
+        k = smp.k
+        rp[f"k{k}_sizes"] = np.array([len(b["logLs"]) for b in smp.samples])
+        rp[f"k{k}_ss"] = np.concatenate([b["ss"] for b in smp.samples])
+        rp[f"k{k}_thetas"] = np.concatenate([b["thetas"] for b in smp.samples]).astype(np.int8)
+        rp[f"k{k}_logLs"] = np.concatenate([b["logLs"] for b in smp.samples])
+        rp[f"k{k}_evidences"] = np.array(smp.evidences, dtype=float)
+        rp[f"k{k}_exhausted"] = np.array(bool(smp.exhausted))
+        if "log_weights" in smp.samples[-1]:
+            for key, name in (("logδs", "logdeltas"), ("cur_log_proposal", "cur_log_proposal"), ("log_weights", "log_weights")):
+                rp[f"k{k}_{name}"] = np.concatenate([b[key] for b in smp.samples])
+            rp[f"k{k}_par_a"] = np.array([p[0] for p in smp.parameters])
+            rp[f"k{k}_par_logp"] = np.array([p[1] for p in smp.parameters])
+    rp["post"] = res.log_marginal_posterior()
+    rp["logk"] = res.log["k"]
+    np.savez_compressed(os.path.join(OUT, "sample_c1_replay.npz"), **rp)
+    print("replay golden:", sum(int(np.sum(rp[f"k{s.k}_sizes"])) for s in res.samplers), "profiles in",
+          sum(len(rp[f"k{s.k}_sizes"]) for s in res.samplers), "batches")
+
+
 if __name__ == "__main__":
-    main()
+    if "--sample-only" not in sys.argv:
+        main()
     sample_goldens()

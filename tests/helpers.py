@@ -80,3 +80,16 @@ def random_profiles(rng, P, T, S, kmax=10):
 def rel_err(a, b):
     a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
     return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b)))) if a.size else 0.0
+
+
+def logl_c_parallel(mod, x, s2, Cind, states, threads=None):
+    """The C oracle over every host core: ctypes releases the GIL for the duration of the call, so plain threads
+    scale (a fork pool is not an option inside a process that has initialised CUDA)."""
+    import concurrent.futures as cf
+    states = np.asarray(states)
+    threads = threads or min(len(states), os.cpu_count() or 1)
+    chunks = [c for c in np.array_split(np.arange(len(states)), threads) if len(c)]
+    args = [mod[k] for k in MODEL_KEYS]
+    with cf.ThreadPoolExecutor(len(chunks)) as ex:
+        parts = list(ex.map(lambda c: ko.logl_c(*args, x, s2, Cind, states[c]), chunks))
+    return np.concatenate([np.atleast_1d(p) for p in parts])

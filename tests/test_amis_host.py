@@ -257,7 +257,7 @@ class OracleBackedRouse(bild.models.MultiStateRouse):
         return super().__getattribute__(name)
 
 
-def test_sample_matches_reference_run_rouse_config1(runs):
+def test_sample_matches_reference_run_rouse_config1(runs, replay):
     """BASELINE.json configs[0] with the host layer of the product and the oracle as likelihood."""
     model = OracleBackedRouse(20, 1, 5, d=3, localization_error=0.3)
     traj = bild.Trajectory(runs["c1_x"], localization_error=[0.3] * 3)
@@ -265,22 +265,116 @@ def test_sample_matches_reference_run_rouse_config1(runs):
     res = bild.sample(traj, model)
     assert np.array_equal(res.k, runs["c1_k"])
     assert np.array_equal(res.log["k"], runs["c1_logk"])            # identical sequence of 140 AMIS steps
-    check_c1_evidence(res, runs)
+    check_c1_evidence(res, runs, replay)
 
 
-def check_c1_evidence(res, runs):
+def _finite_rel(a, b):
+    """max relative difference over entries that are finite in both; infinities must coincide."""
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    assert np.array_equal(np.isfinite(a), np.isfinite(b)) and np.array_equal(a[~np.isfinite(a)], b[~np.isfinite(b)])
+    ok = np.isfinite(a)
+    return float(np.max(np.abs(a[ok] - b[ok]) / np.maximum(1.0, np.abs(b[ok])))) if ok.any() else 0.0
+
+
+def check_c1_evidence(res, runs, replay=None):
     """
-    Evidences agree to 1e-9 relative - except where the reference's own profile discretisation is
-    ill-conditioned: a concentrated Dirichlet proposal emits interval lengths at rounding level
-    (s_last ~ 1e-16), so ``floor(cumsum(s) * (T-1))`` (amis.py:688) sits exactly on a frame boundary and a
-    1e-15 perturbation of the proposal (from a 1e-13 difference in logL) moves a switch by one frame.
-    Observed: 1 of 9 samplers, |d logE| ~ 2e-5, no effect on any decision.  Tolerate at most one such
-    sampler and only at that magnitude.
+    FREE run under the reference's seed (the proposals are refitted from OUR likelihoods, which differ from the
+    reference's by ~1e-14): same decisions, and every number within 1e-9 - except where the reference's own profile
+    discretisation is ill-conditioned, which is ASSERTED, not tolerated blindly: a concentrated Dirichlet proposal
+    emits a last interval at rounding level, so ``cumsum(s)[-2] * (T-1)`` lands on the integer T-1 up to a few ulp
+    and ``floor`` (amis.py:688) sends the last switch to frame T (the run vanishes) or T-1 depending on the last bit
+    of s.  A sample may deviate only if (i) its state trace is identical, (ii) its interval lengths agree to 1e-7,
+    (iii) the switch that moved sits within 1e-9 of a frame boundary in the reference's own data.  Samplers without
+    such a tie must reproduce evidence to 1e-9; the (identical-batch) replay test below has no exception at all.
     """
+    tie_k = set()
+    if replay is not None:
+        T = len(replay["x"])
+        for smp in res.samplers:
+            k = smp.k
+            ss = np.concatenate([b["ss"] for b in smp.samples])
+            th = np.concatenate([b["thetas"] for b in smp.samples])
+            ll = np.concatenate([b["logLs"] for b in smp.samples])
+            rss, rth, rll = replay[f"k{k}_ss"], replay[f"k{k}_thetas"].astype(int), replay[f"k{k}_logLs"]
+            assert ss.shape == rss.shape and np.array_equal(th, rth)                       # (i) same batches drawn
+            assert np.max(np.abs(ss - rss)) < 1e-7                                         # (ii)
+            off = np.nonzero(np.abs(ll - rll) > 1e-9 * np.abs(rll))[0]
+            for i in off:                                                                  # (iii) each one is a floor tie
+                c_ref = np.cumsum(rss[i])[:-1] * (T - 1)
+                c_our = np.cumsum(ss[i])[:-1] * (T - 1)
+                moved = np.nonzero(np.floor(c_ref) != np.floor(c_our))[0]
+                assert len(moved) >= 1, f"k={k} sample {i}: logL differs without a moved switch"
+                assert np.all(np.abs(c_ref[moved] - np.round(c_ref[moved])) < 1e-9), (k, i, c_ref[moved])
+            if len(off):
+                tie_k.add(k)
     rel = np.abs(res.evidence - runs["c1_evidence"]) / np.abs(runs["c1_evidence"])
-    assert np.sum(rel > 1e-9) <= 1 and np.max(rel) < 1e-6
+    clean = np.array([k not in tie_k for k in res.k])
+    if replay is None:
+        assert np.sum(rel > 1e-9) <= 1 and np.max(rel) < 1e-6
+    else:
+        assert np.all(rel[clean] < 1e-9), rel
+        assert np.all(rel < 1e-6), rel
+        assert len(tie_k) <= 3
     assert np.array_equal(res.best_profile()[:], runs["c1_best"])
-    np.testing.assert_allclose(np.exp(res.log_marginal_posterior()), np.exp(runs["c1_post"]), atol=1e-4)
+    tol = 1e-9 if (replay is not None and res.best_k() not in tie_k) else 1e-4
+    np.testing.assert_allclose(np.exp(res.log_marginal_posterior()), np.exp(runs["c1_post"]), atol=tol)
+    return tie_k
+
+
+def replay_reference_batches(model, replay, tol=1e-9):
+    """
+    "Identical profile batches" (BASELINE.json north_star): feed OUR `FixedkSampler` the very (ss, thetas) batches the
+    unmodified reference drew in its config-1 run (tests/golden/sample_c1_replay.npz, oracle/make_golden.py) and compare,
+    after EVERY AMIS step: the batch likelihoods, the evidence triple (log evidence, its standard error, KL;
+    amis.py:878-900) and the refitted proposal (amis.py:847-876); at the end the ensemble's log-weights and mixture
+    denominators (amis.py:843-845).  Everything at `tol` relative (1e-9), no exceptions.
+    """
+    traj = bild.Trajectory(replay["x"], localization_error=[0.3] * 3)
+    worst = {}
+    n_steps = 0
+    for k in range(int(replay["n_samplers"])):
+        sizes = replay[f"k{k}_sizes"]
+        off = np.concatenate([[0], np.cumsum(sizes)])
+        ss, th, ll = replay[f"k{k}_ss"], replay[f"k{k}_thetas"].astype(int), replay[f"k{k}_logLs"]
+        ev = replay[f"k{k}_evidences"]
+        smp = amis.FixedkSampler(traj, model, k=k)
+        if f"k{k}_log_weights" not in replay.files:                      # exhaustive sampler: one deterministic batch
+            assert smp.exhausted and len(smp.samples) == 1
+            assert np.array_equal(smp.samples[0]["ss"], ss) and np.array_equal(smp.samples[0]["thetas"], th)
+            w = {"logL": _finite_rel(smp.samples[0]["logLs"], ll), "logev": _finite_rel(np.array(smp.evidences)[:, 0], ev[:, 0]),
+                 "KL": _finite_rel(np.array(smp.evidences)[:, 2], ev[:, 2])}
+        else:
+            w = dict(logL=0.0, logev=0.0, sem=0.0, KL=0.0, alpha=0.0, p=0.0)
+            for j in range(len(sizes)):
+                lo, hi = off[j], off[j + 1]
+                smp.dirichlet.sample = lambda a, N, lo=lo, hi=hi: ss[lo:hi].copy()
+                smp.cfc.sample = lambda logp, N, lo=lo, hi=hi: th[lo:hi].copy()
+                assert smp.step() is True
+                n_steps += 1
+                e = smp.evidences[-1]
+                w["logL"] = max(w["logL"], _finite_rel(smp.samples[-1]["logLs"], ll[lo:hi]))
+                w["logev"] = max(w["logev"], abs(e[0] - ev[j, 0]) / abs(ev[j, 0]))
+                w["sem"] = max(w["sem"], abs(e[1] - ev[j, 1]) / abs(ev[j, 1]))
+                w["KL"] = max(w["KL"], abs(e[2] - ev[j, 2]) / max(1.0, abs(ev[j, 2])))
+                w["alpha"] = max(w["alpha"], _finite_rel(smp.parameters[-1][0] / replay[f"k{k}_par_a"][j + 1], np.ones(k + 1)))
+                w["p"] = max(w["p"], float(np.max(np.abs(np.exp(smp.parameters[-1][1]) - np.exp(replay[f"k{k}_par_logp"][j + 1])))))
+            w["log_weights"] = _finite_rel(np.concatenate([b["log_weights"] for b in smp.samples]), replay[f"k{k}_log_weights"])
+            w["logdeltas"] = _finite_rel(np.concatenate([b["logδs"] for b in smp.samples]), replay[f"k{k}_logdeltas"])
+            assert smp.exhausted == bool(replay[f"k{k}_exhausted"])
+        worst[k] = w
+        assert max(w.values()) < tol, (k, w)
+    assert n_steps == len(replay["logk"])                                # all 140 AMIS steps of the reference run
+    return worst
+
+
+@pytest.fixture(scope="module")
+def replay(golden_dir):
+    return np.load(os.path.join(golden_dir, "sample_c1_replay.npz"))
+
+
+def test_replay_reference_batches_host(replay):
+    """CPU: host AMIS layer + C oracle likelihood on the reference's own batches, 1e-9 after every one of the 140 steps."""
+    replay_reference_batches(OracleBackedRouse(20, 1, 5, d=3, localization_error=0.3), replay)
 
 
 def test_postproc_with_batched_model():
@@ -363,3 +457,57 @@ def test_generator_api_equals_synchronous_api():
     with pytest.raises(StopIteration) as stop:
         gen.send(model.logL_st_batch(ss, thetas, traj))
     assert stop.value.value is True and len(smp.samples) == 2
+
+
+def test_log_proposal_numpy_statement_equals_native_helper(monkeypatch):
+    """`FixedkSampler.log_proposal_multi` without the built library (pure-CPU models on a machine without nvcc) uses the
+    numpy statement of the same arithmetic; both agree, including the +inf conventions of amis.py:98-108."""
+    model = bild.models.FactorizedModel([scipy.stats.maxwell(scale=1), scipy.stats.maxwell(scale=4)], d=1)
+    traj = bild.Trajectory(np.linspace(0.5, 4.0, 12))
+    smp = amis.FixedkSampler(traj, model, k=3, N=40, max_fcomplete=1)
+    np.random.seed(5)
+    for _ in range(4):
+        smp.step()
+    ss = np.concatenate([b["ss"] for b in smp.samples])
+    th = np.concatenate([b["thetas"] for b in smp.samples])
+    ss[0] = [0.5, 0.5, 0.0, 0.0]                     # zeros on the boundary: +inf where a_i < 1
+    pars = smp.parameters + [(np.array([0.5, 2.0, 0.7, 1.0]), smp.parameters[-1][1])]
+    native = smp.log_proposal_multi(pars, ss, th)
+    monkeypatch.setattr(amis, "_NATIVE", False)
+    host = smp.log_proposal_multi(pars, ss, th)
+    assert np.array_equal(np.isposinf(native), np.isposinf(host)) and np.isposinf(host[-1, 0])
+    ok = np.isfinite(native)
+    np.testing.assert_allclose(host[ok], native[ok], rtol=1e-12, atol=1e-12)
+
+
+def test_sample_many_groups_by_localization_error_and_restores_rng():
+    """Trajectories that carry their OWN, differing localisation errors (model.localization_error is None) are fused per
+    error group, results equal the one-by-one runs; an exception inside a run leaves the caller's RNG state untouched."""
+    from bild_b200.dataset import sample_many
+    model = OracleBackedRouse(8, 1, 5, d=2)
+    gen = OracleBackedRouse(8, 1, 5, d=2, localization_error=0.3)
+    np.random.seed(33)
+    trajs = [gen.trajectory_from_loopingprofile(bild.Loopingprofile([0] * a + [1] * b)) for a, b in [(10, 9), (7, 12), (12, 8)]]
+    for tr, err in zip(trajs, (0.3, 0.2, 0.3)):
+        tr.localization_error = np.array([err, err])
+    kw = dict(init_runs=3, sampler_kw={"N": 15, "max_fcomplete": 40}, k_max=3, certainty_in_k=0.9)
+    seeds = [7, 8, 9]
+    np.random.seed(99)
+    before = np.random.get_state()[1].copy()
+    res, stats = sample_many(trajs, model, seeds=seeds, **kw)
+    assert np.array_equal(np.random.get_state()[1], before)
+    assert stats["launches"] > stats["rounds"]                     # two error groups -> more launches than rounds
+    for i, tr in enumerate(trajs):
+        np.random.seed(seeds[i])
+        solo = bild.sample(tr, model, **kw)
+        assert np.array_equal(solo.evidence, res[i].evidence) and solo.best_profile() == res[i].best_profile()
+
+    class Boom(OracleBackedRouse):
+        def logL_runs_multi(self, *a, **k):
+            raise RuntimeError("boom")
+
+    bad = Boom(8, 1, 5, d=2)
+    np.random.seed(99)
+    with pytest.raises(RuntimeError, match="boom"):
+        sample_many(trajs, bad, seeds=seeds, **kw)
+    assert np.array_equal(np.random.get_state()[1], before)

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import kalman_oracle as ko
-from helpers import MODEL_KEYS, golden_cases, load_golden, oracle_model, random_profiles, rel_err, synth_traj
+from helpers import MODEL_KEYS, golden_cases, load_golden, logl_c_parallel, oracle_model, random_profiles, rel_err, synth_traj
 
 pytestmark = pytest.mark.gpu
 
@@ -285,6 +285,37 @@ def test_round_trip_properties_full_size():
     traj_p = eng.trajectory(x[:, [2, 0, 1]], [0.3] * d)
     e = eng.logl_st(traj_p, ss[:256], thetas[:256])
     assert rel_err(e, a[:256]) < 1e-12
+
+
+FULL_SIZE = [
+    # name, N, T, P, p_nan, n_check                                      BASELINE.json sizes, checked on a random sample
+    ("north-star N=50 T=1000", 50, 1000, 16384, 0.0, 256),                # k_mma2
+    ("configs[2] N=100 T=1000 10% NaN", 100, 1000, 16384, 0.10, 256),     # k_mmact
+    ("sweep N=200 T=100", 200, 100, 1024, 0.0, 256),                      # k_mmag2
+]
+
+
+@pytest.mark.parametrize("name,N,T,P,p_nan,n_check", FULL_SIZE, ids=[c[0] for c in FULL_SIZE])
+def test_full_size_sampled_parity(name, N, T, P, p_nan, n_check):
+    """The batch of the BASELINE configuration at FULL size on the GPU; `n_check` randomly chosen filters of it against the
+    C oracle (all host cores), 1e-9 relative; plus the size-independent properties (bitwise permutation equivariance)."""
+    rng = np.random.default_rng(50 + N)
+    mod = oracle_model(N, d=3)
+    x, _ = synth_traj(mod, T, rng, 0.3, p_nan=p_nan)
+    ss, thetas = random_profiles(rng, P, T, 2, 10)
+    eng = engine_for(mod)
+    traj = eng.trajectory(x, [0.3] * 3)
+    got = eng.logl_st(traj, ss, thetas)
+    assert np.all(np.isfinite(got))
+    idx = np.sort(rng.choice(P, n_check, replace=False))
+    s2, Cind = ko.noise_to_s2_cind([0.3] * 3)
+    st = np.array([ko.st2states(ss[i], thetas[i], T) for i in idx])
+    want = logl_c_parallel(mod, x, s2, Cind, st)
+    assert rel_err(got[idx], want) < TOL
+    # the checked filters evaluated alone, in another order, in a small batch (other CTA / wave geometry): same bits
+    perm = rng.permutation(n_check)
+    again = eng.logl_st(traj, ss[idx][perm], thetas[idx][perm])
+    assert np.array_equal(again, got[idx][perm])
 
 
 def test_in_library_profile_coding_matches_numpy():

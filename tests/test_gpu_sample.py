@@ -10,7 +10,7 @@ import pytest
 
 import kalman_oracle as ko
 import bild_b200 as bild
-from test_amis_host import check_c1_evidence
+from test_amis_host import check_c1_evidence, replay_reference_batches
 
 pytestmark = pytest.mark.gpu
 
@@ -36,14 +36,29 @@ def test_models_logL_reference_fixture():
     assert np.array_equal(model2.initial_loopingprofile(traj).state, [1, 0, 0, 0])
 
 
-def test_sample_config1_matches_reference_run(runs):
+@pytest.fixture(scope="module")
+def replay(golden_dir):
+    return np.load(os.path.join(golden_dir, "sample_c1_replay.npz"))
+
+
+def test_replay_reference_batches(replay):
+    """The reference's own 142 profile batches through the GPU engine and the device weight reduction: likelihoods, weights,
+    evidence, standard error, KL and refitted proposals within 1e-9 of the reference after every AMIS step."""
+    model = bild.models.MultiStateRouse(20, 1, 5, d=3, localization_error=0.3)
+    worst = replay_reference_batches(model, replay, tol=1e-9)
+    assert max(w["logL"] for w in worst.values()) < 1e-12
+    from bild_b200 import _lib
+    assert _lib.load().bildk_launch_count() >= 142
+
+
+def test_sample_config1_matches_reference_run(runs, replay):
     model = bild.models.MultiStateRouse(20, 1, 5, d=3, localization_error=0.3)
     traj = bild.Trajectory(runs["c1_x"], localization_error=[0.3] * 3)
     np.random.seed(1234)
     res = bild.sample(traj, model)
     assert np.array_equal(res.k, runs["c1_k"])
     assert np.array_equal(res.log["k"], runs["c1_logk"])
-    check_c1_evidence(res, runs)
+    check_c1_evidence(res, runs, replay)
     # every likelihood batch went through the CUDA library
     from bild_b200 import _lib
     assert _lib.load().bildk_launch_count() >= int(runs["c1_n_logl_batches"])

@@ -232,3 +232,45 @@ def test_tile_slot_tables():
         assert len(seen) == GT * (GT + 1) // 2
         assert (t[0, 2], t[0, 3]) == (0, GT - 1)
         assert max(sched) - min(sched) <= 3, (GT, sched)      # e.g. GT = 13: 24 / 23 / 23 / 21 of 91 tiles
+
+
+# ------------------------------------------------------------------ round-2 host-side behaviour
+def test_engine_rebuilt_when_model_edited(monkeypatch):
+    """The reference re-reads the dynamics and the measurement vector on every call (pyx:150-160): editing either
+    between two likelihood calls must invalidate the GPU copy (no device needed: the engine factory is stubbed)."""
+    import bild_b200 as bild
+    from bild_b200 import engine as eng_mod
+    built = []
+
+    class Dummy:
+        device = 0
+
+    def fake(models, measurement, device=0):
+        built.append((models[1]._dynamics["B"][0, 0], float(measurement[-1])))
+        return Dummy()
+
+    monkeypatch.setattr(eng_mod.RouseEngine, "from_models", staticmethod(fake))
+    model = bild.models.MultiStateRouse(6, 1, 5, d=2, localization_error=0.3)
+    e1 = model.engine
+    assert model.engine is e1 and len(built) == 1
+    model.models[1].k = 2.0                         # check_dynamics() notices the stale k and refreshes -> new dynamics dict
+    e2 = model.engine
+    assert e2 is not e1 and len(built) == 2 and built[1][0] != built[0][0]
+    model.models[0].update_dynamics()               # explicit refresh: new dict, engine follows
+    assert model.engine is not e2 and len(built) == 3
+    e3 = model.engine
+    model.measurement[-1] = 0.5
+    assert model.engine is not e3 and built[-1][1] == 0.5
+    assert model.engine is model.engine
+
+
+def test_state_arrays_refuse_values_that_would_wrap():
+    from bild_b200.engine import st_to_runs, states_to_runs
+    with pytest.raises(ValueError):
+        st_to_runs(np.array([[0.5, 0.5]]), np.array([[0, 256]]), 10)
+    with pytest.raises(ValueError):
+        states_to_runs(np.array([[0, 0, 300, 300]]))
+    with pytest.raises(ValueError):
+        states_to_runs(np.array([[0, -1, 0, 0]]))
+    a, b = states_to_runs(np.array([[0, 0, 255, 255]]))
+    assert b.tolist() == [[0, 255]] and a.tolist() == [[0, 2]]

@@ -128,6 +128,42 @@ static double time_ms(F launch, int reps) {
     return best;
 }
 
+// Roofline denominators for bench.py / tools/sweep.py (MEASURED_PEAKS.json has no FP64 entry).  Built as its own
+// small library, tools/libfp64peak.so (bild_b200/build.py), NOT part of the product ABI:
+//   fp64_peak_measure(device, &dfma_tflops, &dmma_tflops) -> 0 on success, else the CUDA error code
+extern "C" int fp64_peak_measure(int device, double* dfma_tflops, double* dmma_tflops) {
+    cudaError_t e;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return static_cast<int>(e);
+    int sms = 0;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return static_cast<int>(e);
+    double* d = nullptr;
+    if ((e = cudaMalloc(&d, 8)) != cudaSuccess) return static_cast<int>(e);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int iters = 4096, blocks = sms * 4;   // 32 warps per SM
+    double best[2] = {1e30, 1e30};
+    for (int which = 0; which < 2; ++which)
+        for (int rep = 0; rep < 7; ++rep) {
+            cudaEventRecord(e0);
+            if (which == 0) k_dfma<16><<<blocks, 256>>>(d, iters, 1.0000001, 1e-9);
+            else k_dmma<8><<<blocks, 256>>>(d, iters, 1.0000001, 1e-9);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep >= 2 && ms < best[which]) best[which] = ms;
+        }
+    e = cudaGetLastError();
+    *dfma_tflops = 2.0 * 16 * iters * 256.0 * blocks / best[0] * 1e-9;
+    *dmma_tflops = 2.0 * 256 * 8 * iters * 8.0 * blocks / best[1] * 1e-9;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    return static_cast<int>(e);
+}
+
+#ifndef FP64_PEAK_NO_MAIN
 int main() {
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
     int sms = prop.multiProcessorCount;
@@ -178,3 +214,4 @@ int main() {
     printf("\n}\n");
     return 0;
 }
+#endif

@@ -5,7 +5,6 @@ Cython path on all host cores (bounded sample per point).  One JSON object per p
     python tools/sweep.py [--quick] > profiles/sweep.jsonl
 """
 import argparse
-import ctypes
 import json
 import os
 import sys
@@ -18,7 +17,7 @@ import bench  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--quick", action="store_true")
-ap.add_argument("--cpu-seconds", type=float, default=4.0, help="CPU work per point (core-seconds) for the reference sample")
+ap.add_argument("--cpu-seconds", type=float, default=2.0, help="wall seconds on all cores per point and CPU implementation")
 ap.add_argument("--only-N", type=int, nargs="*", default=None, help="restrict the sweep to these polymer sizes")
 a = ap.parse_args()
 
@@ -29,34 +28,29 @@ points = [(N, T, P) for N in Ns for T in Ts for P in Ps]
 if a.quick:
     points = [(N, 100, 1024) for N in Ns]
 
-# CPU legs first (fork pools must precede CUDA initialisation)
+# CPU legs first (fork pools must precede CUDA initialisation): the reference's compiled .pyx AND its pure-Python twin
+# (MSRouse_logL_py.py, the faster CPU path for N >= 50) on all host cores; the speed-up is quoted against the faster one
 sys.path.insert(0, os.path.join(bench.ROOT, "oracle"))
 import kalman_oracle as ko  # noqa: E402
 cpu = {}
-inputs = {}
 for N, T, P in points:
     key = (N, T)
     if key in cpu:
         continue
     wl = dict(N=N, T=T, P=2048, p_nan=0.0)
     model, traj, ss, thetas = bench.make_inputs(wl, 0)
-    inputs[key] = (model, traj)
-    probe_states = np.array([ko.st2states(ss[i], thetas[i], T) for i in range(16)])
-    probe = bench.cpu_reference(model, traj, probe_states, 16)
-    per_eval = probe["seconds"] * min(probe["cores"], probe["n"]) / probe["n"]
-    n = int(min(2048, max(probe["cores"], a.cpu_seconds / max(per_eval, 1e-9))))
-    states = np.array([ko.st2states(ss[i], thetas[i], T) for i in range(n)])
-    r = bench.cpu_reference(model, traj, states, n)
-    cpu[key] = dict(frame_steps_per_s=n * (T - 1) / r["seconds"], cores=r["cores"], kind=r["kind"], n=n, logL=r["logL"], ss=ss[:n], thetas=thetas[:n])
-    print(f"# cpu N={N} T={T}: {cpu[key]['frame_steps_per_s']:.4g} frame-steps/s on {r['cores']} cores ({n} profiles)", file=sys.stderr, flush=True)
+    r = bench.cpu_arm(wl, model, traj, ss, thetas, budget_s=a.cpu_seconds)
+    best = r["impls"][r["best"]]
+    pyx = r["impls"].get("cython_pyx", best)
+    cpu[key] = dict(frame_steps_per_s=best["frame_steps_per_s"], cores=best["cores"], kind=r["kind"], impl=r["best"], n=pyx["n"], logL=pyx["logL"],
+                    ss=ss[:pyx["n"]], thetas=thetas[:pyx["n"]],
+                    all={k: v["frame_steps_per_s"] for k, v in r["impls"].items()})
 
 import torch  # noqa: E402
 from bild_b200 import _lib  # noqa: E402
 from bild_b200.engine import st_to_runs  # noqa: E402
 lib = _lib.load()
-dfma, dmma = ctypes.c_double(), ctypes.c_double()
-_lib.check(lib.bildk_measure_fp64_peak(0, ctypes.byref(dfma), ctypes.byref(dmma)))
-peak = max(dfma.value, dmma.value)
+peak = max(bench.measure_fp64_peak(0))
 dev = torch.device("cuda", 0)
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 rows = []
@@ -93,7 +87,6 @@ for N, T, P in points:
     host = model.logL_st_batch(ss, thetas, traj)
     e2e_s = time.perf_counter() - t0
     c = cpu[(N, T)]
-    ref_model, ref_traj = inputs[(N, T)]
     # parity on the CPU sample: same model parameters and seed -> same trajectory; evaluate the CPU sample's profiles
     chk = model.logL_st_batch(c["ss"], c["thetas"], traj)
     want, note = c["logL"], ""
@@ -110,17 +103,17 @@ for N, T, P in points:
     fl = bench.flops_per_eval(N, 3, 1, T, T) * P
     row = dict(N=N, T=T, P=P, kernel_ms=ms, frame_steps_per_s=P * (T - 1) / (ms * 1e-3), evals_per_s=P / (ms * 1e-3),
                e2e_frame_steps_per_s=P * (T - 1) / e2e_s, tflops=fl / (ms * 1e-3) * 1e-12, frac_of_fp64_peak=fl / (ms * 1e-3) * 1e-12 / peak,
-               cpu_frame_steps_per_s=c["frame_steps_per_s"], cpu_cores=c["cores"], cpu_kind=c["kind"], cpu_sample=c["n"],
+               cpu_frame_steps_per_s=c["frame_steps_per_s"], cpu_cores=c["cores"], cpu_kind=c["kind"], cpu_impl=c["impl"], cpu_all=c["all"], cpu_sample=c["n"],
                speedup_vs_cpu=P * (T - 1) / (ms * 1e-3) / c["frame_steps_per_s"], max_rel_err_vs_cpu=rel,
                plan=th.describe_plan(P), peak_tflops=peak, note=note)
     rows.append(row)
     print(json.dumps(row), flush=True)
 
-print("\n| N | T | P | kernel ms | frame-steps/s | TFLOP/s (alg.) | of FP64 peak | CPU ref (all cores) | speed-up | max rel err | kernel |", file=sys.stderr)
+print("\n| N | T | P | kernel ms | frame-steps/s | TFLOP/s (alg.) | of FP64 peak | CPU ref, faster of .pyx / twin (all cores) | speed-up | max rel err | kernel |", file=sys.stderr)
 print("|---|---|---|---|---|---|---|---|---|---|---|", file=sys.stderr)
 for r in rows:
     if "skipped" in r:
         print(f"| {r['N']} | {r['T']} | {r['P']} | - | - | - | - | - | - | - | {r['skipped']} |", file=sys.stderr)
     else:
         print(f"| {r['N']} | {r['T']} | {r['P']} | {r['kernel_ms']:.2f} | {r['frame_steps_per_s']:.3g} | {r['tflops']:.1f} | {r['frac_of_fp64_peak']:.2f} | "
-              f"{r['cpu_frame_steps_per_s']:.3g} ({r['cpu_cores']} cores) | {r['speedup_vs_cpu']:.0f}x | {r['max_rel_err_vs_cpu']:.1e} | {r['plan'].split(' threads')[0]} |", file=sys.stderr)
+              f"{r['cpu_frame_steps_per_s']:.3g} ({r['cpu_impl']}, {r['cpu_cores']} cores) | {r['speedup_vs_cpu']:.0f}x | {r['max_rel_err_vs_cpu']:.1e} | {r['plan'].split(' threads')[0]} |", file=sys.stderr)
