@@ -194,24 +194,48 @@ def cpu_arm(wl, model, traj, ss, thetas, budget_s, only=None):
     T, P = wl["T"], len(ss)
     impls, kind = reference_impls(model, traj)
     cores = os.cpu_count() or 1
-    n_probe = min(P, max(8, cores))
+    n_probe = min(P, cores)
     states_probe = np.array([ko.st2states(ss[i], thetas[i], T) for i in range(n_probe)])
-    out = {}
+    # pre-probe: one profile on a trajectory truncated to 24 frames, single process - an implementation that is more than
+    # 4x slower per frame than the best one here is not timed on the pool (e.g. the pure-Python twin at N = 200 with k = 5:
+    # B = exp(-kA) is full of denormals and numpy's dgemm crawls at ~0.4 s per frame)
+    from bild_b200.trajectory import Trajectory
+    from bild_b200.util import Loopingprofile
+    Tp = min(T, 24)
+    short = Trajectory(np.ascontiguousarray(traj[:][:Tp]), localization_error=model._get_noise(traj))
+    per_frame = {}
     for name, fn in impls.items():
         if only and name != only:
+            continue
+        prof = Loopingprofile(states_probe[0][:Tp])
+        fn(model, prof, short)
+        t0 = time.perf_counter()
+        fn(model, prof, short)
+        per_frame[name] = (time.perf_counter() - t0) / Tp
+    fastest = min(per_frame.values())
+    out, skipped = {}, {}
+    for name, fn in impls.items():
+        if name not in per_frame:
+            continue
+        if per_frame[name] > 4.0 * fastest:
+            skipped[name] = f"not timed on the pool: {per_frame[name] * 1e3:.3g} ms per frame in the single-profile probe vs {fastest * 1e3:.3g} ms for the fastest implementation"
+            log(f"cpu {wl['N']}x{T} {name}: {skipped[name]}")
             continue
         probe = pool_time(fn, model, traj, states_probe, n_probe)
         per_eval_wall = probe["seconds"] / max(1, -(-probe["n"] // probe["cores"]))      # one eval on one core
         n_sample = int(min(P, max(probe["cores"], budget_s / max(per_eval_wall, 1e-9) * probe["cores"])))
         n_sample = max(probe["cores"], n_sample // probe["cores"] * probe["cores"])
         n_sample = min(n_sample, P)
-        states = np.array([ko.st2states(ss[i], thetas[i], T) for i in range(n_sample)])
-        r = pool_time(fn, model, traj, states, n_sample)
+        if n_sample <= probe["n"]:
+            r = probe                                   # the probe already was a full sample of this size
+        else:
+            states = np.array([ko.st2states(ss[i], thetas[i], T) for i in range(n_sample)])
+            r = pool_time(fn, model, traj, states, n_sample)
         r["frame_steps_per_s"] = r["n"] * (T - 1) / r["seconds"]
         out[name] = r
         log(f"cpu {wl['N']}x{T} {name}: {r['frame_steps_per_s']:.4g} frame-steps/s on {r['cores']} cores ({r['n']} profiles, {r['seconds']:.2f} s)")
     best = max(out, key=lambda k: out[k]["frame_steps_per_s"])
-    return {"impls": out, "best": best, "kind": kind}
+    return {"impls": out, "best": best, "kind": kind, "skipped": skipped}
 
 
 def cpu_baseline_record(cpu, P):
@@ -219,6 +243,7 @@ def cpu_baseline_record(cpu, P):
     return {"value": b["frame_steps_per_s"], "unit": UNIT, "cores": b["cores"], "kind": cpu["kind"], "implementation": cpu["best"],
             "sample": f"first {b['n']} of {P} profiles, multiprocessing fork pool over all host cores, 1 BLAS thread per worker",
             "all": {k: {"value": v["frame_steps_per_s"], "profiles": v["n"], "seconds": v["seconds"]} for k, v in cpu["impls"].items()},
+            "skipped": cpu.get("skipped", {}),
             "note": "the faster of the reference's compiled .pyx and its pure-Python twin is quoted (SURVEY.md 8d)"}
 
 

@@ -42,6 +42,11 @@ SYMBOLS = {
                                                 ctypes.POINTER(ctypes.c_int64), c_double_p]),
     "bildk_amis_weights_device": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,
                                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "bildk_amis_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_uint8_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "bildk_amis_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "bildk_amis_size": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    "bildk_amis_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_double_p, ctypes.POINTER(ctypes.c_int64), c_double_p, c_double_p,
+                                        c_double_p, c_double_p, c_double_p]),
     "bildk_launch_count": (ctypes.c_longlong, []),
     "bildk_describe_plan": (ctypes.c_char_p, [ctypes.c_void_p, ctypes.c_int]),
     "bildk_debug_tables": (ctypes.c_int, [ctypes.c_int] * 4 + [c_uint8_p]),

@@ -115,6 +115,11 @@ class Dirichlet:
             w /= np.sum(w)
             m = w @ ss
             v = w @ (ss - m[None, :]) ** 2
+        return self.estimate_from_moments(m, v)
+
+    @staticmethod
+    def estimate_from_moments(m, v):
+        """``alpha`` from the weighted mean ``m`` and variance ``v`` of the interval lengths (amis.py:145-151)."""
         if np.any(v == 0):
             A = 1e10   # degenerate ensemble: very concentrated but finite; the concentration brake takes over
         else:
@@ -177,6 +182,10 @@ class CFC:
         """Method of marginals (amis.py:283-305): weighted state marginals per slot -> weight parameters."""
         onehot = thetas[None, :, :] == np.arange(self.n)[:, None, None]     # (n, N, k+1)
         log_marginals = _lse(np.broadcast_to(log_weights[None, :, None], onehot.shape), axis=1, mask=onehot)
+        return self.estimate_from_log_marginals(log_marginals)
+
+    def estimate_from_log_marginals(self, log_marginals):
+        """Weight parameters from the (unnormalised) per-slot log marginals ``(n, k+1)`` (amis.py:302-305)."""
         log_marginals = log_marginals - _lse(log_marginals, axis=0, keepdims=True)
         return self.logp_from_marginals(log_marginals)
 
@@ -396,16 +405,17 @@ class FixedkSampler:
         self.exhausted = True
 
     # ------------------------------------------------------------------ one AMIS iteration
-    def step(self):
-        """Returns False (and does nothing) if the sampler is exhausted, True otherwise."""
-        return drive(self.step_gen(), self.logL)
+    def _device_ensemble(self):
+        """The device-resident ensemble of this sampler (created on first use), or None: model without a GPU engine, or a
+        shape beyond the device kernel (more than 32 slots / 4 states)."""
+        if not hasattr(self, "_ens"):
+            make = getattr(self.model, "amis_ensemble", None)
+            self._ens = make(self.k + 1, self.cfc.transitions) if make is not None and not self.samples else None
+        return self._ens
 
-    def step_gen(self):
-        """Generator form of `step`: yields the ``(ss, thetas)`` batch whose likelihoods it needs."""
-        if self.exhausted:
-            return False
-        cur = self.parameters[-1]
-
+    def _step_host(self, cur):
+        """Host (numpy) bookkeeping of one AMIS iteration - models without a GPU engine.  Returns
+        ``(summary or None, log_w, new_a, new_logp)``."""
         # the current proposal joins the mixture: update the denominators of all previous samples
         if self.samples:
             sizes = [len(smp["logLs"]) for smp in self.samples]
@@ -437,9 +447,43 @@ class FixedkSampler:
             smp["log_weights"] = lw
 
         # refit the proposal
-        old_a, old_logp = cur
         new_a = self.dirichlet.estimate(ens["ss"], log_w)
         new_logp = self.cfc.estimate(ens["thetas"], log_w)
+        self._host_ens = {"logLs": ens["logLs"], "cur_log_proposal": ens["cur_log_proposal"]}
+        return summary, log_w, new_a, new_logp
+
+    def step(self):
+        """Returns False (and does nothing) if the sampler is exhausted, True otherwise."""
+        return drive(self.step_gen(), self.logL)
+
+    def step_gen(self):
+        """Generator form of `step`: yields the ``(ss, thetas)`` batch whose likelihoods it needs."""
+        if self.exhausted:
+            return False
+        cur = self.parameters[-1]
+
+        device = self._device_ensemble()
+        if device is not None:
+            # ---- bookkeeping on the device (bildk_amis_step): the ensemble and all proposals live in HBM; only the new
+            #      batch goes up, only the statistics of the refit (and the per-sample log weights) come back
+            new = {"ss": self.dirichlet.sample(cur[0], self.N), "thetas": self.cfc.sample(cur[1], self.N)}   # RNG order: Dirichlet -> CFC
+            new["logLs"] = yield (new["ss"], new["thetas"])
+            new["logLs"] = np.asarray(new["logLs"], dtype=float)
+            summary, mom_m, mom_v, log_marginals, per = device.step(new["ss"], new["thetas"], new["logLs"], cur[0], cur[1])
+            self.samples.append(new)
+            log_w = per[:, 0]
+            lo = 0
+            for smp in self.samples:                 # views into the ensemble-level buffer the device call refreshed
+                hi = lo + len(smp["logLs"])
+                smp["log_weights"], smp["logδs"], smp["cur_log_proposal"] = per[lo:hi, 0], per[lo:hi, 1], per[lo:hi, 2]
+                lo = hi
+            old_a, old_logp = cur
+            new_a = self.dirichlet.estimate_from_moments(mom_m.copy(), mom_v)
+            new_logp = self.cfc.estimate_from_log_marginals(log_marginals)
+        else:
+            summary, log_w, new_a, new_logp = yield from self._step_host(cur)
+            ens = self._host_ens
+            old_a, old_logp = cur
 
         ratio = np.log(np.sum(new_a) / np.sum(old_a))           # concentration brake
         cap = self.N * self.brakes[0]

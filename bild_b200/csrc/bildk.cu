@@ -9,6 +9,7 @@
 #include "bildk_mmar.cuh"
 #include "bildk_mmag2.cuh"
 #include "bildk_mmact.cuh"
+#include "bildk_amis.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -1072,6 +1073,7 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
             rp.k = kp;
             rp.Br = m->dBr; rp.Sigm = m->dSigm; rp.C0m = m->dC0m;
             rp.WPC = pl.WPC; rp.fstride = pl.fstride; rp.r = m->r_last;
+            rp.ww00 = m->wz_val[0] * m->wz_val[0]; rp.ww11 = m->wz_val[1] * m->wz_val[1]; rp.ww01 = 2.0 * m->wz_val[0] * m->wz_val[1];
             for (int e = 0; e < dstar; ++e) mmar_tables(m->GT, m->r_last, t0->ncols[e], rp.lastrow[e], rp.mrow[e]);
             CU(mmar_launch_for(m->GT, pl.nb, rp, grid, pl.threads, pl.smem, st));
         } else if (pl.mma2) {
@@ -1488,5 +1490,202 @@ extern "C" int bildk_amis_weights_device(int n, const double* d_logL, const doub
     if (n < 1 || !d_logL || !d_logdelta || !d_curlp || !d_stats) return fail(BILDK_EINVAL, "bad argument");
     NvtxRange nvtx("bildk_amis_weights_device");
     CU(launch_amis_weights(n, d_logL, d_logdelta, d_curlp, log_nsteps, d_log_w, d_stats, static_cast<cudaStream_t>(stream)));
+    return BILDK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device-resident AMIS ensemble (bildk_amis.cuh): one call per AMIS iteration.
+template <typename T>
+static int grow_keep(T** p, size_t* cap, size_t used, size_t need, cudaStream_t st) {   // growable device array, contents kept
+    if (need <= *cap) return BILDK_OK;
+    size_t want = std::max(need, *cap * 2);
+    T* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, want * sizeof(T));
+    if (e != cudaSuccess) return fail(BILDK_ENOMEM, "cudaMalloc(%zu bytes): %s", want * sizeof(T), cudaGetErrorString(e));
+    if (*p && used) {
+        e = cudaMemcpyAsync(q, *p, used * sizeof(T), cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { cudaFree(q); return fail(BILDK_ECUDA, "device copy failed: %s", cudaGetErrorString(e)); }
+    }
+    if (*p) cudaFree(*p);
+    *p = q;
+    *cap = want;
+    return BILDK_OK;
+}
+
+struct bildk_amis {
+    int device = 0, K1 = 0, S = 0;
+    int n = 0, n_par = 0;
+    std::vector<uint8_t> transitions;
+    // ensemble (capacities in samples)
+    double *ss = nullptr, *logs = nullptr, *logL = nullptr, *per = nullptr;
+    uint8_t *thetas = nullptr, *flags = nullptr;
+    size_t cap_ss = 0, cap_logs = 0, cap_logL = 0, cap_per = 0, cap_th = 0, cap_fl = 0;
+    // proposals (capacities in proposals)
+    double *A = nullptr, *lognorm = nullptr, *logp = nullptr, *reach = nullptr, *norm0 = nullptr;
+    size_t cap_A = 0, cap_ln = 0, cap_lp = 0, cap_rc = 0, cap_n0 = 0;
+    double* head = nullptr;        // [4 + 2 K1 + S K1]
+    double* stage = nullptr;       // device staging of one step's inputs
+    size_t cap_stage = 0;
+    double* pinned = nullptr;      // host staging (inputs) / copy-back (head + 3 n)
+    size_t cap_pinned = 0;
+    cudaStream_t st = nullptr;
+    std::mutex mu;
+};
+
+extern "C" int bildk_amis_destroy(bildk_amis_t h) {
+    if (!h) return BILDK_OK;
+    cudaSetDevice(h->device);
+    for (void* q : {static_cast<void*>(h->ss), static_cast<void*>(h->logs), static_cast<void*>(h->logL), static_cast<void*>(h->per),
+                    static_cast<void*>(h->thetas), static_cast<void*>(h->flags), static_cast<void*>(h->A), static_cast<void*>(h->lognorm),
+                    static_cast<void*>(h->logp), static_cast<void*>(h->reach), static_cast<void*>(h->norm0), static_cast<void*>(h->head),
+                    static_cast<void*>(h->stage)})
+        if (q) cudaFree(q);
+    if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+    return BILDK_OK;
+}
+
+extern "C" int bildk_amis_create(int K1, int S, const uint8_t* transitions, int device, bildk_amis_t* out) {
+    if (!out) return fail(BILDK_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (K1 < 1 || S < 1 || !transitions) return fail(BILDK_EINVAL, "bad argument");
+    if (K1 > AMIS_MAXK1 || S > AMIS_MAXS)
+        return fail(BILDK_EUNSUP, "the device AMIS ensemble handles up to %d slots and %d states (got %d, %d)", AMIS_MAXK1, AMIS_MAXS, K1, S);
+    int ndev = bildk_device_count();
+    if (ndev == 0) return fail(BILDK_ECUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(BILDK_EINVAL, "device %d out of range", device);
+    CU(cudaSetDevice(device));
+    bildk_amis* h = new bildk_amis();
+    struct Guard { bildk_amis* h; ~Guard() { if (h) bildk_amis_destroy(h); } } guard{h};
+    h->device = device; h->K1 = K1; h->S = S;
+    h->transitions.assign(transitions, transitions + static_cast<size_t>(S) * S);
+    CU(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    CU(cudaMalloc(&h->head, (4 + 2 * static_cast<size_t>(K1) + static_cast<size_t>(S) * K1) * sizeof(double)));
+    guard.h = nullptr;
+    *out = h;
+    return BILDK_OK;
+}
+
+extern "C" int bildk_amis_size(bildk_amis_t h, int* n_samples, int* n_proposals) {
+    if (!h) return fail(BILDK_EINVAL, "NULL handle");
+    if (n_samples) *n_samples = h->n;
+    if (n_proposals) *n_proposals = h->n_par;
+    return BILDK_OK;
+}
+
+extern "C" int bildk_amis_step(bildk_amis_t h, int n_new, const double* ss, const int64_t* thetas, const double* logL,
+                               const double* A_cur, const double* logp_cur, double* head, double* per_sample) {
+    if (!h) return fail(BILDK_EINVAL, "NULL handle");
+    if (n_new < 1 || !ss || !thetas || !logL || !A_cur || !logp_cur || !head) return fail(BILDK_EINVAL, "bad argument");
+    const int K1 = h->K1, S = h->S;
+    const size_t nk = static_cast<size_t>(n_new) * K1, sk = static_cast<size_t>(S) * K1;
+    for (size_t i = 0; i < nk; ++i)
+        if (thetas[i] < 0 || thetas[i] >= S) return fail(BILDK_EINVAL, "state %lld out of range [0,%d)", static_cast<long long>(thetas[i]), S);
+    NvtxRange nvtx("bildk_amis_step");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = h->st;
+    const size_t n_old = h->n, n_tot = n_old + n_new, n_par = h->n_par + 1;
+    int rc;
+    if ((rc = grow_keep(&h->ss, &h->cap_ss, n_old * K1, n_tot * K1, st)) || (rc = grow_keep(&h->logs, &h->cap_logs, n_old * K1, n_tot * K1, st)) ||
+        (rc = grow_keep(&h->thetas, &h->cap_th, n_old * K1, n_tot * K1, st)) || (rc = grow_keep(&h->flags, &h->cap_fl, n_old, n_tot, st)) ||
+        (rc = grow_keep(&h->logL, &h->cap_logL, n_old, n_tot, st)) || (rc = grow_keep(&h->per, &h->cap_per, 3 * n_old, 3 * n_tot, st)) ||
+        (rc = grow_keep(&h->A, &h->cap_A, h->n_par * static_cast<size_t>(K1), n_par * K1, st)) ||
+        (rc = grow_keep(&h->lognorm, &h->cap_ln, static_cast<size_t>(h->n_par), n_par, st)) ||
+        (rc = grow_keep(&h->norm0, &h->cap_n0, static_cast<size_t>(h->n_par), n_par, st)) ||
+        (rc = grow_keep(&h->logp, &h->cap_lp, h->n_par * sk, n_par * sk, st)) || (rc = grow_keep(&h->reach, &h->cap_rc, h->n_par * sk, n_par * sk, st)))
+        return rc;
+    // ---- one packed upload: ss | logL | A | lognorm | norm0 | logp | reach | thetas (bytes)
+    const size_t o_ss = 0, o_ll = o_ss + nk, o_A = o_ll + n_new, o_ln = o_A + K1, o_n0 = o_ln + 1, o_lp = o_n0 + 1, o_rc = o_lp + sk,
+                 o_th = o_rc + sk, in_doubles = o_th + (nk + 7) / 8;
+    const size_t n_head = 4 + 2 * static_cast<size_t>(K1) + sk;
+    const size_t out_doubles = n_head + (per_sample ? 3 * n_tot : 0);
+    const size_t need_pinned = std::max(in_doubles, out_doubles);
+    if (need_pinned > h->cap_pinned) {
+        if (h->pinned) cudaFreeHost(h->pinned);
+        h->pinned = nullptr; h->cap_pinned = 0;
+        const size_t want = need_pinned * 2;
+        cudaError_t e = cudaMallocHost(&h->pinned, want * sizeof(double));
+        if (e != cudaSuccess) return fail(BILDK_ENOMEM, "cudaMallocHost(%zu bytes): %s", want * sizeof(double), cudaGetErrorString(e));
+        h->cap_pinned = want;
+    }
+    if (in_doubles > h->cap_stage) {
+        if (h->stage) cudaFree(h->stage);
+        h->stage = nullptr; h->cap_stage = 0;
+        cudaError_t e = cudaMalloc(&h->stage, in_doubles * 2 * sizeof(double));
+        if (e != cudaSuccess) return fail(BILDK_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(e));
+        h->cap_stage = in_doubles * 2;
+    }
+    double* pin = h->pinned;
+    std::memcpy(pin + o_ss, ss, nk * sizeof(double));
+    std::memcpy(pin + o_ll, logL, n_new * sizeof(double));
+    std::memcpy(pin + o_A, A_cur, K1 * sizeof(double));
+    {   // normalisers of the joining proposal (amis.py:83-108, 258-281), once per proposal
+        const double inf = std::numeric_limits<double>::infinity();
+        auto lse = [&](const double* v, int stride, const uint8_t* allowed) {
+            double top = -inf;
+            for (int m = 0; m < S; ++m)
+                if (!allowed || allowed[m]) top = std::max(top, v[m * stride]);
+            if (!std::isfinite(top)) top = 0.0;
+            double acc = 0.0;
+            for (int m = 0; m < S; ++m)
+                if (!allowed || allowed[m]) acc += std::exp(v[m * stride] - top);
+            return std::log(acc) + top;
+        };
+        double asum = 0.0, lg = 0.0;
+        for (int c = 0; c < K1; ++c) { asum += A_cur[c]; lg += std::lgamma(A_cur[c]); }
+        pin[o_ln] = std::lgamma(asum) - lg;
+        pin[o_n0] = lse(logp_cur, K1, nullptr);
+        std::memcpy(pin + o_lp, logp_cur, sk * sizeof(double));
+        for (int m = 0; m < S; ++m) {
+            pin[o_rc + static_cast<size_t>(m) * K1] = 0.0;
+            for (int c = 1; c < K1; ++c) pin[o_rc + static_cast<size_t>(m) * K1 + c] = lse(logp_cur + c, K1, h->transitions.data() + static_cast<size_t>(m) * S);
+        }
+    }
+    uint8_t* thb = reinterpret_cast<uint8_t*>(pin + o_th);
+    for (size_t i = 0; i < nk; ++i) thb[i] = static_cast<uint8_t>(thetas[i]);
+    CU(cudaMemcpyAsync(h->stage, pin, in_doubles * sizeof(double), cudaMemcpyHostToDevice, st));
+    // proposal parameters: device-to-device scatter from the staging block (five small copies)
+    CU(cudaMemcpyAsync(h->A + h->n_par * static_cast<size_t>(K1), h->stage + o_A, K1 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(h->lognorm + h->n_par, h->stage + o_ln, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(h->norm0 + h->n_par, h->stage + o_n0, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(h->logp + h->n_par * sk, h->stage + o_lp, sk * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(h->reach + h->n_par * sk, h->stage + o_rc, sk * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    k_amis_append<<<(n_new + 127) / 128, 128, 0, st>>>(n_new, K1, h->stage + o_ss, reinterpret_cast<const uint8_t*>(h->stage + o_th), h->stage + o_ll,
+                                                     h->ss + n_old * K1, h->logs + n_old * K1, h->thetas + n_old * K1, h->flags + n_old, h->logL + n_old);
+    CU(cudaGetLastError());
+    g_launches++;
+    AmisParams ap{};
+    ap.n_old = static_cast<int>(n_old); ap.n_new = n_new; ap.K1 = K1; ap.S = S; ap.n_par = static_cast<int>(n_par);
+    ap.logs = h->logs; ap.thetas = h->thetas; ap.flags = h->flags; ap.ss = h->ss; ap.logL = h->logL; ap.per = h->per;
+    ap.A = h->A; ap.lognorm = h->lognorm; ap.logp = h->logp; ap.reach = h->reach; ap.norm0 = h->norm0;
+    ap.log_nsteps = std::log(static_cast<double>(n_par));
+    ap.out = h->head;
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(AMIS_CLUSTER);
+        cfg.blockDim = dim3(AMIS_THREADS);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = AMIS_CLUSTER;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (K1 <= 16) CU(cudaLaunchKernelEx(&cfg, k_amis_step<16>, ap));
+        else CU(cudaLaunchKernelEx(&cfg, k_amis_step<32>, ap));
+        g_launches++;
+    }
+    CU(cudaMemcpyAsync(pin, h->head, n_head * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (per_sample) CU(cudaMemcpyAsync(pin + n_head, h->per, 3 * n_tot * sizeof(double), cudaMemcpyDeviceToHost, st));
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(BILDK_ECUDA, "AMIS step failed: %s", cudaGetErrorString(e));
+    std::memcpy(head, pin, n_head * sizeof(double));
+    if (per_sample) std::memcpy(per_sample, pin + n_head, 3 * n_tot * sizeof(double));
+    h->n = static_cast<int>(n_tot);
+    h->n_par = static_cast<int>(n_par);
     return BILDK_OK;
 }

@@ -35,6 +35,8 @@ struct RParams {
     int WPC;               // warps (= filters) per CTA
     int fstride;           // doubles of shared memory per filter
     int r;                 // N - 8 (GT - 1), 1..4
+    double ww00, ww11, ww01;   // w0 w0, w1 w1, 2 w0 w1 (host-computed with the same IEEE operations): constant-bank operands of
+                               // the S = s2 + w^T C' w FMAs instead of six live registers (k_mmar<3,4> spilled one double per frame)
     unsigned char lastrow[DMAX][8];   // per sub-filter: buffer row read by B-fragment lane g for the last tile column
     unsigned char mrow[DMAX][4];      // per sub-filter: buffer row of mean column q (M^T)
 };
@@ -115,7 +117,6 @@ __global__ void __launch_bounds__(128, NB) k_mmar(const __grid_constant__ RParam
     // measured 2-3 % SLOWER than reading it back from the published columns: SHFL shares the LSU pipe.)
     const int cj1 = rr - 1;
     const bool e1 = cj1 & 1;
-    const double ww00 = w0 * w0, ww11 = w1 * w1, ww01 = 2.0 * w0 * w1;
 
     // lane-constant fragment offsets (doubles).  Rows 8 t + g flip column bit 2 when (g >> 1) & 1.
     const int fx = 4 * ((g >> 1) & 1);
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(128, NB) k_mmar(const __grid_constant__ RParam
 
         if (is_valid) {
             // S = s2 + w^T C' w from the 2x2 block of C' at (0, N-1) (pyx:55-63); three parallel terms, then 1/S
-            const double Sinv = rcp3(fma(ww11, colb[R + 8 * (GT - 1) + cj1], fma(ww00, colb[0], s2)) + ww01 * colb[R]);
+            const double Sinv = rcp3(fma(rp.ww11, colb[R + 8 * (GT - 1) + cj1], fma(rp.ww00, colb[0], s2)) + rp.ww01 * colb[R]);
             double kr[GT];
 #pragma unroll
             for (int ti = 0; ti < GT; ++ti)

@@ -15,7 +15,7 @@ import numpy as np
 from . import _lib
 from ._lib import c_double_p, c_int32_p, c_uint8_p, c_uint32_p, as_f64, ptr
 
-__all__ = ["RouseEngine", "TrajectoryHandle", "st_to_runs", "states_to_runs"]
+__all__ = ["RouseEngine", "TrajectoryHandle", "AmisEnsemble", "st_to_runs", "states_to_runs"]
 
 
 def st_to_runs(ss, thetas, T):
@@ -95,6 +95,53 @@ class TrajectoryHandle:
 
     def describe_plan(self, P):
         return _lib.load().bildk_describe_plan(self._h, int(P)).decode()
+
+
+class AmisEnsemble:
+    """
+    Device-resident ensemble of one `FixedkSampler` (C ABI ``bildk_amis_*``): samples, likelihoods, mixture
+    denominators, weights and all past proposals live in HBM; `step` adds a batch, lets the proposal it was drawn
+    from join the mixture, and returns the statistics of amis.py:843-845, 878-900, 137-151, 300-303 in one launch.
+    """
+
+    MAX_K1, MAX_STATES = 32, 4
+
+    def __init__(self, K1, transitions, device=0):
+        transitions = np.ascontiguousarray(transitions, dtype=np.uint8)
+        self.K1, self.S = int(K1), transitions.shape[0]
+        lib = _lib.load()
+        h = ctypes.c_void_p()
+        _lib.check(lib.bildk_amis_create(self.K1, self.S, ptr(transitions, c_uint8_p), int(device), ctypes.byref(h)))
+        self._h = h
+        self._fin = weakref.finalize(self, lib.bildk_amis_destroy, h)
+        self.n = 0
+        self._per = np.empty((1024, 3))
+
+    @classmethod
+    def supports(cls, K1, n_states):
+        return K1 <= cls.MAX_K1 and n_states <= cls.MAX_STATES
+
+    def step(self, ss, thetas, logLs, a, logp):
+        """-> ((max, sum w, sum (w - mean)^2, nansum w (logL - log q)), mean (K1,), var (K1,), log marginals (S, K1),
+        per-sample array (n, 3): log_w | logdelta | log q_cur of the whole ensemble - a view that later steps overwrite)."""
+        ss = np.ascontiguousarray(ss, dtype=np.float64)
+        thetas = np.ascontiguousarray(thetas, dtype=np.int64)
+        logLs = np.ascontiguousarray(logLs, dtype=np.float64)
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        logp = np.ascontiguousarray(logp, dtype=np.float64)
+        n_new = len(logLs)
+        if ss.shape != (n_new, self.K1) or thetas.shape != ss.shape or a.shape != (self.K1,) or logp.shape != (self.S, self.K1):
+            raise ValueError("inconsistent AMIS batch")
+        n_tot = self.n + n_new
+        if n_tot > len(self._per):
+            self._per = np.empty((max(n_tot, 2 * len(self._per)), 3))   # contents are rewritten in full by every step
+        head = np.empty(4 + 2 * self.K1 + self.S * self.K1)
+        _lib.check(_lib.load().bildk_amis_step(self._h, n_new, ptr(ss, c_double_p), thetas.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                               ptr(logLs, c_double_p), ptr(a, c_double_p), ptr(logp, c_double_p), ptr(head, c_double_p),
+                                               ptr(self._per, c_double_p)))
+        self.n = n_tot
+        K1 = self.K1
+        return tuple(head[:4]), head[4:4 + K1], head[4 + K1:4 + 2 * K1], head[4 + 2 * K1:].reshape(self.S, K1), self._per[:n_tot]
 
 
 class RouseEngine:

@@ -248,6 +248,14 @@ class MultiStateRouse(MultiStateModel):
                                                   _lib.ptr(log_w, dp), _lib.ptr(st, dp), self.engine.device))
         return log_w, tuple(st)
 
+    def amis_ensemble(self, K1, transitions):
+        """Device-resident ensemble for one `FixedkSampler` (bild_b200.engine.AmisEnsemble), or None when the shape is
+        outside what the device kernel handles (the sampler then keeps its bookkeeping on the host)."""
+        from .engine import AmisEnsemble
+        if not AmisEnsemble.supports(K1, len(transitions)):
+            return None
+        return AmisEnsemble(K1, transitions, device=self.engine.device)
+
     def marginal_posterior(self, ss, thetas, T, log_weights):
         """
         ``(n_states, T)`` normalised log posterior probability of each state at each frame from the weighted

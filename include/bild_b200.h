@@ -149,6 +149,26 @@ int bildk_marginal_posterior(int n, int K1, int T, int S, const int32_t *run_sta
 int bildk_amis_log_proposal(int n_par, int n, int K1, int S, const double *A, const double *logp,
                             const uint8_t *transitions, const double *ss, const int64_t *thetas, double *out);
 
+/*
+ * Device-resident AMIS ensemble: the whole per-iteration bookkeeping of FixedkSampler.step (amis.py:824-845 mixture
+ * denominators and weights, :878-900 evidence statistics, :137-151 Dirichlet moments, :300-303 CFC marginals) in ONE call.
+ * The ensemble (interval lengths, state traces, likelihoods, mixture denominators, weights) and all past proposals stay
+ * on the device; per step only the new batch goes up and the statistics of the refit come back:
+ *   ss (n_new, K1), thetas (n_new, K1), logL (n_new)   the batch just evaluated (host arrays)
+ *   A_cur (K1), logp_cur (S, K1)                        the proposal it was drawn from (it joins the mixture now)
+ *   head[0..3]              max log_w | sum w | sum (w - mean w)^2 | nansum w (logL - log q_cur)    (as bildk_amis_weights)
+ *   head[4 .. 4+K1)         weighted mean of the interval lengths       head[4+K1 .. 4+2K1)  their weighted variance
+ *   head[4+2K1 + s*K1 + c]  log sum of the weights of the samples with theta[c] == s  (not normalised over s)
+ *   per_sample (n_total, 3) log_w | logdelta | log q_cur of EVERY sample so far, or NULL
+ * Limits: K1 <= 32, S <= 4 (BILDK_EUNSUP otherwise: the caller keeps the bookkeeping on the host).
+ */
+typedef struct bildk_amis *bildk_amis_t;
+int bildk_amis_create(int K1, int S, const uint8_t *transitions, int device, bildk_amis_t *out);
+int bildk_amis_destroy(bildk_amis_t h);
+int bildk_amis_size(bildk_amis_t h, int *n_samples, int *n_proposals);
+int bildk_amis_step(bildk_amis_t h, int n_new, const double *ss, const int64_t *thetas, const double *logL,
+                    const double *A_cur, const double *logp_cur, double *head, double *per_sample);
+
 /* Device-resident variant of bildk_amis_weights: device pointers (d_log_w may be NULL, d_stats has
  * room for 4 doubles), asynchronous on `stream`. */
 int bildk_amis_weights_device(int n, const double *d_logL, const double *d_logdelta,

@@ -166,3 +166,47 @@ def test_sample_many_on_gpu_equals_one_by_one():
         solo = bild.sample(tr, model, **kw)
         assert np.array_equal(solo.log["k"], res[i].log["k"])
         assert np.array_equal(solo.evidence, res[i].evidence)       # bitwise: same kernels, same random numbers
+
+
+def test_device_ensemble_matches_host_bookkeeping():
+    """`bildk_amis_step` (device-resident ensemble: mixture denominators, weights, evidence sums, Dirichlet moments, CFC
+    marginals in one launch) against the host numpy bookkeeping of the same sampler, step by step, incl. the +inf
+    conventions for rejected samples (amis.py:98-108) and three states."""
+    from bild_b200 import amis
+    model = bild.models.MultiStateRouse(12, 1, 5, d=2, looppositions=(None, (0, -1), (2, 8)), localization_error=0.3)
+    np.random.seed(8)
+    truth = bild.Loopingprofile([0] * 15 + [1] * 15 + [2] * 15 + [0] * 15)
+    traj = model.trajectory_from_loopingprofile(truth, missing_frames=0.1)
+    for k in (2, 5, 17):                                      # 17: K1 = 18 > 16 -> the 32-column kernel variant
+        dev = amis.FixedkSampler(traj, model, k=k, N=64)
+        host = amis.FixedkSampler(traj, model, k=k, N=64)
+        host._ens = None                                      # force the numpy bookkeeping
+        assert dev._device_ensemble() is not None
+        for step in range(6):
+            np.random.seed(100 * k + step)
+            state = np.random.get_state()
+            batches = []
+            for smp in (dev, host):
+                np.random.set_state(state)
+                cur = smp.parameters[-1]
+                ss, th = smp.dirichlet.sample(cur[0], smp.N), smp.cfc.sample(cur[1], smp.N)
+                if step == 2:                                 # a rejected sample: zero-length interval, and one off the simplex
+                    ss[0, 0] += ss[0, 1]; ss[0, 1] = 0.0
+                    ss[1] *= 1.001
+                batches.append((ss, th))
+                smp.dirichlet.sample = lambda a, N, ss=ss: ss
+                smp.cfc.sample = lambda logp, N, th=th: th
+                assert smp.step() is True
+                del smp.dirichlet.sample, smp.cfc.sample
+            assert np.array_equal(batches[0][0], batches[1][0]) and np.array_equal(batches[0][1], batches[1][1])
+            np.testing.assert_allclose(dev.evidences[-1], host.evidences[-1], rtol=1e-10, atol=1e-10)
+            np.testing.assert_allclose(dev.parameters[-1][0], host.parameters[-1][0], rtol=1e-9)
+            np.testing.assert_allclose(np.exp(dev.parameters[-1][1]), np.exp(host.parameters[-1][1]), atol=1e-12)
+        for key in ("log_weights", "logδs", "cur_log_proposal"):
+            a = np.concatenate([b[key] for b in dev.samples])
+            b = np.concatenate([b[key] for b in host.samples])
+            assert np.array_equal(np.isfinite(a), np.isfinite(b)) and np.array_equal(a[~np.isfinite(a)], b[~np.isfinite(b)])
+            ok = np.isfinite(a)
+            np.testing.assert_allclose(a[ok], b[ok], rtol=1e-11, atol=1e-11)
+        assert np.isposinf(np.concatenate([b["logδs"] for b in dev.samples])).sum() >= 2
+        np.testing.assert_allclose(np.exp(dev.log_marginal_posterior()), np.exp(host.log_marginal_posterior()), atol=1e-10)
