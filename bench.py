@@ -532,6 +532,24 @@ def run_workload(ctx, name, wl, steps, warmup, cpu=None, strong=False, with_cloc
         launches = lib.bildk_launch_count() - launches0
         # kernel-only duration of the filter kernel for the roofline (same stream, CUDA events, L2 flushed)
         kms = ctx.timed(kernel_only, max(3, min(steps, 10)))
+        # where a step's time goes (CUDA events between the phases, a few extra untimed-for-`value` steps)
+        phases = []
+        for _ in range(3):
+            ctx.flush.zero_()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record(stream)
+            kernel_only()
+            ev[1].record(stream)
+            if world > 1:
+                dist.all_gather_into_tensor(d_all, d_out)
+            ev[2].record(stream)
+            _lib.check(lib.bildk_amis_weights_device(n_w, ctypes.c_void_p((d_all if world > 1 else d_out).data_ptr()), ctypes.c_void_p(d_logdelta.data_ptr()),
+                                                     ctypes.c_void_p(d_curlp.data_ptr()), float(np.log(7.0)), ctypes.c_void_p(d_logw.data_ptr()),
+                                                     ctypes.c_void_p(d_stats.data_ptr()), ctypes.c_void_p(stream.cuda_stream)))
+            ev[3].record(stream)
+            torch.cuda.synchronize()
+            phases.append([ev[i].elapsed_time(ev[i + 1]) for i in range(3)])
+        phases = np.median(np.array(phases), axis=0)
         clocks = clk.summary(wall0, time.perf_counter()) if clk else None
     finally:
         if clk:
@@ -584,7 +602,9 @@ def run_workload(ctx, name, wl, steps, warmup, cpu=None, strong=False, with_cloc
                        + " + MultiStateRouse.amis_weights(...): numpy in / numpy out, pageable host buffers"},
         "gpu_launches": int(launches),
         "wall_s_timed_region": wall,
-        "detail": {"valid_frames": V, "l2": "flushed between timed steps (256 MiB memset, untimed)", "plan": plan},
+        "detail": {"valid_frames": V, "l2": "flushed between timed steps (256 MiB memset, untimed)", "plan": plan,
+                   "phase_ms_rank0": {"filter_kernel": float(phases[0]), "nccl_all_gather": float(phases[1]), "amis_weights_kernel": float(phases[2]),
+                                      "how": "CUDA events between the phases of a step on the launching stream, median of 3 extra steps"}},
         # "tensor": the bounding unit is the FP64 tensor pipe (DMMA m8n8k4) - the peak below is ITS measured rate, not bf16
         "roofline": {"bound": "tensor", "pipe": "fp64 DMMA m8n8k4 (no tcgen05 kind for f64)", "achieved": ach_tf, "peak": ctx.peak_tf, "unit": "TFLOP/s",
                      "frac": ach_tf / ctx.peak_tf, "traffic": _ncu_traffic(name), "kernel": plan.split(" FPC")[0].split(" WPC")[0], "kernel_ms": kavg_ms,

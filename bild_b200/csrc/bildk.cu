@@ -122,19 +122,29 @@ struct bildk_model {
     bool mmar_ok = false;
     int r_last = 0, LDr = 0, fstride_r = 0;
     double* dBr = nullptr;
-    // per-model scratch for the host-pointer entry points
-    DevBuf<int32_t> starts;
-    DevBuf<uint8_t> states;
-    DevBuf<double> out, part, work;
-    DevBuf<int> meta;          // traj_first / cta maps / prof_traj
-    DevBuf<int> meta2;         // prof_traj of the L2-workspace tensor-core kernel
-    DevBuf<const double*> xptrs;
-    DevBuf<const uint8_t*> vptrs;
+    // per-model scratch of the launcher: partial logL of the d* sub-filters; covariance workspace of the N > 112 kernels
+    DevBuf<double> part, work;
     int max_smem_optin = 0;
     int n_sm = 0;
-    // the scratch buffers above are shared by every call on this model: host-pointer entry points hold this lock from
-    // staging to copy-back (ctypes releases the GIL, so two Python threads may call in concurrently)
+    // the scratch buffers above are shared by every call on this model: host-pointer entry points hold this lock while
+    // they stage and enqueue (ctypes releases the GIL, so two Python threads may call in concurrently)
     std::mutex mu;
+    // host-pointer batches go through two SLOTS (double buffering): a pinned host block and its device mirror that hold one
+    // batch's inputs, launch metadata and outputs, on a private stream.  Nothing in the submit path synchronises the
+    // stream (all copies are pinned <-> device), so the host code of one group of trajectories overlaps the kernel of
+    // another (bild_b200/dataset.py); bildk_logl_runs_multi = submit + wait.
+    struct Slot {
+        bildk_model* owner = nullptr;
+        char* pin = nullptr;
+        char* dev = nullptr;
+        size_t cap = 0;
+        cudaEvent_t done = nullptr;
+        double* user_out = nullptr;
+        size_t off_out = 0;
+        int P = 0;
+        bool busy = false;
+    } slots[2];
+    cudaStream_t st = nullptr;
 };
 
 struct bildk_traj {
@@ -226,8 +236,13 @@ extern "C" int bildk_model_destroy(bildk_model_t m) {
     for (double* p : {m->dB, m->dSig, m->dC0, m->dBpad, m->dSigpad, m->dC0pad, m->dG, m->dM0, m->dw, m->dBm, m->dSigm, m->dC0m, m->dBr})
         if (p) cudaFree(p);
     if (m->d_lane_ab) cudaFree(m->d_lane_ab);
-    m->starts.release(); m->states.release(); m->out.release(); m->part.release(); m->work.release();
-    m->meta.release(); m->meta2.release(); m->xptrs.release(); m->vptrs.release();
+    m->part.release(); m->work.release();
+    for (auto& sl : m->slots) {
+        if (sl.pin) cudaFreeHost(sl.pin);
+        if (sl.dev) cudaFree(sl.dev);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
+    if (m->st) cudaStreamDestroy(m->st);
     delete m;
     return BILDK_OK;
 }
@@ -258,6 +273,11 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
     m->N = N; m->D = d; m->S = S; m->device = device;
     CU(cudaDeviceGetAttribute(&m->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CU(cudaDeviceGetAttribute(&m->n_sm, cudaDevAttrMultiProcessorCount, device));
+    CU(cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking));
+    for (auto& sl : m->slots) {
+        sl.owner = m;
+        CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    }
     m->hasG = false;
     for (size_t i = 0; i < S * ND; ++i) if (G[i] != 0.0) m->hasG = true;
     m->nnz = 0;
@@ -701,8 +721,24 @@ static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
             const size_t matb = static_cast<size_t>(m->NPm) * m->LDBm * 8;
             const size_t fbytes = (static_cast<size_t>(m->NPm) * m->LDCm + static_cast<size_t>(2) * m->NPm + 2) * 8;
             const size_t cap = static_cast<size_t>(m->max_smem_optin);
-            int f = env_int("BILDK_FPC2", 6);
-            while (f > 1 && 16 + matb * m->S + fbytes * f > cap) --f;
+            // filters per CTA (one CTA per SM: the propagators take 2 x 26 KB of it).  Measured time of ONE full wave at
+            // N = 50 (T = 200, 148 f filters, profiles/r02_mma2_fpc_table.txt), relative: a single warp pair is latency bound,
+            // odd counts leave one scheduler pair with an unmatched role.  Pick the count that minimises waves x time per
+            // wave for this batch: P = 16384 -> 6 (19 waves), P = 1024 -> 4 (2 waves of 148 + 108 CTAs instead of 148 + 23).
+            static const double wave_time[7] = {0.0, 1.70, 1.715, 2.33, 2.43, 3.33, 3.19};
+            int fmax = 6;
+            while (fmax > 1 && 16 + matb * m->S + fbytes * fmax > cap) --fmax;
+            int f = env_int("BILDK_FPC2", 0);
+            if (f <= 0) {
+                double best = 1e300;
+                f = fmax;
+                for (int c = fmax; c >= 1; --c) {
+                    const long long n_cta = (static_cast<long long>(std::max(1, P_per_traj_hint)) + c - 1) / c;
+                    const double cost = static_cast<double>((n_cta + m->n_sm - 1) / m->n_sm) * wave_time[c];
+                    if (cost < best - 1e-9) { best = cost; f = c; }
+                }
+            }
+            f = std::min(f, fmax);
             if (16 + matb * m->S + fbytes * f <= cap) {
                 pl.mma2 = true;
                 pl.tile = false;
@@ -980,11 +1016,20 @@ extern "C" int bildk_debug_tables(int kernel, int GT, int r, int ncols, unsigned
     return fail(BILDK_EINVAL, "unknown kernel %d", kernel);
 }
 
+// Launch maps of a multi-trajectory batch (CTA -> trajectory / first filter; filter -> trajectory): written into pinned host
+// memory and copied asynchronously, so that enqueuing a batch never waits for the stream.
+struct MapArena {
+    int* h_cta = nullptr;   // pinned, capacity 2 (P + n_traj)
+    int* d_cta = nullptr;
+    int* h_pt = nullptr;    // pinned, capacity P
+    int* d_pt = nullptr;
+};
+
 // Core launcher on device-resident profile arrays.  Trajectory metadata arrays are device pointers.
 static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const double* const* d_x,
                          const uint8_t* const* d_valid, const int* d_T, const int* d_first,
                          const std::vector<int>& h_first, int P, int K1, const int32_t* d_starts,
-                         const uint8_t* d_states, double* d_out, cudaStream_t st) {
+                         const uint8_t* d_states, double* d_out, cudaStream_t st, const MapArena* arena = nullptr) {
     if (P == 0) return BILDK_OK;
     const int dstar = t0->dstar;
     int max_per_traj = 0;
@@ -1017,17 +1062,14 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
             n_cta = (P + pl.FPC - 1) / pl.FPC;
             kp.cta_traj = nullptr; kp.cta_first = nullptr;
         } else {
-            std::vector<int> map;   // [cta_traj..., cta_first...]
-            std::vector<int> ct, cf;
+            if (!arena) return fail(BILDK_EINVAL, "internal: multi-trajectory launch without a map arena");
             for (int i = 0; i < n_traj; ++i)
-                for (int f = h_first[i]; f < h_first[i + 1]; f += pl.FPC) { ct.push_back(i); cf.push_back(f); }
-            n_cta = static_cast<int>(ct.size());
-            int rc = m->meta.reserve(static_cast<size_t>(2) * n_cta + 64);
-            if (rc) return rc;
-            CU(cudaMemcpyAsync(m->meta.p, ct.data(), n_cta * sizeof(int), cudaMemcpyHostToDevice, st));
-            CU(cudaMemcpyAsync(m->meta.p + n_cta, cf.data(), n_cta * sizeof(int), cudaMemcpyHostToDevice, st));
-            CU(cudaStreamSynchronize(st));   // ct/cf are stack vectors
-            kp.cta_traj = m->meta.p; kp.cta_first = m->meta.p + n_cta;
+                for (int f = h_first[i]; f < h_first[i + 1]; f += pl.FPC) ++n_cta;
+            int k = 0;
+            for (int i = 0; i < n_traj; ++i)
+                for (int f = h_first[i]; f < h_first[i + 1]; f += pl.FPC, ++k) { arena->h_cta[k] = i; arena->h_cta[n_cta + k] = f; }
+            CU(cudaMemcpyAsync(arena->d_cta, arena->h_cta, static_cast<size_t>(2) * n_cta * sizeof(int), cudaMemcpyHostToDevice, st));
+            kp.cta_traj = arena->d_cta; kp.cta_first = arena->d_cta + n_cta;
         }
         dim3 grid(n_cta, dstar);
         if (pl.mmag) {
@@ -1040,12 +1082,9 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
             for (int i = 0; i < 40; ++i) gp.colmap[i] = pl.colmap[i];
             gp.prof_traj = nullptr;
             if (n_traj > 1) {
-                std::vector<int> pt(P);
-                for (int i = 0; i < n_traj; ++i) for (int f = h_first[i]; f < h_first[i + 1]; ++f) pt[f] = i;
-                int rc = m->meta2.reserve(P);
-                if (rc) return rc;
-                CU(cudaMemcpy(m->meta2.p, pt.data(), P * sizeof(int), cudaMemcpyHostToDevice));
-                gp.prof_traj = m->meta2.p;
+                for (int i = 0; i < n_traj; ++i) for (int f = h_first[i]; f < h_first[i + 1]; ++f) arena->h_pt[f] = i;
+                CU(cudaMemcpyAsync(arena->d_pt, arena->h_pt, P * sizeof(int), cudaMemcpyHostToDevice, st));
+                gp.prof_traj = arena->d_pt;
             }
             const int nc = std::min(P, 2 * m->n_sm);
             const size_t wsz = static_cast<size_t>(2) * m->NPm * m->LDCm;
@@ -1125,12 +1164,10 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
         gp.P = P; gp.K1 = K1; gp.run_starts = d_starts; gp.run_states = d_states; gp.out = d_part;
         gp.prof_traj = nullptr;
         if (n_traj > 1) {
-            std::vector<int> pt(P);
-            for (int i = 0; i < n_traj; ++i) for (int f = h_first[i]; f < h_first[i + 1]; ++f) pt[f] = i;
-            int rc = m->meta.reserve(P + 64);
-            if (rc) return rc;
-            CU(cudaMemcpy(m->meta.p, pt.data(), P * sizeof(int), cudaMemcpyHostToDevice));
-            gp.prof_traj = m->meta.p;
+            if (!arena) return fail(BILDK_EINVAL, "internal: multi-trajectory launch without a map arena");
+            for (int i = 0; i < n_traj; ++i) for (int f = h_first[i]; f < h_first[i + 1]; ++f) arena->h_pt[f] = i;
+            CU(cudaMemcpyAsync(arena->d_pt, arena->h_pt, P * sizeof(int), cudaMemcpyHostToDevice, st));
+            gp.prof_traj = arena->d_pt;
         }
         const int n_cta = std::min(P, 4 * m->n_sm);
         const size_t wsz = 2 * static_cast<size_t>(m->N) * m->N + 3 * static_cast<size_t>(m->N) * m->D + 2 * m->N;
@@ -1180,8 +1217,26 @@ extern "C" int bildk_logl_runs_device(bildk_traj_t t, int P, int K1, const int32
     return launch_device(m, t, 1, t->d_xptr, t->d_vptr, t->d_T, t->d_first, hf, P, K1, d_starts, d_states, d_out, st);
 }
 
-extern "C" int bildk_logl_runs_multi(int n_traj, const bildk_traj_t* trajs, const int32_t* offsets, int K1,
-                                     const int32_t* starts, const uint8_t* states, double* out) {
+static size_t align16(size_t x) { return (x + 15) / 16 * 16; }
+
+extern "C" int bildk_logl_wait(void* ticket) {
+    if (!ticket) return BILDK_OK;                      // an empty batch has no ticket
+    bildk_model::Slot* sl = static_cast<bildk_model::Slot*>(ticket);
+    if (!sl->busy) return fail(BILDK_EINVAL, "ticket is not in flight");
+    NvtxRange nvtx("bildk_logl_wait");
+    cudaError_t e = cudaEventSynchronize(sl->done);
+    int rc = BILDK_OK;
+    if (e != cudaSuccess) rc = fail(BILDK_ECUDA, "kernel or copy-back failed: %s", cudaGetErrorString(e));
+    else std::memcpy(sl->user_out, sl->pin + sl->off_out, static_cast<size_t>(sl->P) * sizeof(double));
+    std::lock_guard<std::mutex> lock(sl->owner->mu);
+    sl->busy = false;
+    return rc;
+}
+
+extern "C" int bildk_logl_runs_multi_submit(int n_traj, const bildk_traj_t* trajs, const int32_t* offsets, int K1,
+                                            const int32_t* starts, const uint8_t* states, double* out, void** ticket) {
+    if (!ticket) return fail(BILDK_EINVAL, "ticket is NULL");
+    *ticket = nullptr;
     if (n_traj < 1 || !trajs || !offsets) return fail(BILDK_EINVAL, "need at least one trajectory");
     if (K1 < 1) return fail(BILDK_EINVAL, "K1 must be >= 1");
     bildk_model* m = trajs[0] ? trajs[0]->m : nullptr;
@@ -1203,43 +1258,61 @@ extern "C" int bildk_logl_runs_multi(int n_traj, const bildk_traj_t* trajs, cons
         int rc = validate_runs(m, t->T, hf[i + 1] - hf[i], K1, starts + static_cast<size_t>(hf[i]) * K1, states + static_cast<size_t>(hf[i]) * K1, hf[i]);
         if (rc) return rc;
     }
-    NvtxRange nvtx("bildk_logl_runs_multi");
-    std::lock_guard<std::mutex> lock(m->mu);   // staging buffers, launch and copy-back of this model are one critical section
+    NvtxRange nvtx("bildk_logl_runs_multi_submit");
+    std::lock_guard<std::mutex> lock(m->mu);
     CU(cudaSetDevice(m->device));
-    int rc;
+    bildk_model::Slot* sl = nullptr;
+    for (auto& cand : m->slots)
+        if (!cand.busy) { sl = &cand; break; }
+    if (!sl) return fail(BILDK_EINVAL, "both batch slots of this model are in flight: call bildk_logl_wait first");
+    // ---- slot layout (bytes): run starts | run states | T per trajectory | first filter per trajectory | x pointers |
+    //      valid-mask pointers | CTA maps | filter -> trajectory | out
     const size_t nrun = static_cast<size_t>(P) * K1;
-    if ((rc = m->starts.reserve(nrun)) || (rc = m->states.reserve(nrun)) || (rc = m->out.reserve(P))) return rc;
-    CU(cudaMemcpy(m->starts.p, starts, nrun * sizeof(int32_t), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(m->states.p, states, nrun, cudaMemcpyHostToDevice));
-    const double* const* d_x;
-    const uint8_t* const* d_v;
-    const int* d_T;
-    const int* d_first;
-    DevBuf<int> tmeta;   // T + first, freed at the end (kept separate from m->meta used for the CTA map)
-    if (n_traj == 1) {
-        bildk_traj* t = trajs[0];
-        int first[2] = {0, P};
-        CU(cudaMemcpy(t->d_first, first, sizeof first, cudaMemcpyHostToDevice));
-        d_x = t->d_xptr; d_v = t->d_vptr; d_T = t->d_T; d_first = t->d_first;
-    } else {
-        std::vector<const double*> xs(n_traj);
-        std::vector<const uint8_t*> vs(n_traj);
-        std::vector<int> Ts(n_traj);
-        for (int i = 0; i < n_traj; ++i) { xs[i] = trajs[i]->dx; vs[i] = trajs[i]->dvalid; Ts[i] = trajs[i]->T; }
-        if ((rc = m->xptrs.reserve(n_traj)) || (rc = m->vptrs.reserve(n_traj)) || (rc = tmeta.reserve(2 * static_cast<size_t>(n_traj) + 1))) return rc;
-        CU(cudaMemcpy(m->xptrs.p, xs.data(), n_traj * sizeof(double*), cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(m->vptrs.p, vs.data(), n_traj * sizeof(uint8_t*), cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(tmeta.p, Ts.data(), n_traj * sizeof(int), cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(tmeta.p + n_traj, hf.data(), (n_traj + 1) * sizeof(int), cudaMemcpyHostToDevice));
-        d_x = m->xptrs.p; d_v = m->vptrs.p; d_T = tmeta.p; d_first = tmeta.p + n_traj;
+    const size_t o_st = 0, o_rs = align16(o_st + nrun * sizeof(int32_t)), o_T = align16(o_rs + nrun), o_first = align16(o_T + n_traj * sizeof(int)),
+                 o_x = align16(o_first + (n_traj + 1) * sizeof(int)), o_v = align16(o_x + n_traj * sizeof(void*)),
+                 o_cta = align16(o_v + n_traj * sizeof(void*)), o_pt = align16(o_cta + 2 * (static_cast<size_t>(P) + n_traj) * sizeof(int)),
+                 o_out = align16(o_pt + static_cast<size_t>(P) * sizeof(int)), total = align16(o_out + static_cast<size_t>(P) * sizeof(double));
+    if (total > sl->cap) {
+        if (sl->pin) cudaFreeHost(sl->pin);
+        if (sl->dev) cudaFree(sl->dev);
+        sl->pin = sl->dev = nullptr; sl->cap = 0;
+        const size_t want = total * 2;
+        cudaError_t e = cudaMallocHost(&sl->pin, want);
+        if (e == cudaSuccess) e = cudaMalloc(&sl->dev, want);
+        if (e != cudaSuccess) return fail(BILDK_ENOMEM, "slot allocation (%zu bytes): %s", want, cudaGetErrorString(e));
+        sl->cap = want;
     }
-    rc = launch_device(m, trajs[0], n_traj, d_x, d_v, d_T, d_first, hf, P, K1, m->starts.p, m->states.p, m->out.p, nullptr);
-    if (rc == BILDK_OK) {
-        cudaError_t e = cudaMemcpy(out, m->out.p, P * sizeof(double), cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) rc = fail(BILDK_ECUDA, "kernel or copy-back failed: %s", cudaGetErrorString(e));
-    }
-    tmeta.release();
-    return rc;
+    std::memcpy(sl->pin + o_st, starts, nrun * sizeof(int32_t));
+    std::memcpy(sl->pin + o_rs, states, nrun);
+    int* hT = reinterpret_cast<int*>(sl->pin + o_T);
+    int* hfirst = reinterpret_cast<int*>(sl->pin + o_first);
+    const double** hx = reinterpret_cast<const double**>(sl->pin + o_x);
+    const uint8_t** hv = reinterpret_cast<const uint8_t**>(sl->pin + o_v);
+    for (int i = 0; i < n_traj; ++i) { hT[i] = trajs[i]->T; hx[i] = trajs[i]->dx; hv[i] = trajs[i]->dvalid; }
+    for (int i = 0; i <= n_traj; ++i) hfirst[i] = hf[i];
+    cudaStream_t st = m->st;
+    CU(cudaMemcpyAsync(sl->dev, sl->pin, o_cta, cudaMemcpyHostToDevice, st));     // everything up to the CTA maps in one copy
+    MapArena arena;
+    arena.h_cta = reinterpret_cast<int*>(sl->pin + o_cta); arena.d_cta = reinterpret_cast<int*>(sl->dev + o_cta);
+    arena.h_pt = reinterpret_cast<int*>(sl->pin + o_pt); arena.d_pt = reinterpret_cast<int*>(sl->dev + o_pt);
+    int rc = launch_device(m, trajs[0], n_traj, reinterpret_cast<const double* const*>(sl->dev + o_x),
+                           reinterpret_cast<const uint8_t* const*>(sl->dev + o_v), reinterpret_cast<const int*>(sl->dev + o_T),
+                           reinterpret_cast<const int*>(sl->dev + o_first), hf, P, K1, reinterpret_cast<const int32_t*>(sl->dev + o_st),
+                           reinterpret_cast<const uint8_t*>(sl->dev + o_rs), reinterpret_cast<double*>(sl->dev + o_out), st, &arena);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(sl->pin + o_out, sl->dev + o_out, static_cast<size_t>(P) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(sl->done, st));
+    sl->user_out = out; sl->off_out = o_out; sl->P = P; sl->busy = true;
+    *ticket = sl;
+    return BILDK_OK;
+}
+
+extern "C" int bildk_logl_runs_multi(int n_traj, const bildk_traj_t* trajs, const int32_t* offsets, int K1,
+                                     const int32_t* starts, const uint8_t* states, double* out) {
+    void* ticket = nullptr;
+    int rc = bildk_logl_runs_multi_submit(n_traj, trajs, offsets, K1, starts, states, out, &ticket);
+    if (rc) return rc;
+    return bildk_logl_wait(ticket);
 }
 
 extern "C" int bildk_logl_runs(bildk_traj_t t, int P, int K1, const int32_t* starts, const uint8_t* states, double* out) {

@@ -144,6 +144,20 @@ class AmisEnsemble:
         return tuple(head[:4]), head[4:4 + K1], head[4 + K1:4 + 2 * K1], head[4 + 2 * K1:].reshape(self.S, K1), self._per[:n_tot]
 
 
+class PendingBatch:
+    """A batch in flight (C ABI ``bildk_logl_runs_multi_submit`` / ``bildk_logl_wait``)."""
+
+    def __init__(self, ticket, out, keep):
+        self._ticket, self._out, self._keep = ticket, out, keep      # `keep`: the handles must outlive the launch
+
+    def wait(self):
+        if self._ticket is not None:
+            ticket, self._ticket = self._ticket, None
+            if ticket.value:
+                _lib.check(_lib.load().bildk_logl_wait(ticket))
+        return self._out
+
+
 class RouseEngine:
     """
     GPU-resident multi-state Rouse model.
@@ -240,6 +254,23 @@ class RouseEngine:
             _lib.check(_lib.load().bildk_logl_runs_multi(len(trajs), arr, ptr(offsets, c_int32_p), starts.shape[1],
                                                          ptr(starts, c_int32_p), ptr(run_states, c_uint8_p), ptr(out, c_double_p)))
         return out
+
+    def logl_runs_multi_submit(self, trajs, offsets, starts, run_states):
+        """Asynchronous `logl_runs_multi`: stages and enqueues the batch (nothing waits for the GPU) and returns a
+        `PendingBatch`; ``.wait()`` returns the (P,) log-likelihoods.  At most two batches in flight per model."""
+        starts = np.ascontiguousarray(starts, dtype=np.int32)
+        run_states = np.ascontiguousarray(run_states, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+        if len(offsets) != len(trajs) + 1 or starts.shape != run_states.shape or starts.shape[0] != offsets[-1]:
+            raise ValueError("inconsistent multi-trajectory batch")
+        out = np.empty(starts.shape[0], dtype=np.float64)
+        ticket = ctypes.c_void_p()
+        if len(out):
+            arr = (ctypes.c_void_p * len(trajs))(*[t._h for t in trajs])
+            _lib.check(_lib.load().bildk_logl_runs_multi_submit(len(trajs), arr, ptr(offsets, c_int32_p), starts.shape[1],
+                                                                ptr(starts, c_int32_p), ptr(run_states, c_uint8_p), ptr(out, c_double_p),
+                                                                ctypes.byref(ticket)))
+        return PendingBatch(ticket, out, trajs)
 
     def logl_runs_device(self, traj, P, K1, d_starts, d_states, d_out, stream=0):
         """Device pointers (ints); asynchronous on ``stream``."""

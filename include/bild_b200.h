@@ -113,6 +113,17 @@ int bildk_logl_runs_multi(int n_traj, const bildk_traj_t *trajs, const int32_t *
                           const int32_t *run_starts, const uint8_t *run_states, double *out);
 
 /*
+ * Asynchronous form of bildk_logl_runs_multi: `submit` stages the batch in pinned memory, enqueues upload, kernel and
+ * download on the model's private stream WITHOUT waiting for anything, and returns a ticket; `out` must stay valid until
+ * bildk_logl_wait(ticket) has returned (it fills out[]).  A model has two batch slots, i.e. at most two tickets in flight
+ * (BILDK_EINVAL beyond that): the host code of one group of trajectories overlaps the kernel of the other
+ * (bild_b200/dataset.py).  An empty batch returns a NULL ticket, which bildk_logl_wait accepts.
+ */
+int bildk_logl_runs_multi_submit(int n_traj, const bildk_traj_t *trajs, const int32_t *offsets, int K1,
+                                 const int32_t *run_starts, const uint8_t *run_states, double *out, void **ticket);
+int bildk_logl_wait(void *ticket);
+
+/*
  * AMIS weight normalisation (amis.py:843-845, 878-900), deterministic fixed-order reduction:
  *   log_w[i] = logL[i] - logdelta[i] + log_nsteps
  *   stats[0] = max_i log_w        stats[1] = sum_i wo_i, wo_i = exp(log_w_i - max)

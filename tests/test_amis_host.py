@@ -252,7 +252,7 @@ class OracleBackedRouse(bild.models.MultiStateRouse):
     amis_weights = None    # host numpy weights, host marginal posterior: no device in the CPU suite
 
     def __getattribute__(self, name):
-        if name in ("amis_weights", "marginal_posterior", "amis_ensemble"):
+        if name in ("amis_weights", "marginal_posterior", "amis_ensemble", "logL_runs_multi_submit"):
             raise AttributeError(name)
         return super().__getattribute__(name)
 

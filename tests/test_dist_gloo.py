@@ -79,3 +79,49 @@ def test_sharded_sampler_gloo_world2(tmp_path):
         smp.step()
     assert np.array_equal(np.array(smp.evidences), r0["ev"])
     assert np.array_equal(smp.samples[-1]["logLs"], r0["logL"])
+
+
+def _claim_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bild_b200 as bild
+    from bild_b200.dataset import sample_many, store_claimer
+    from test_amis_host import OracleBackedRouse
+    model = OracleBackedRouse(8, 1, 5, d=2, localization_error=0.3)
+    np.random.seed(21)
+    trajs = [model.trajectory_from_loopingprofile(bild.Loopingprofile([0] * a + [1] * b + [0] * c))
+             for a, b, c in [(8, 9, 7), (12, 10, 0), (5, 5, 9), (20, 0, 0), (6, 8, 6), (9, 9, 4), (3, 14, 5)]]
+    kw = dict(init_runs=3, sampler_kw={"N": 15, "max_fcomplete": 40}, k_max=3, certainty_in_k=0.9)
+    res, stats = sample_many(trajs, model, seeds=list(range(300, 307)), claim=store_claimer(len(trajs)), max_active=2, **kw)
+    np.savez(os.path.join(out_dir, f"claim{rank}.npz"), idx=np.array(sorted(res), dtype=int),
+             **{f"ev{i}": res[i].evidence for i in res})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dynamic_trajectory_assignment_gloo_world2(tmp_path):
+    """`store_claimer`: every trajectory is claimed by exactly one rank; the results do not depend on the rank."""
+    import torch.multiprocessing as mp
+    port = 29950 + os.getpid() % 300
+    mp.spawn(_claim_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r = [np.load(tmp_path / f"claim{i}.npz") for i in range(2)]
+    got = sorted(list(r[0]["idx"]) + list(r[1]["idx"]))
+    assert got == list(range(7)) and len(r[0]["idx"]) >= 1 and len(r[1]["idx"]) >= 1
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import bild_b200 as bild
+    from test_amis_host import OracleBackedRouse
+    model = OracleBackedRouse(8, 1, 5, d=2, localization_error=0.3)
+    np.random.seed(21)
+    trajs = [model.trajectory_from_loopingprofile(bild.Loopingprofile([0] * a + [1] * b + [0] * c))
+             for a, b, c in [(8, 9, 7), (12, 10, 0), (5, 5, 9), (20, 0, 0), (6, 8, 6), (9, 9, 4), (3, 14, 5)]]
+    kw = dict(init_runs=3, sampler_kw={"N": 15, "max_fcomplete": 40}, k_max=3, certainty_in_k=0.9)
+    for i in range(7):
+        np.random.seed(300 + i)
+        solo = bild.sample(trajs[i], model, **kw)
+        owner = r[0] if i in r[0]["idx"] else r[1]
+        assert np.array_equal(solo.evidence, owner[f"ev{i}"])

@@ -184,21 +184,16 @@ def test_device_ensemble_matches_host_bookkeeping():
         assert dev._device_ensemble() is not None
         for step in range(6):
             np.random.seed(100 * k + step)
-            state = np.random.get_state()
-            batches = []
+            cur = dev.parameters[-1]                          # ONE batch, drawn from the device sampler's proposal, fed to both
+            ss, th = dev.dirichlet.sample(cur[0], dev.N), dev.cfc.sample(cur[1], dev.N)
+            if step == 2:                                     # a rejected sample: zero-length interval, and one off the simplex
+                ss[0, 0] += ss[0, 1]; ss[0, 1] = 0.0
+                ss[1] *= 1.001
             for smp in (dev, host):
-                np.random.set_state(state)
-                cur = smp.parameters[-1]
-                ss, th = smp.dirichlet.sample(cur[0], smp.N), smp.cfc.sample(cur[1], smp.N)
-                if step == 2:                                 # a rejected sample: zero-length interval, and one off the simplex
-                    ss[0, 0] += ss[0, 1]; ss[0, 1] = 0.0
-                    ss[1] *= 1.001
-                batches.append((ss, th))
-                smp.dirichlet.sample = lambda a, N, ss=ss: ss
-                smp.cfc.sample = lambda logp, N, th=th: th
+                smp.dirichlet.sample = lambda a, N, ss=ss: ss.copy()
+                smp.cfc.sample = lambda logp, N, th=th: th.copy()
                 assert smp.step() is True
                 del smp.dirichlet.sample, smp.cfc.sample
-            assert np.array_equal(batches[0][0], batches[1][0]) and np.array_equal(batches[0][1], batches[1][1])
             np.testing.assert_allclose(dev.evidences[-1], host.evidences[-1], rtol=1e-10, atol=1e-10)
             np.testing.assert_allclose(dev.parameters[-1][0], host.parameters[-1][0], rtol=1e-9)
             np.testing.assert_allclose(np.exp(dev.parameters[-1][1]), np.exp(host.parameters[-1][1]), atol=1e-12)

@@ -16,13 +16,15 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bild_b200 as bild  # noqa: E402
-from bild_b200.dataset import sample_many  # noqa: E402
+from bild_b200.dataset import sample_many, store_claimer  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--n-traj", type=int, default=128)
 ap.add_argument("--N", type=int, default=50)
 ap.add_argument("--T", type=int, default=300)
 ap.add_argument("--check", type=int, default=2, help="re-run this many trajectories one by one and compare")
+ap.add_argument("--static", action="store_true", help="static round-robin partition instead of dynamic claims from a shared counter")
+ap.add_argument("--max-active", type=int, default=0, help="concurrent state machines per rank (default: 64 dynamic / all static)")
 a = ap.parse_args()
 rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 local = int(os.environ.get("LOCAL_RANK", 0))
@@ -45,11 +47,12 @@ if world > 1:
 from bild_b200 import _lib  # noqa: E402
 l0 = _lib.load().bildk_launch_count()
 t0 = time.perf_counter()
-res, stats = sample_many(trajs, model, seeds=seeds, rank=rank, world=world)
+claim = store_claimer(len(trajs)) if (world > 1 and not a.static) else None
+res, stats = sample_many(trajs, model, seeds=seeds, rank=rank, world=world, claim=claim, max_active=a.max_active or None)
 wall = time.perf_counter() - t0
 launches = _lib.load().bildk_launch_count() - l0
 summary = np.array([wall, stats["frame_steps"], stats["profiles"], stats["rounds"], len(res),
-                    sum(int(np.array_equal(res[i].best_profile()[:], truths[i])) for i in res)], dtype=np.float64)
+                    sum(int(np.array_equal(res[i].best_profile()[:], truths[i])) for i in res), -wall], dtype=np.float64)
 if world > 1:
     t = torch.from_numpy(summary).cuda()
     tmax = t.clone()
@@ -58,6 +61,7 @@ if world > 1:
     summary = t.cpu().numpy()
     summary[0] = float(tmax[0])
     summary[3] = float(tmax[3])
+    summary[6] = float(tmax[6])          # max of -wall = -(fastest rank's wall)
 
 check = {}
 if rank == 0 and a.check:
@@ -75,7 +79,8 @@ if rank == 0:
         "n_gpus": world, "config": {"workload": f"configs[3]: {a.n_traj} trajectories, N={a.N}, T={a.T}, full bild.sample, defaults",
                                     "parallelism": f"trajectories partitioned over {world} rank(s), fused likelihood batches"},
         "frame_steps": summary[1], "frame_steps_per_s": summary[1] / summary[0], "profiles": summary[2],
-        "fused_rounds_max": summary[3], "launches_rank0": int(launches), "trajectories": int(summary[4]),
+        "fused_rounds_max": summary[3], "rank_wall_min_s": -summary[6], "rank_imbalance": summary[0] / max(-summary[6], 1e-9) - 1.0,
+        "partition": "static round-robin" if (a.static or world == 1) else "dynamic (shared counter)", "launches_rank0": int(launches), "trajectories": int(summary[4]),
         "truth_recovered_exactly": int(summary[5]), "check": check,
         "rank0_wall_split_s": {k: round(stats[k], 3) for k in ("t_host_lanes", "t_pack", "t_gpu")}, "data": "synthetic", "dtype": "f64"}), flush=True)
 if world > 1:

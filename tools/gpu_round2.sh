@@ -62,3 +62,12 @@ if has sweep; then
   tail -24 gpurun_out/sweep_$TAG.md
 fi
 du -sh gpurun_out
+if has dataset; then
+  timeout 900 python tools/bench_dataset.py --n-traj ${NTRAJ:-128} --check 2 > gpurun_out/dataset_${NTRAJ:-128}traj_1gpu_$TAG.json 2> gpurun_out/dataset_$TAG.err
+  cat gpurun_out/dataset_${NTRAJ:-128}traj_1gpu_$TAG.json; tail -3 gpurun_out/dataset_$TAG.err
+fi
+if has small; then
+  timeout 600 python bench.py --workload n50small --steps 10 --warmup 3 --no-cpu --also '' > gpurun_out/bench_n50small_$TAG.json 2> gpurun_out/bench_n50small_$TAG.err
+  python -c "
+import json; d=json.load(open('gpurun_out/bench_n50small_$TAG.json')); print('n50small frac %.3f value %.4g'%(d['roofline']['frac'], d['value']), d['detail']['plan'])"
+fi
