@@ -164,20 +164,29 @@ def reference_impls(model, traj):
     return {"c_port": port}, "port"
 
 
-def pool_time(fn, model, traj, states, n_sample):
+def pool_time(fn, model, traj, states, n_sample, timeout_s=None):
     """Wall seconds of `fn` on the first n_sample profiles over every host core (fork pool, 1 BLAS thread per worker,
-    warm-up pass excluded)."""
+    warm-up pass excluded).  Returns None if the pass does not finish within `timeout_s` (the pool is terminated)."""
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     n_sample = min(n_sample, len(states))
     _W.update(fn=fn, model=model, traj=traj, states=states)
     chunks = [list(range(i, n_sample, cores)) for i in range(cores)]
     chunks = [c for c in chunks if c]
-    with mp.get_context("fork").Pool(len(chunks)) as pool:
-        pool.map(_cpu_worker, [c[:1] for c in chunks])          # warm-up: imports, caches
+    pool = mp.get_context("fork").Pool(len(chunks))
+    try:
+        t_start = time.perf_counter()
+        pool.map_async(_cpu_worker, [c[:1] for c in chunks]).get(timeout=timeout_s)          # warm-up: imports, caches
+        left = None if timeout_s is None else max(1.0, timeout_s - (time.perf_counter() - t_start))
         t0 = time.perf_counter()
-        res = pool.map(_cpu_worker, chunks)
+        res = pool.map_async(_cpu_worker, chunks).get(timeout=left)
         dt = time.perf_counter() - t0
+    except mp.TimeoutError:
+        pool.terminate()
+        pool.join()
+        return None
+    pool.close()
+    pool.join()
     out = np.empty(n_sample)
     for c, r in zip(chunks, res):
         out[c] = r
@@ -197,8 +206,9 @@ def cpu_arm(wl, model, traj, ss, thetas, budget_s, only=None):
     n_probe = min(P, cores)
     states_probe = np.array([ko.st2states(ss[i], thetas[i], T) for i in range(n_probe)])
     # pre-probe: one profile on a trajectory truncated to 24 frames, single process - an implementation that is more than
-    # 4x slower per frame than the best one here is not timed on the pool (e.g. the pure-Python twin at N = 200 with k = 5:
-    # B = exp(-kA) is full of denormals and numpy's dgemm crawls at ~0.4 s per frame)
+    # 20x slower per frame than the best one here is not timed on the pool; every pool pass has a hard time limit on top
+    # (on the 16-core GPU hosts the pure-Python twin at N = 200 ran 0.38 s per frame on the pool - 385 s for sixteen
+    # T = 1000 profiles - although its first 24 frames take 0.3 ms each: B = exp(-kA) with k = 5 is full of denormals)
     from bild_b200.trajectory import Trajectory
     from bild_b200.util import Loopingprofile
     Tp = min(T, 24)
@@ -217,11 +227,16 @@ def cpu_arm(wl, model, traj, ss, thetas, budget_s, only=None):
     for name, fn in impls.items():
         if name not in per_frame:
             continue
-        if per_frame[name] > 4.0 * fastest:
+        if per_frame[name] > 20.0 * fastest:
             skipped[name] = f"not timed on the pool: {per_frame[name] * 1e3:.3g} ms per frame in the single-profile probe vs {fastest * 1e3:.3g} ms for the fastest implementation"
             log(f"cpu {wl['N']}x{T} {name}: {skipped[name]}")
             continue
-        probe = pool_time(fn, model, traj, states_probe, n_probe)
+        limit = max(30.0, 12.0 * budget_s)               # hard cap per pass: an implementation that crawls on this host is dropped
+        probe = pool_time(fn, model, traj, states_probe, n_probe, timeout_s=limit)
+        if probe is None:
+            skipped[name] = f"not timed: one profile per core did not finish within {limit:.0f} s on the pool"
+            log(f"cpu {wl['N']}x{T} {name}: {skipped[name]}")
+            continue
         per_eval_wall = probe["seconds"] / max(1, -(-probe["n"] // probe["cores"]))      # one eval on one core
         n_sample = int(min(P, max(probe["cores"], budget_s / max(per_eval_wall, 1e-9) * probe["cores"])))
         n_sample = max(probe["cores"], n_sample // probe["cores"] * probe["cores"])
@@ -230,7 +245,7 @@ def cpu_arm(wl, model, traj, ss, thetas, budget_s, only=None):
             r = probe                                   # the probe already was a full sample of this size
         else:
             states = np.array([ko.st2states(ss[i], thetas[i], T) for i in range(n_sample)])
-            r = pool_time(fn, model, traj, states, n_sample)
+            r = pool_time(fn, model, traj, states, n_sample, timeout_s=limit) or probe
         r["frame_steps_per_s"] = r["n"] * (T - 1) / r["seconds"]
         out[name] = r
         log(f"cpu {wl['N']}x{T} {name}: {r['frame_steps_per_s']:.4g} frame-steps/s on {r['cores']} cores ({r['n']} profiles, {r['seconds']:.2f} s)")

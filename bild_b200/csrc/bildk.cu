@@ -1568,54 +1568,62 @@ extern "C" int bildk_amis_weights_device(int n, const double* d_logL, const doub
 
 // ------------------------------------------------------------------------------------------------
 // Device-resident AMIS ensemble (bildk_amis.cuh): one call per AMIS iteration.
-template <typename T>
-static int grow_keep(T** p, size_t* cap, size_t used, size_t need, cudaStream_t st) {   // growable device array, contents kept
-    if (need <= *cap) return BILDK_OK;
-    size_t want = std::max(need, *cap * 2);
-    T* q = nullptr;
-    cudaError_t e = cudaMalloc(&q, want * sizeof(T));
-    if (e != cudaSuccess) return fail(BILDK_ENOMEM, "cudaMalloc(%zu bytes): %s", want * sizeof(T), cudaGetErrorString(e));
-    if (*p && used) {
-        e = cudaMemcpyAsync(q, *p, used * sizeof(T), cudaMemcpyDeviceToDevice, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) { cudaFree(q); return fail(BILDK_ECUDA, "device copy failed: %s", cudaGetErrorString(e)); }
-    }
-    if (*p) cudaFree(*p);
-    *p = q;
-    *cap = want;
-    return BILDK_OK;
+//
+// A dataset run creates thousands of ensembles (one per FixedkSampler: ~10 per trajectory), so creating one must be
+// cheap: the stream, the pinned staging buffer and the device staging block are shared PER DEVICE, and an ensemble is
+// two stream-ordered allocations (cudaMallocAsync from the device's memory pool: microseconds once the pool is warm) -
+// one block for the samples, one for the proposals - that grow by doubling.
+struct AmisDevice {
+    std::mutex mu;                 // one AMIS step at a time per device (the calls are synchronous anyway)
+    cudaStream_t st = nullptr;
+    double* pinned = nullptr;      // host staging (inputs) / copy-back (head + 3 n)
+    size_t cap_pinned = 0;
+    double* stage = nullptr;       // device staging of one step's inputs
+    size_t cap_stage = 0;
+};
+static AmisDevice* amis_device(int device) {
+    static std::mutex mu;
+    static std::map<int, AmisDevice*> devs;
+    std::lock_guard<std::mutex> lock(mu);
+    AmisDevice*& d = devs[device];
+    if (!d) d = new AmisDevice();       // lives until process exit
+    return d;
 }
 
 struct bildk_amis {
     int device = 0, K1 = 0, S = 0;
     int n = 0, n_par = 0;
     std::vector<uint8_t> transitions;
-    // ensemble (capacities in samples)
-    double *ss = nullptr, *logs = nullptr, *logL = nullptr, *per = nullptr;
-    uint8_t *thetas = nullptr, *flags = nullptr;
-    size_t cap_ss = 0, cap_logs = 0, cap_logL = 0, cap_per = 0, cap_th = 0, cap_fl = 0;
-    // proposals (capacities in proposals)
-    double *A = nullptr, *lognorm = nullptr, *logp = nullptr, *reach = nullptr, *norm0 = nullptr;
-    size_t cap_A = 0, cap_ln = 0, cap_lp = 0, cap_rc = 0, cap_n0 = 0;
+    AmisDevice* dev = nullptr;
+    // samples block: ss [cap][K1] | logs [cap][K1] | logL [cap] | per [cap][3] | thetas [cap][K1] bytes | flags [cap] bytes
+    char* sblock = nullptr;
+    size_t cap = 0;
+    // proposals block: A [capp][K1] | lognorm [capp] | norm0 [capp] | logp [capp][S K1] | reach [capp][S K1]
+    char* pblock = nullptr;
+    size_t capp = 0;
     double* head = nullptr;        // [4 + 2 K1 + S K1]
-    double* stage = nullptr;       // device staging of one step's inputs
-    size_t cap_stage = 0;
-    double* pinned = nullptr;      // host staging (inputs) / copy-back (head + 3 n)
-    size_t cap_pinned = 0;
-    cudaStream_t st = nullptr;
-    std::mutex mu;
+    double* ss() const { return reinterpret_cast<double*>(sblock); }
+    double* logs() const { return ss() + cap * K1; }
+    double* logL() const { return logs() + cap * K1; }
+    double* per() const { return logL() + cap; }
+    uint8_t* thetas() const { return reinterpret_cast<uint8_t*>(per() + 3 * cap); }
+    uint8_t* flags() const { return thetas() + cap * K1; }
+    static size_t sbytes(size_t cap, int K1) { return (cap * (2 * static_cast<size_t>(K1) + 4)) * 8 + (cap * (static_cast<size_t>(K1) + 1) + 15) / 16 * 16; }
+    double* A() const { return reinterpret_cast<double*>(pblock); }
+    double* lognorm() const { return A() + capp * K1; }
+    double* norm0() const { return lognorm() + capp; }
+    double* logp() const { return norm0() + capp; }
+    double* reach() const { return logp() + capp * S * K1; }
+    static size_t pbytes(size_t capp, int K1, int S) { return capp * (static_cast<size_t>(K1) + 2 + 2 * static_cast<size_t>(S) * K1) * 8; }
 };
 
 extern "C" int bildk_amis_destroy(bildk_amis_t h) {
     if (!h) return BILDK_OK;
     cudaSetDevice(h->device);
-    for (void* q : {static_cast<void*>(h->ss), static_cast<void*>(h->logs), static_cast<void*>(h->logL), static_cast<void*>(h->per),
-                    static_cast<void*>(h->thetas), static_cast<void*>(h->flags), static_cast<void*>(h->A), static_cast<void*>(h->lognorm),
-                    static_cast<void*>(h->logp), static_cast<void*>(h->reach), static_cast<void*>(h->norm0), static_cast<void*>(h->head),
-                    static_cast<void*>(h->stage)})
-        if (q) cudaFree(q);
-    if (h->pinned) cudaFreeHost(h->pinned);
-    if (h->st) cudaStreamDestroy(h->st);
+    cudaStream_t st = h->dev ? h->dev->st : nullptr;
+    if (h->sblock) cudaFreeAsync(h->sblock, st);
+    if (h->pblock) cudaFreeAsync(h->pblock, st);
+    if (h->head) cudaFreeAsync(h->head, st);
     delete h;
     return BILDK_OK;
 }
@@ -1630,12 +1638,21 @@ extern "C" int bildk_amis_create(int K1, int S, const uint8_t* transitions, int 
     if (ndev == 0) return fail(BILDK_ECUDA, "no CUDA device available (this library has no CPU fallback)");
     if (device < 0 || device >= ndev) return fail(BILDK_EINVAL, "device %d out of range", device);
     CU(cudaSetDevice(device));
+    AmisDevice* dev = amis_device(device);
+    std::lock_guard<std::mutex> lock(dev->mu);
+    if (!dev->st) {
+        CU(cudaStreamCreateWithFlags(&dev->st, cudaStreamNonBlocking));
+        cudaMemPool_t pool;                                   // keep freed blocks in the pool instead of returning them to the OS
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     bildk_amis* h = new bildk_amis();
     struct Guard { bildk_amis* h; ~Guard() { if (h) bildk_amis_destroy(h); } } guard{h};
-    h->device = device; h->K1 = K1; h->S = S;
+    h->device = device; h->K1 = K1; h->S = S; h->dev = dev;
     h->transitions.assign(transitions, transitions + static_cast<size_t>(S) * S);
-    CU(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
-    CU(cudaMalloc(&h->head, (4 + 2 * static_cast<size_t>(K1) + static_cast<size_t>(S) * K1) * sizeof(double)));
+    CU(cudaMallocAsync(&h->head, (4 + 2 * static_cast<size_t>(K1) + static_cast<size_t>(S) * K1) * sizeof(double), dev->st));
     guard.h = nullptr;
     *out = h;
     return BILDK_OK;
@@ -1648,6 +1665,47 @@ extern "C" int bildk_amis_size(bildk_amis_t h, int* n_samples, int* n_proposals)
     return BILDK_OK;
 }
 
+// grow the samples / proposals block (stream ordered: the copies queue behind earlier steps, the old block is freed after them)
+static int amis_grow(bildk_amis* h, size_t need_samples, size_t need_par, cudaStream_t st) {
+    const int K1 = h->K1, S = h->S;
+    if (need_samples > h->cap) {
+        bildk_amis old = *h;
+        const size_t cap = std::max<size_t>(std::max<size_t>(need_samples, 2 * h->cap), 1024);
+        char* blk = nullptr;
+        cudaError_t e = cudaMallocAsync(&blk, bildk_amis::sbytes(cap, K1), st);
+        if (e != cudaSuccess) return fail(BILDK_ENOMEM, "cudaMallocAsync(%zu bytes): %s", bildk_amis::sbytes(cap, K1), cudaGetErrorString(e));
+        h->sblock = blk; h->cap = cap;
+        if (old.sblock && old.n) {
+            const size_t n = old.n;
+            CU(cudaMemcpyAsync(h->ss(), old.ss(), n * K1 * 8, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(h->logs(), old.logs(), n * K1 * 8, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(h->logL(), old.logL(), n * 8, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(h->per(), old.per(), 3 * n * 8, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(h->thetas(), old.thetas(), n * K1, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(h->flags(), old.flags(), n, cudaMemcpyDeviceToDevice, st));
+        }
+        if (old.sblock) CU(cudaFreeAsync(old.sblock, st));
+    }
+    if (need_par > h->capp) {
+        bildk_amis old = *h;
+        const size_t capp = std::max<size_t>(std::max<size_t>(need_par, 2 * h->capp), 32);
+        char* blk = nullptr;
+        cudaError_t e = cudaMallocAsync(&blk, bildk_amis::pbytes(capp, K1, S), st);
+        if (e != cudaSuccess) return fail(BILDK_ENOMEM, "cudaMallocAsync(%zu bytes): %s", bildk_amis::pbytes(capp, K1, S), cudaGetErrorString(e));
+        h->pblock = blk; h->capp = capp;
+        if (old.pblock && old.n_par) {
+            const size_t n = old.n_par, sk = static_cast<size_t>(S) * K1;
+            CU(cudaMemcpyAsync(h->A(), old.A(), n * K1 * 8, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(h->lognorm(), old.lognorm(), n * 8, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(h->norm0(), old.norm0(), n * 8, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(h->logp(), old.logp(), n * sk * 8, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(h->reach(), old.reach(), n * sk * 8, cudaMemcpyDeviceToDevice, st));
+        }
+        if (old.pblock) CU(cudaFreeAsync(old.pblock, st));
+    }
+    return BILDK_OK;
+}
+
 extern "C" int bildk_amis_step(bildk_amis_t h, int n_new, const double* ss, const int64_t* thetas, const double* logL,
                                const double* A_cur, const double* logp_cur, double* head, double* per_sample) {
     if (!h) return fail(BILDK_EINVAL, "NULL handle");
@@ -1657,41 +1715,37 @@ extern "C" int bildk_amis_step(bildk_amis_t h, int n_new, const double* ss, cons
     for (size_t i = 0; i < nk; ++i)
         if (thetas[i] < 0 || thetas[i] >= S) return fail(BILDK_EINVAL, "state %lld out of range [0,%d)", static_cast<long long>(thetas[i]), S);
     NvtxRange nvtx("bildk_amis_step");
-    std::lock_guard<std::mutex> lock(h->mu);
+    AmisDevice* dev = h->dev;
+    std::lock_guard<std::mutex> lock(dev->mu);
     CU(cudaSetDevice(h->device));
-    cudaStream_t st = h->st;
+    cudaStream_t st = dev->st;
     const size_t n_old = h->n, n_tot = n_old + n_new, n_par = h->n_par + 1;
-    int rc;
-    if ((rc = grow_keep(&h->ss, &h->cap_ss, n_old * K1, n_tot * K1, st)) || (rc = grow_keep(&h->logs, &h->cap_logs, n_old * K1, n_tot * K1, st)) ||
-        (rc = grow_keep(&h->thetas, &h->cap_th, n_old * K1, n_tot * K1, st)) || (rc = grow_keep(&h->flags, &h->cap_fl, n_old, n_tot, st)) ||
-        (rc = grow_keep(&h->logL, &h->cap_logL, n_old, n_tot, st)) || (rc = grow_keep(&h->per, &h->cap_per, 3 * n_old, 3 * n_tot, st)) ||
-        (rc = grow_keep(&h->A, &h->cap_A, h->n_par * static_cast<size_t>(K1), n_par * K1, st)) ||
-        (rc = grow_keep(&h->lognorm, &h->cap_ln, static_cast<size_t>(h->n_par), n_par, st)) ||
-        (rc = grow_keep(&h->norm0, &h->cap_n0, static_cast<size_t>(h->n_par), n_par, st)) ||
-        (rc = grow_keep(&h->logp, &h->cap_lp, h->n_par * sk, n_par * sk, st)) || (rc = grow_keep(&h->reach, &h->cap_rc, h->n_par * sk, n_par * sk, st)))
-        return rc;
+    int rc = amis_grow(h, n_tot, n_par, st);
+    if (rc) return rc;
     // ---- one packed upload: ss | logL | A | lognorm | norm0 | logp | reach | thetas (bytes)
     const size_t o_ss = 0, o_ll = o_ss + nk, o_A = o_ll + n_new, o_ln = o_A + K1, o_n0 = o_ln + 1, o_lp = o_n0 + 1, o_rc = o_lp + sk,
                  o_th = o_rc + sk, in_doubles = o_th + (nk + 7) / 8;
     const size_t n_head = 4 + 2 * static_cast<size_t>(K1) + sk;
     const size_t out_doubles = n_head + (per_sample ? 3 * n_tot : 0);
     const size_t need_pinned = std::max(in_doubles, out_doubles);
-    if (need_pinned > h->cap_pinned) {
-        if (h->pinned) cudaFreeHost(h->pinned);
-        h->pinned = nullptr; h->cap_pinned = 0;
-        const size_t want = need_pinned * 2;
-        cudaError_t e = cudaMallocHost(&h->pinned, want * sizeof(double));
+    if (need_pinned > dev->cap_pinned) {
+        if (dev->pinned) cudaFreeHost(dev->pinned);
+        dev->pinned = nullptr; dev->cap_pinned = 0;
+        const size_t want = std::max<size_t>(need_pinned * 2, 1 << 16);
+        cudaError_t e = cudaMallocHost(&dev->pinned, want * sizeof(double));
         if (e != cudaSuccess) return fail(BILDK_ENOMEM, "cudaMallocHost(%zu bytes): %s", want * sizeof(double), cudaGetErrorString(e));
-        h->cap_pinned = want;
+        dev->cap_pinned = want;
     }
-    if (in_doubles > h->cap_stage) {
-        if (h->stage) cudaFree(h->stage);
-        h->stage = nullptr; h->cap_stage = 0;
-        cudaError_t e = cudaMalloc(&h->stage, in_doubles * 2 * sizeof(double));
+    if (in_doubles > dev->cap_stage) {
+        if (dev->stage) cudaFree(dev->stage);
+        dev->stage = nullptr; dev->cap_stage = 0;
+        const size_t want = std::max<size_t>(in_doubles * 2, 1 << 14);
+        cudaError_t e = cudaMalloc(&dev->stage, want * sizeof(double));
         if (e != cudaSuccess) return fail(BILDK_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(e));
-        h->cap_stage = in_doubles * 2;
+        dev->cap_stage = want;
     }
-    double* pin = h->pinned;
+    double* pin = dev->pinned;
+    double* stage = dev->stage;
     std::memcpy(pin + o_ss, ss, nk * sizeof(double));
     std::memcpy(pin + o_ll, logL, n_new * sizeof(double));
     std::memcpy(pin + o_A, A_cur, K1 * sizeof(double));
@@ -1719,21 +1773,23 @@ extern "C" int bildk_amis_step(bildk_amis_t h, int n_new, const double* ss, cons
     }
     uint8_t* thb = reinterpret_cast<uint8_t*>(pin + o_th);
     for (size_t i = 0; i < nk; ++i) thb[i] = static_cast<uint8_t>(thetas[i]);
-    CU(cudaMemcpyAsync(h->stage, pin, in_doubles * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(stage, pin, in_doubles * sizeof(double), cudaMemcpyHostToDevice, st));
     // proposal parameters: device-to-device scatter from the staging block (five small copies)
-    CU(cudaMemcpyAsync(h->A + h->n_par * static_cast<size_t>(K1), h->stage + o_A, K1 * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    CU(cudaMemcpyAsync(h->lognorm + h->n_par, h->stage + o_ln, sizeof(double), cudaMemcpyDeviceToDevice, st));
-    CU(cudaMemcpyAsync(h->norm0 + h->n_par, h->stage + o_n0, sizeof(double), cudaMemcpyDeviceToDevice, st));
-    CU(cudaMemcpyAsync(h->logp + h->n_par * sk, h->stage + o_lp, sk * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    CU(cudaMemcpyAsync(h->reach + h->n_par * sk, h->stage + o_rc, sk * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    k_amis_append<<<(n_new + 127) / 128, 128, 0, st>>>(n_new, K1, h->stage + o_ss, reinterpret_cast<const uint8_t*>(h->stage + o_th), h->stage + o_ll,
-                                                     h->ss + n_old * K1, h->logs + n_old * K1, h->thetas + n_old * K1, h->flags + n_old, h->logL + n_old);
+    const size_t jp = h->n_par;
+    CU(cudaMemcpyAsync(h->A() + jp * K1, stage + o_A, K1 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(h->lognorm() + jp, stage + o_ln, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(h->norm0() + jp, stage + o_n0, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(h->logp() + jp * sk, stage + o_lp, sk * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(h->reach() + jp * sk, stage + o_rc, sk * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    k_amis_append<<<(n_new + 127) / 128, 128, 0, st>>>(n_new, K1, stage + o_ss, reinterpret_cast<const uint8_t*>(stage + o_th), stage + o_ll,
+                                                     h->ss() + n_old * K1, h->logs() + n_old * K1, h->thetas() + n_old * K1, h->flags() + n_old,
+                                                     h->logL() + n_old);
     CU(cudaGetLastError());
     g_launches++;
     AmisParams ap{};
     ap.n_old = static_cast<int>(n_old); ap.n_new = n_new; ap.K1 = K1; ap.S = S; ap.n_par = static_cast<int>(n_par);
-    ap.logs = h->logs; ap.thetas = h->thetas; ap.flags = h->flags; ap.ss = h->ss; ap.logL = h->logL; ap.per = h->per;
-    ap.A = h->A; ap.lognorm = h->lognorm; ap.logp = h->logp; ap.reach = h->reach; ap.norm0 = h->norm0;
+    ap.logs = h->logs(); ap.thetas = h->thetas(); ap.flags = h->flags(); ap.ss = h->ss(); ap.logL = h->logL(); ap.per = h->per();
+    ap.A = h->A(); ap.lognorm = h->lognorm(); ap.logp = h->logp(); ap.reach = h->reach(); ap.norm0 = h->norm0();
     ap.log_nsteps = std::log(static_cast<double>(n_par));
     ap.out = h->head;
     {
@@ -1753,7 +1809,7 @@ extern "C" int bildk_amis_step(bildk_amis_t h, int n_new, const double* ss, cons
         g_launches++;
     }
     CU(cudaMemcpyAsync(pin, h->head, n_head * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (per_sample) CU(cudaMemcpyAsync(pin + n_head, h->per, 3 * n_tot * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (per_sample) CU(cudaMemcpyAsync(pin + n_head, h->per(), 3 * n_tot * sizeof(double), cudaMemcpyDeviceToHost, st));
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return fail(BILDK_ECUDA, "AMIS step failed: %s", cudaGetErrorString(e));
     std::memcpy(head, pin, n_head * sizeof(double));

@@ -23,6 +23,7 @@ ap.add_argument("--n-traj", type=int, default=128)
 ap.add_argument("--N", type=int, default=50)
 ap.add_argument("--T", type=int, default=300)
 ap.add_argument("--check", type=int, default=2, help="re-run this many trajectories one by one and compare")
+ap.add_argument("--profile", action="store_true", help="cProfile the driver on rank 0 and print the top of the list to stderr")
 ap.add_argument("--static", action="store_true", help="static round-robin partition instead of dynamic claims from a shared counter")
 ap.add_argument("--max-active", type=int, default=0, help="concurrent state machines per rank (default: 64 dynamic / all static)")
 a = ap.parse_args()
@@ -48,7 +49,19 @@ from bild_b200 import _lib  # noqa: E402
 l0 = _lib.load().bildk_launch_count()
 t0 = time.perf_counter()
 claim = store_claimer(len(trajs)) if (world > 1 and not a.static) else None
+prof = None
+if a.profile and rank == 0:
+    import cProfile
+    prof = cProfile.Profile()
+    prof.enable()
 res, stats = sample_many(trajs, model, seeds=seeds, rank=rank, world=world, claim=claim, max_active=a.max_active or None)
+if prof is not None:
+    import io
+    import pstats
+    prof.disable()
+    buf = io.StringIO()
+    pstats.Stats(prof, stream=buf).sort_stats("tottime").print_stats(30)
+    print(buf.getvalue(), file=sys.stderr)
 wall = time.perf_counter() - t0
 launches = _lib.load().bildk_launch_count() - l0
 summary = np.array([wall, stats["frame_steps"], stats["profiles"], stats["rounds"], len(res),
