@@ -17,6 +17,14 @@ c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int32_p = ctypes.POINTER(ctypes.c_int32)
 c_uint8_p = ctypes.POINTER(ctypes.c_uint8)
 c_uint32_p = ctypes.POINTER(ctypes.c_uint32)
+c_int64_p = ctypes.POINTER(ctypes.c_int64)
+
+
+class AmisReq(ctypes.Structure):
+    """`bildk_amis_req` of include/bild_b200.h: one trajectory's fused AMIS step."""
+    _fields_ = [("ens", ctypes.c_void_p), ("ss", c_double_p), ("thetas", c_int64_p), ("A_cur", c_double_p),
+                ("logp_cur", c_double_p), ("head", c_double_p), ("per_sample", c_double_p)]
+
 
 # every symbol include/bild_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
@@ -36,7 +44,7 @@ SYMBOLS = {
     "bildk_logl_runs_multi": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), c_int32_p, ctypes.c_int, c_int32_p,
                                               c_uint8_p, c_double_p]),
     "bildk_logl_runs_multi_submit": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), c_int32_p, ctypes.c_int, c_int32_p,
-                                                     c_uint8_p, c_double_p, ctypes.POINTER(ctypes.c_void_p)]),
+                                                     c_uint8_p, c_double_p, ctypes.POINTER(AmisReq), ctypes.POINTER(ctypes.c_void_p)]),
     "bildk_logl_wait": (ctypes.c_int, [ctypes.c_void_p]),
     "bildk_amis_weights": (ctypes.c_int, [ctypes.c_int, c_double_p, c_double_p, c_double_p, ctypes.c_double, c_double_p,
                                            c_double_p, ctypes.c_int]),

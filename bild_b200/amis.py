@@ -56,6 +56,19 @@ def _native_helpers():
     return _NATIVE
 
 
+class LikelihoodRequest(tuple):
+    """The ``(ss, thetas)`` batch a sampler yields.  ``amis`` (optional): the sampler's pending device bookkeeping of this
+    very batch (`bild_b200.engine.FusedAmisStep`).  A driver that launches asynchronously may let it ride on the
+    likelihood launch (`bild_b200.dataset.sample_many`); one that does not simply answers with the likelihoods and the
+    sampler runs the step itself."""
+    amis = None
+
+    def __new__(cls, ss, thetas, amis=None):
+        self = super().__new__(cls, (ss, thetas))
+        self.amis = amis
+        return self
+
+
 def drive(gen, evaluate):
     """
     Run a likelihood-requesting generator to completion: every ``(ss, thetas)`` it yields is answered with
@@ -467,9 +480,13 @@ class FixedkSampler:
             # ---- bookkeeping on the device (bildk_amis_step): the ensemble and all proposals live in HBM; only the new
             #      batch goes up, only the statistics of the refit (and the per-sample log weights) come back
             new = {"ss": self.dirichlet.sample(cur[0], self.N), "thetas": self.cfc.sample(cur[1], self.N)}   # RNG order: Dirichlet -> CFC
-            new["logLs"] = yield (new["ss"], new["thetas"])
+            fused = device.fused_step(new["ss"], new["thetas"], cur[0], cur[1])
+            new["logLs"] = yield LikelihoodRequest(new["ss"], new["thetas"], fused)
             new["logLs"] = np.asarray(new["logLs"], dtype=float)
-            summary, mom_m, mom_v, log_marginals, per = device.step(new["ss"], new["thetas"], new["logLs"], cur[0], cur[1])
+            if fused.submitted:                      # the driver let the step ride on the likelihood launch
+                summary, mom_m, mom_v, log_marginals, per = fused.result()
+            else:
+                summary, mom_m, mom_v, log_marginals, per = device.step(new["ss"], new["thetas"], new["logLs"], cur[0], cur[1])
             self.samples.append(new)
             log_w = per[:, 0]
             lo = 0

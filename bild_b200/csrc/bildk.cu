@@ -137,8 +137,10 @@ struct bildk_model {
         bildk_model* owner = nullptr;
         char* pin = nullptr;
         char* dev = nullptr;
-        size_t cap = 0;
+        size_t cap = 0, cap_dev = 0;
         cudaEvent_t done = nullptr;
+        struct PendingAmis { double* head; size_t off_head, n_head; double* per; size_t off_per, n_per; struct bildk_amis* ens; };
+        std::vector<PendingAmis> amis;     // fused AMIS steps of the batch in flight: where their results go
         double* user_out = nullptr;
         size_t off_out = 0;
         int P = 0;
@@ -1217,6 +1219,295 @@ extern "C" int bildk_logl_runs_device(bildk_traj_t t, int P, int K1, const int32
     return launch_device(m, t, 1, t->d_xptr, t->d_vptr, t->d_T, t->d_first, hf, P, K1, d_starts, d_states, d_out, st);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Device-resident AMIS ensemble (bildk_amis.cuh): one call per AMIS iteration.
+//
+// A dataset run creates thousands of ensembles (one per FixedkSampler: ~10 per trajectory), so creating one must be
+// cheap: the stream, the pinned staging buffer and the device staging block are shared PER DEVICE, and an ensemble is
+// two stream-ordered allocations (cudaMallocAsync from the device's memory pool: microseconds once the pool is warm) -
+// one block for the samples, one for the proposals - that grow by doubling.
+struct AmisDevice {
+    std::mutex mu;                 // one AMIS step at a time per device (the calls are synchronous anyway)
+    cudaStream_t st = nullptr;
+    double* pinned = nullptr;      // host staging (inputs) / copy-back (head + 3 n)
+    size_t cap_pinned = 0;
+    double* stage = nullptr;       // device staging of one step's inputs
+    size_t cap_stage = 0;
+};
+static AmisDevice* amis_device(int device) {
+    static std::mutex mu;
+    static std::map<int, AmisDevice*> devs;
+    std::lock_guard<std::mutex> lock(mu);
+    AmisDevice*& d = devs[device];
+    if (!d) d = new AmisDevice();       // lives until process exit
+    return d;
+}
+
+struct bildk_amis {
+    int device = 0, K1 = 0, S = 0;
+    int n = 0, n_par = 0;
+    std::vector<uint8_t> transitions;
+    AmisDevice* dev = nullptr;
+    // samples block: ss [cap][K1] | logs [cap][K1] | logL [cap] | per [cap][3] | thetas [cap][K1] bytes | flags [cap] bytes
+    char* sblock = nullptr;
+    size_t cap = 0;
+    // proposals block: A [capp][K1] | lognorm [capp] | norm0 [capp] | logp [capp][S K1] | reach [capp][S K1]
+    char* pblock = nullptr;
+    size_t capp = 0;
+    double* head = nullptr;        // [4 + 2 K1 + S K1]
+    double* ss() const { return reinterpret_cast<double*>(sblock); }
+    double* logs() const { return ss() + cap * K1; }
+    double* logL() const { return logs() + cap * K1; }
+    double* per() const { return logL() + cap; }
+    uint8_t* thetas() const { return reinterpret_cast<uint8_t*>(per() + 3 * cap); }
+    uint8_t* flags() const { return thetas() + cap * K1; }
+    static size_t sbytes(size_t cap, int K1) { return (cap * (2 * static_cast<size_t>(K1) + 4)) * 8 + (cap * (static_cast<size_t>(K1) + 1) + 15) / 16 * 16; }
+    double* A() const { return reinterpret_cast<double*>(pblock); }
+    double* lognorm() const { return A() + capp * K1; }
+    double* norm0() const { return lognorm() + capp; }
+    double* logp() const { return norm0() + capp; }
+    double* reach() const { return logp() + capp * S * K1; }
+    static size_t pbytes(size_t capp, int K1, int S) { return capp * (static_cast<size_t>(K1) + 2 + 2 * static_cast<size_t>(S) * K1) * 8; }
+};
+
+extern "C" int bildk_amis_destroy(bildk_amis_t h) {
+    if (!h) return BILDK_OK;
+    cudaSetDevice(h->device);
+    cudaStream_t st = h->dev ? h->dev->st : nullptr;
+    if (h->sblock) cudaFreeAsync(h->sblock, st);
+    if (h->pblock) cudaFreeAsync(h->pblock, st);
+    if (h->head) cudaFreeAsync(h->head, st);
+    delete h;
+    return BILDK_OK;
+}
+
+extern "C" int bildk_amis_create(int K1, int S, const uint8_t* transitions, int device, bildk_amis_t* out) {
+    if (!out) return fail(BILDK_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (K1 < 1 || S < 1 || !transitions) return fail(BILDK_EINVAL, "bad argument");
+    if (K1 > AMIS_MAXK1 || S > AMIS_MAXS)
+        return fail(BILDK_EUNSUP, "the device AMIS ensemble handles up to %d slots and %d states (got %d, %d)", AMIS_MAXK1, AMIS_MAXS, K1, S);
+    int ndev = bildk_device_count();
+    if (ndev == 0) return fail(BILDK_ECUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(BILDK_EINVAL, "device %d out of range", device);
+    CU(cudaSetDevice(device));
+    AmisDevice* dev = amis_device(device);
+    std::lock_guard<std::mutex> lock(dev->mu);
+    if (!dev->st) {
+        CU(cudaStreamCreateWithFlags(&dev->st, cudaStreamNonBlocking));
+        cudaMemPool_t pool;                                   // keep freed blocks in the pool instead of returning them to the OS
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
+    bildk_amis* h = new bildk_amis();
+    struct Guard { bildk_amis* h; ~Guard() { if (h) bildk_amis_destroy(h); } } guard{h};
+    h->device = device; h->K1 = K1; h->S = S; h->dev = dev;
+    h->transitions.assign(transitions, transitions + static_cast<size_t>(S) * S);
+    CU(cudaMallocAsync(&h->head, (4 + 2 * static_cast<size_t>(K1) + static_cast<size_t>(S) * K1) * sizeof(double), dev->st));
+    guard.h = nullptr;
+    *out = h;
+    return BILDK_OK;
+}
+
+extern "C" int bildk_amis_size(bildk_amis_t h, int* n_samples, int* n_proposals) {
+    if (!h) return fail(BILDK_EINVAL, "NULL handle");
+    if (n_samples) *n_samples = h->n;
+    if (n_proposals) *n_proposals = h->n_par;
+    return BILDK_OK;
+}
+
+// grow the samples / proposals block (stream ordered: the copies queue behind earlier steps, the old block is freed after them)
+static int amis_grow(bildk_amis* h, size_t need_samples, size_t need_par, cudaStream_t st) {
+    const int K1 = h->K1, S = h->S;
+    if (need_samples > h->cap) {
+        bildk_amis old = *h;
+        const size_t cap = std::max<size_t>(std::max<size_t>(need_samples, 2 * h->cap), 1024);
+        char* blk = nullptr;
+        cudaError_t e = cudaMallocAsync(&blk, bildk_amis::sbytes(cap, K1), st);
+        if (e != cudaSuccess) return fail(BILDK_ENOMEM, "cudaMallocAsync(%zu bytes): %s", bildk_amis::sbytes(cap, K1), cudaGetErrorString(e));
+        h->sblock = blk; h->cap = cap;
+        if (old.sblock && old.n) {
+            const size_t n = old.n;
+            CU(cudaMemcpyAsync(h->ss(), old.ss(), n * K1 * 8, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(h->logs(), old.logs(), n * K1 * 8, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(h->logL(), old.logL(), n * 8, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(h->per(), old.per(), 3 * n * 8, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(h->thetas(), old.thetas(), n * K1, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(h->flags(), old.flags(), n, cudaMemcpyDeviceToDevice, st));
+        }
+        if (old.sblock) CU(cudaFreeAsync(old.sblock, st));
+    }
+    if (need_par > h->capp) {
+        bildk_amis old = *h;
+        const size_t capp = std::max<size_t>(std::max<size_t>(need_par, 2 * h->capp), 32);
+        char* blk = nullptr;
+        cudaError_t e = cudaMallocAsync(&blk, bildk_amis::pbytes(capp, K1, S), st);
+        if (e != cudaSuccess) return fail(BILDK_ENOMEM, "cudaMallocAsync(%zu bytes): %s", bildk_amis::pbytes(capp, K1, S), cudaGetErrorString(e));
+        h->pblock = blk; h->capp = capp;
+        if (old.pblock && old.n_par) {
+            const size_t n = old.n_par, sk = static_cast<size_t>(S) * K1;
+            CU(cudaMemcpyAsync(h->A(), old.A(), n * K1 * 8, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(h->lognorm(), old.lognorm(), n * 8, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(h->norm0(), old.norm0(), n * 8, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(h->logp(), old.logp(), n * sk * 8, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(h->reach(), old.reach(), n * sk * 8, cudaMemcpyDeviceToDevice, st));
+        }
+        if (old.pblock) CU(cudaFreeAsync(old.pblock, st));
+    }
+    return BILDK_OK;
+}
+
+// Staging of one AMIS step (doubles): ss (n K1) | prop: A (K1) lognorm norm0 logp (S K1) reach (S K1) | thetas bytes (n K1)
+static size_t amis_stage_doubles(int n_new, int K1, int S) {
+    const size_t nk = static_cast<size_t>(n_new) * K1, sk = static_cast<size_t>(S) * K1;
+    return nk + K1 + 2 + 2 * sk + (nk + 7) / 8;
+}
+static size_t amis_head_doubles(int K1, int S) { return 4 + 2 * static_cast<size_t>(K1) + static_cast<size_t>(S) * K1; }
+
+// Fill the pinned staging of one step (see amis_stage_doubles); the normalisers of the joining proposal
+// (amis.py:83-108, 258-281) are computed here, once per proposal.
+static void amis_fill_stage(const bildk_amis* h, int n_new, const double* ss, const int64_t* thetas, const double* A_cur,
+                            const double* logp_cur, double* pin) {
+    const int K1 = h->K1, S = h->S;
+    const size_t nk = static_cast<size_t>(n_new) * K1, sk = static_cast<size_t>(S) * K1;
+    const size_t o_A = nk, o_ln = o_A + K1, o_n0 = o_ln + 1, o_lp = o_n0 + 1, o_rc = o_lp + sk, o_th = o_rc + sk;
+    std::memcpy(pin, ss, nk * sizeof(double));
+    std::memcpy(pin + o_A, A_cur, K1 * sizeof(double));
+    const double inf = std::numeric_limits<double>::infinity();
+    auto lse = [&](const double* v, int stride, const uint8_t* allowed) {
+        double top = -inf;
+        for (int m = 0; m < S; ++m)
+            if (!allowed || allowed[m]) top = std::max(top, v[m * stride]);
+        if (!std::isfinite(top)) top = 0.0;
+        double acc = 0.0;
+        for (int m = 0; m < S; ++m)
+            if (!allowed || allowed[m]) acc += std::exp(v[m * stride] - top);
+        return std::log(acc) + top;
+    };
+    double asum = 0.0, lg = 0.0;
+    for (int c = 0; c < K1; ++c) { asum += A_cur[c]; lg += std::lgamma(A_cur[c]); }
+    pin[o_ln] = std::lgamma(asum) - lg;
+    pin[o_n0] = lse(logp_cur, K1, nullptr);
+    std::memcpy(pin + o_lp, logp_cur, sk * sizeof(double));
+    for (int m = 0; m < S; ++m) {
+        pin[o_rc + static_cast<size_t>(m) * K1] = 0.0;
+        for (int c = 1; c < K1; ++c) pin[o_rc + static_cast<size_t>(m) * K1 + c] = lse(logp_cur + c, K1, h->transitions.data() + static_cast<size_t>(m) * S);
+    }
+    uint8_t* thb = reinterpret_cast<uint8_t*>(pin + o_th);
+    for (size_t i = 0; i < nk; ++i) thb[i] = static_cast<uint8_t>(thetas[i]);
+}
+
+// Describe one AMIS step as a device job: the step's inputs will be on the device at `d_stage` (layout of
+// amis_stage_doubles), the new likelihoods at `d_logL` (device, valid in stream order - e.g. the output of the filter
+// kernel enqueued just before); the statistics go to `d_head` (device).  Grows the ensemble's blocks (stream ordered on
+// `st`) and updates its sizes.  Nothing here waits for the GPU.
+static int amis_make_job(bildk_amis* h, int n_new, const double* d_stage, const double* d_logL, double* d_head, cudaStream_t st, AmisJob* job) {
+    const size_t n_old = h->n, n_tot = n_old + n_new, n_par = h->n_par + 1;
+    int rc = amis_grow(h, n_tot, n_par, st);
+    if (rc) return rc;
+    AmisParams& ap = job->p;
+    ap = AmisParams{};
+    ap.n_old = static_cast<int>(n_old); ap.n_new = n_new; ap.K1 = h->K1; ap.S = h->S; ap.n_par = static_cast<int>(n_par);
+    ap.logs = h->logs(); ap.thetas = h->thetas(); ap.flags = h->flags(); ap.ss = h->ss(); ap.logL = h->logL(); ap.per = h->per();
+    ap.A = h->A(); ap.lognorm = h->lognorm(); ap.logp = h->logp(); ap.reach = h->reach(); ap.norm0 = h->norm0();
+    ap.log_nsteps = std::log(static_cast<double>(n_par));
+    ap.out = d_head;
+    job->stage = d_stage;
+    job->logL_new = d_logL;
+    h->n = static_cast<int>(n_tot);
+    h->n_par = static_cast<int>(n_par);
+    return BILDK_OK;
+}
+
+// Launch the jobs at `d_jobs` (device copy; the first n16 have K1 <= 16, the next n32 more slots - the column width of
+// the reduction is a function of the ensemble alone, so a result never depends on its companions): one append launch and
+// one cluster launch per width class, for all ensembles together.
+static int amis_launch(const AmisJob* d_jobs, int n16, int n32, int max_new, cudaStream_t st) {
+    const int n_jobs = n16 + n32;
+    if (n_jobs == 0) return BILDK_OK;
+    k_amis_append<<<dim3((max_new + 127) / 128, n_jobs), 128, 0, st>>>(d_jobs);
+    CU(cudaGetLastError());
+    g_launches++;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(AMIS_THREADS);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = AMIS_CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (n16) {
+        cfg.gridDim = dim3(AMIS_CLUSTER, n16);
+        CU(cudaLaunchKernelEx(&cfg, k_amis_step<16>, d_jobs));
+        g_launches++;
+    }
+    if (n32) {
+        cfg.gridDim = dim3(AMIS_CLUSTER, n32);
+        CU(cudaLaunchKernelEx(&cfg, k_amis_step<32>, d_jobs + n16));
+        g_launches++;
+    }
+    return BILDK_OK;
+}
+
+extern "C" int bildk_amis_step(bildk_amis_t h, int n_new, const double* ss, const int64_t* thetas, const double* logL,
+                               const double* A_cur, const double* logp_cur, double* head, double* per_sample) {
+    if (!h) return fail(BILDK_EINVAL, "NULL handle");
+    if (n_new < 1 || !ss || !thetas || !logL || !A_cur || !logp_cur || !head) return fail(BILDK_EINVAL, "bad argument");
+    const int K1 = h->K1, S = h->S;
+    const size_t nk = static_cast<size_t>(n_new) * K1;
+    for (size_t i = 0; i < nk; ++i)
+        if (thetas[i] < 0 || thetas[i] >= S) return fail(BILDK_EINVAL, "state %lld out of range [0,%d)", static_cast<long long>(thetas[i]), S);
+    NvtxRange nvtx("bildk_amis_step");
+    AmisDevice* dev = h->dev;
+    std::lock_guard<std::mutex> lock(dev->mu);
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = dev->st;
+    const size_t n_tot = static_cast<size_t>(h->n) + n_new;
+    // ---- one packed upload: [job | step staging | logL]
+    constexpr size_t n_job = sizeof(AmisJob) / sizeof(double);
+    static_assert(sizeof(AmisJob) % sizeof(double) == 0, "the job sits in front of the staged doubles");
+    const size_t n_stage = amis_stage_doubles(n_new, K1, S), in_doubles = n_job + n_stage + n_new;
+    const size_t n_head = amis_head_doubles(K1, S);
+    const size_t out_doubles = n_head + (per_sample ? 3 * n_tot : 0);
+    const size_t need_pinned = std::max(in_doubles, out_doubles);
+    if (need_pinned > dev->cap_pinned) {
+        if (dev->pinned) cudaFreeHost(dev->pinned);
+        dev->pinned = nullptr; dev->cap_pinned = 0;
+        const size_t want = std::max<size_t>(need_pinned * 2, 1 << 16);
+        cudaError_t e = cudaMallocHost(&dev->pinned, want * sizeof(double));
+        if (e != cudaSuccess) return fail(BILDK_ENOMEM, "cudaMallocHost(%zu bytes): %s", want * sizeof(double), cudaGetErrorString(e));
+        dev->cap_pinned = want;
+    }
+    if (in_doubles > dev->cap_stage) {
+        if (dev->stage) cudaFree(dev->stage);
+        dev->stage = nullptr; dev->cap_stage = 0;
+        const size_t want = std::max<size_t>(in_doubles * 2, 1 << 14);
+        cudaError_t e = cudaMalloc(&dev->stage, want * sizeof(double));
+        if (e != cudaSuccess) return fail(BILDK_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(e));
+        dev->cap_stage = want;
+    }
+    double* pin = dev->pinned;
+    int rc = amis_make_job(h, n_new, dev->stage + n_job, dev->stage + n_job + n_stage, h->head, st, reinterpret_cast<AmisJob*>(pin));
+    if (rc) return rc;
+    amis_fill_stage(h, n_new, ss, thetas, A_cur, logp_cur, pin + n_job);
+    std::memcpy(pin + n_job + n_stage, logL, n_new * sizeof(double));
+    CU(cudaMemcpyAsync(dev->stage, pin, in_doubles * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = amis_launch(reinterpret_cast<const AmisJob*>(dev->stage), K1 <= 16 ? 1 : 0, K1 <= 16 ? 0 : 1, n_new, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(pin, h->head, n_head * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (per_sample) CU(cudaMemcpyAsync(pin + n_head, h->per(), 3 * n_tot * sizeof(double), cudaMemcpyDeviceToHost, st));
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(BILDK_ECUDA, "AMIS step failed: %s", cudaGetErrorString(e));
+    std::memcpy(head, pin, n_head * sizeof(double));
+    if (per_sample) std::memcpy(per_sample, pin + n_head, 3 * n_tot * sizeof(double));
+    return BILDK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 static size_t align16(size_t x) { return (x + 15) / 16 * 16; }
 
 extern "C" int bildk_logl_wait(void* ticket) {
@@ -1227,14 +1518,22 @@ extern "C" int bildk_logl_wait(void* ticket) {
     cudaError_t e = cudaEventSynchronize(sl->done);
     int rc = BILDK_OK;
     if (e != cudaSuccess) rc = fail(BILDK_ECUDA, "kernel or copy-back failed: %s", cudaGetErrorString(e));
-    else std::memcpy(sl->user_out, sl->pin + sl->off_out, static_cast<size_t>(sl->P) * sizeof(double));
+    else {
+        std::memcpy(sl->user_out, sl->pin + sl->off_out, static_cast<size_t>(sl->P) * sizeof(double));
+        for (const auto& pa : sl->amis) {
+            std::memcpy(pa.head, sl->pin + pa.off_head, pa.n_head * sizeof(double));
+            if (pa.per) std::memcpy(pa.per, sl->pin + pa.off_per, pa.n_per * sizeof(double));
+        }
+    }
     std::lock_guard<std::mutex> lock(sl->owner->mu);
+    sl->amis.clear();
     sl->busy = false;
     return rc;
 }
 
 extern "C" int bildk_logl_runs_multi_submit(int n_traj, const bildk_traj_t* trajs, const int32_t* offsets, int K1,
-                                            const int32_t* starts, const uint8_t* states, double* out, void** ticket) {
+                                            const int32_t* starts, const uint8_t* states, double* out,
+                                            const bildk_amis_req* amis, void** ticket) {
     if (!ticket) return fail(BILDK_EINVAL, "ticket is NULL");
     *ticket = nullptr;
     if (n_traj < 1 || !trajs || !offsets) return fail(BILDK_EINVAL, "need at least one trajectory");
@@ -1258,6 +1557,31 @@ extern "C" int bildk_logl_runs_multi_submit(int n_traj, const bildk_traj_t* traj
         int rc = validate_runs(m, t->T, hf[i + 1] - hf[i], K1, starts + static_cast<size_t>(hf[i]) * K1, states + static_cast<size_t>(hf[i]) * K1, hf[i]);
         if (rc) return rc;
     }
+    // fused AMIS bookkeeping (optional): validate, and size the staging / result areas
+    size_t amis_in = 0, amis_heads = 0, amis_per = 0;
+    std::vector<int> amis_order;                  // trajectories with a fused step: K1 <= 16 first, then the wider ones
+    int amis_n16 = 0;
+    if (amis) {
+        for (int i = 0; i < n_traj; ++i) {
+            const bildk_amis_req& rq = amis[i];
+            const int n_i = hf[i + 1] - hf[i];
+            if (!rq.ens || n_i == 0) continue;
+            if (!rq.ss || !rq.thetas || !rq.A_cur || !rq.logp_cur || !rq.head) return fail(BILDK_EINVAL, "AMIS request %d: NULL array", i);
+            if (rq.ens->device != m->device) return fail(BILDK_EINVAL, "AMIS request %d: ensemble lives on another device", i);
+            const size_t nk = static_cast<size_t>(n_i) * rq.ens->K1;
+            for (size_t e = 0; e < nk; ++e)
+                if (rq.thetas[e] < 0 || rq.thetas[e] >= rq.ens->S) return fail(BILDK_EINVAL, "AMIS request %d: state out of range", i);
+            amis_in += amis_stage_doubles(n_i, rq.ens->K1, rq.ens->S);
+            amis_heads += amis_head_doubles(rq.ens->K1, rq.ens->S);
+            if (rq.per_sample) amis_per += 3 * (static_cast<size_t>(rq.ens->n) + n_i);
+            for (int j : amis_order)
+                if (amis[j].ens == rq.ens) return fail(BILDK_EINVAL, "AMIS request %d: the same ensemble twice in one batch", i);
+            amis_order.push_back(i);
+        }
+        std::stable_partition(amis_order.begin(), amis_order.end(), [&](int i) { return amis[i].ens->K1 <= 16; });
+        for (int i : amis_order) amis_n16 += amis[i].ens->K1 <= 16;
+    }
+    const size_t amis_jobs = amis_order.size();
     NvtxRange nvtx("bildk_logl_runs_multi_submit");
     std::lock_guard<std::mutex> lock(m->mu);
     CU(cudaSetDevice(m->device));
@@ -1266,21 +1590,31 @@ extern "C" int bildk_logl_runs_multi_submit(int n_traj, const bildk_traj_t* traj
         if (!cand.busy) { sl = &cand; break; }
     if (!sl) return fail(BILDK_EINVAL, "both batch slots of this model are in flight: call bildk_logl_wait first");
     // ---- slot layout (bytes): run starts | run states | T per trajectory | first filter per trajectory | x pointers |
-    //      valid-mask pointers | CTA maps | filter -> trajectory | out
+    //      valid-mask pointers | jobs and staging of the fused AMIS steps | CTA maps | filter -> trajectory | out | AMIS statistics
+    //      (device mirror up to here) | per-sample AMIS arrays (pinned only: copied straight from the ensembles)
     const size_t nrun = static_cast<size_t>(P) * K1;
     const size_t o_st = 0, o_rs = align16(o_st + nrun * sizeof(int32_t)), o_T = align16(o_rs + nrun), o_first = align16(o_T + n_traj * sizeof(int)),
                  o_x = align16(o_first + (n_traj + 1) * sizeof(int)), o_v = align16(o_x + n_traj * sizeof(void*)),
-                 o_cta = align16(o_v + n_traj * sizeof(void*)), o_pt = align16(o_cta + 2 * (static_cast<size_t>(P) + n_traj) * sizeof(int)),
-                 o_out = align16(o_pt + static_cast<size_t>(P) * sizeof(int)), total = align16(o_out + static_cast<size_t>(P) * sizeof(double));
+                 o_jobs = align16(o_v + n_traj * sizeof(void*)), o_ain = align16(o_jobs + amis_jobs * sizeof(AmisJob)),
+                 o_cta = align16(o_ain + amis_in * sizeof(double)),
+                 o_pt = align16(o_cta + 2 * (static_cast<size_t>(P) + n_traj) * sizeof(int)),
+                 o_out = align16(o_pt + static_cast<size_t>(P) * sizeof(int)), o_heads = o_out + static_cast<size_t>(P) * sizeof(double),
+                 total_dev = align16(o_heads + amis_heads * sizeof(double)), total = align16(total_dev + amis_per * sizeof(double));
     if (total > sl->cap) {
         if (sl->pin) cudaFreeHost(sl->pin);
-        if (sl->dev) cudaFree(sl->dev);
-        sl->pin = sl->dev = nullptr; sl->cap = 0;
+        sl->pin = nullptr; sl->cap = 0;
         const size_t want = total * 2;
         cudaError_t e = cudaMallocHost(&sl->pin, want);
-        if (e == cudaSuccess) e = cudaMalloc(&sl->dev, want);
-        if (e != cudaSuccess) return fail(BILDK_ENOMEM, "slot allocation (%zu bytes): %s", want, cudaGetErrorString(e));
+        if (e != cudaSuccess) return fail(BILDK_ENOMEM, "pinned slot allocation (%zu bytes): %s", want, cudaGetErrorString(e));
         sl->cap = want;
+    }
+    if (total_dev > sl->cap_dev) {
+        if (sl->dev) cudaFree(sl->dev);
+        sl->dev = nullptr; sl->cap_dev = 0;
+        const size_t want = total_dev * 2;
+        cudaError_t e = cudaMalloc(&sl->dev, want);
+        if (e != cudaSuccess) return fail(BILDK_ENOMEM, "device slot allocation (%zu bytes): %s", want, cudaGetErrorString(e));
+        sl->cap_dev = want;
     }
     std::memcpy(sl->pin + o_st, starts, nrun * sizeof(int32_t));
     std::memcpy(sl->pin + o_rs, states, nrun);
@@ -1291,6 +1625,32 @@ extern "C" int bildk_logl_runs_multi_submit(int n_traj, const bildk_traj_t* traj
     for (int i = 0; i < n_traj; ++i) { hT[i] = trajs[i]->T; hx[i] = trajs[i]->dx; hv[i] = trajs[i]->dvalid; }
     for (int i = 0; i <= n_traj; ++i) hfirst[i] = hf[i];
     cudaStream_t st = m->st;
+    // ---- fused AMIS bookkeeping: every trajectory's step consumes its likelihoods straight from the kernel's output,
+    //      in stream order behind the filter kernel - no host round trip, no extra synchronisation
+    sl->amis.clear();
+    int amis_max_new = 0;
+    std::unique_lock<std::mutex> amis_lock;       // the ensembles change size here: keep synchronous bildk_amis_step calls out
+    if (amis_jobs) {
+        amis_lock = std::unique_lock<std::mutex>(amis[amis_order[0]].ens->dev->mu);
+        double* ain = reinterpret_cast<double*>(sl->pin + o_ain);
+        AmisJob* jobs = reinterpret_cast<AmisJob*>(sl->pin + o_jobs);
+        size_t off_ain = o_ain, off_head = o_heads;
+        for (size_t j = 0; j < amis_jobs; ++j) {
+            const int i = amis_order[j];
+            const bildk_amis_req& rq = amis[i];
+            const int n_i = hf[i + 1] - hf[i];
+            const size_t n_head = amis_head_doubles(rq.ens->K1, rq.ens->S);
+            amis_fill_stage(rq.ens, n_i, rq.ss, rq.thetas, rq.A_cur, rq.logp_cur, ain);
+            int rc = amis_make_job(rq.ens, n_i, reinterpret_cast<const double*>(sl->dev + off_ain),
+                                   reinterpret_cast<const double*>(sl->dev + o_out) + hf[i], reinterpret_cast<double*>(sl->dev + off_head), st, &jobs[j]);
+            if (rc) return rc;
+            sl->amis.push_back(bildk_model::Slot::PendingAmis{rq.head, off_head, n_head, rq.per_sample, 0, 0, rq.ens});
+            ain += amis_stage_doubles(n_i, rq.ens->K1, rq.ens->S);
+            off_ain += amis_stage_doubles(n_i, rq.ens->K1, rq.ens->S) * sizeof(double);
+            off_head += n_head * sizeof(double);
+            amis_max_new = std::max(amis_max_new, n_i);
+        }
+    }
     CU(cudaMemcpyAsync(sl->dev, sl->pin, o_cta, cudaMemcpyHostToDevice, st));     // everything up to the CTA maps in one copy
     MapArena arena;
     arena.h_cta = reinterpret_cast<int*>(sl->pin + o_cta); arena.d_cta = reinterpret_cast<int*>(sl->dev + o_cta);
@@ -1300,7 +1660,19 @@ extern "C" int bildk_logl_runs_multi_submit(int n_traj, const bildk_traj_t* traj
                            reinterpret_cast<const int*>(sl->dev + o_first), hf, P, K1, reinterpret_cast<const int32_t*>(sl->dev + o_st),
                            reinterpret_cast<const uint8_t*>(sl->dev + o_rs), reinterpret_cast<double*>(sl->dev + o_out), st, &arena);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(sl->pin + o_out, sl->dev + o_out, static_cast<size_t>(P) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (amis_jobs) {
+        rc = amis_launch(reinterpret_cast<const AmisJob*>(sl->dev + o_jobs), amis_n16, static_cast<int>(amis_jobs) - amis_n16, amis_max_new, st);
+        if (rc) return rc;
+        size_t off_per = total_dev;
+        for (auto& pa : sl->amis) {
+            if (!pa.per) continue;
+            pa.off_per = off_per;
+            pa.n_per = 3 * static_cast<size_t>(pa.ens->n);
+            CU(cudaMemcpyAsync(sl->pin + off_per, pa.ens->per(), pa.n_per * sizeof(double), cudaMemcpyDeviceToHost, st));
+            off_per += pa.n_per * sizeof(double);
+        }
+    }
+    CU(cudaMemcpyAsync(sl->pin + o_out, sl->dev + o_out, static_cast<size_t>(P) * sizeof(double) + amis_heads * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(sl->done, st));
     sl->user_out = out; sl->off_out = o_out; sl->P = P; sl->busy = true;
     *ticket = sl;
@@ -1310,7 +1682,7 @@ extern "C" int bildk_logl_runs_multi_submit(int n_traj, const bildk_traj_t* traj
 extern "C" int bildk_logl_runs_multi(int n_traj, const bildk_traj_t* trajs, const int32_t* offsets, int K1,
                                      const int32_t* starts, const uint8_t* states, double* out) {
     void* ticket = nullptr;
-    int rc = bildk_logl_runs_multi_submit(n_traj, trajs, offsets, K1, starts, states, out, &ticket);
+    int rc = bildk_logl_runs_multi_submit(n_traj, trajs, offsets, K1, starts, states, out, nullptr, &ticket);
     if (rc) return rc;
     return bildk_logl_wait(ticket);
 }
@@ -1563,258 +1935,5 @@ extern "C" int bildk_amis_weights_device(int n, const double* d_logL, const doub
     if (n < 1 || !d_logL || !d_logdelta || !d_curlp || !d_stats) return fail(BILDK_EINVAL, "bad argument");
     NvtxRange nvtx("bildk_amis_weights_device");
     CU(launch_amis_weights(n, d_logL, d_logdelta, d_curlp, log_nsteps, d_log_w, d_stats, static_cast<cudaStream_t>(stream)));
-    return BILDK_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Device-resident AMIS ensemble (bildk_amis.cuh): one call per AMIS iteration.
-//
-// A dataset run creates thousands of ensembles (one per FixedkSampler: ~10 per trajectory), so creating one must be
-// cheap: the stream, the pinned staging buffer and the device staging block are shared PER DEVICE, and an ensemble is
-// two stream-ordered allocations (cudaMallocAsync from the device's memory pool: microseconds once the pool is warm) -
-// one block for the samples, one for the proposals - that grow by doubling.
-struct AmisDevice {
-    std::mutex mu;                 // one AMIS step at a time per device (the calls are synchronous anyway)
-    cudaStream_t st = nullptr;
-    double* pinned = nullptr;      // host staging (inputs) / copy-back (head + 3 n)
-    size_t cap_pinned = 0;
-    double* stage = nullptr;       // device staging of one step's inputs
-    size_t cap_stage = 0;
-};
-static AmisDevice* amis_device(int device) {
-    static std::mutex mu;
-    static std::map<int, AmisDevice*> devs;
-    std::lock_guard<std::mutex> lock(mu);
-    AmisDevice*& d = devs[device];
-    if (!d) d = new AmisDevice();       // lives until process exit
-    return d;
-}
-
-struct bildk_amis {
-    int device = 0, K1 = 0, S = 0;
-    int n = 0, n_par = 0;
-    std::vector<uint8_t> transitions;
-    AmisDevice* dev = nullptr;
-    // samples block: ss [cap][K1] | logs [cap][K1] | logL [cap] | per [cap][3] | thetas [cap][K1] bytes | flags [cap] bytes
-    char* sblock = nullptr;
-    size_t cap = 0;
-    // proposals block: A [capp][K1] | lognorm [capp] | norm0 [capp] | logp [capp][S K1] | reach [capp][S K1]
-    char* pblock = nullptr;
-    size_t capp = 0;
-    double* head = nullptr;        // [4 + 2 K1 + S K1]
-    double* ss() const { return reinterpret_cast<double*>(sblock); }
-    double* logs() const { return ss() + cap * K1; }
-    double* logL() const { return logs() + cap * K1; }
-    double* per() const { return logL() + cap; }
-    uint8_t* thetas() const { return reinterpret_cast<uint8_t*>(per() + 3 * cap); }
-    uint8_t* flags() const { return thetas() + cap * K1; }
-    static size_t sbytes(size_t cap, int K1) { return (cap * (2 * static_cast<size_t>(K1) + 4)) * 8 + (cap * (static_cast<size_t>(K1) + 1) + 15) / 16 * 16; }
-    double* A() const { return reinterpret_cast<double*>(pblock); }
-    double* lognorm() const { return A() + capp * K1; }
-    double* norm0() const { return lognorm() + capp; }
-    double* logp() const { return norm0() + capp; }
-    double* reach() const { return logp() + capp * S * K1; }
-    static size_t pbytes(size_t capp, int K1, int S) { return capp * (static_cast<size_t>(K1) + 2 + 2 * static_cast<size_t>(S) * K1) * 8; }
-};
-
-extern "C" int bildk_amis_destroy(bildk_amis_t h) {
-    if (!h) return BILDK_OK;
-    cudaSetDevice(h->device);
-    cudaStream_t st = h->dev ? h->dev->st : nullptr;
-    if (h->sblock) cudaFreeAsync(h->sblock, st);
-    if (h->pblock) cudaFreeAsync(h->pblock, st);
-    if (h->head) cudaFreeAsync(h->head, st);
-    delete h;
-    return BILDK_OK;
-}
-
-extern "C" int bildk_amis_create(int K1, int S, const uint8_t* transitions, int device, bildk_amis_t* out) {
-    if (!out) return fail(BILDK_EINVAL, "out is NULL");
-    *out = nullptr;
-    if (K1 < 1 || S < 1 || !transitions) return fail(BILDK_EINVAL, "bad argument");
-    if (K1 > AMIS_MAXK1 || S > AMIS_MAXS)
-        return fail(BILDK_EUNSUP, "the device AMIS ensemble handles up to %d slots and %d states (got %d, %d)", AMIS_MAXK1, AMIS_MAXS, K1, S);
-    int ndev = bildk_device_count();
-    if (ndev == 0) return fail(BILDK_ECUDA, "no CUDA device available (this library has no CPU fallback)");
-    if (device < 0 || device >= ndev) return fail(BILDK_EINVAL, "device %d out of range", device);
-    CU(cudaSetDevice(device));
-    AmisDevice* dev = amis_device(device);
-    std::lock_guard<std::mutex> lock(dev->mu);
-    if (!dev->st) {
-        CU(cudaStreamCreateWithFlags(&dev->st, cudaStreamNonBlocking));
-        cudaMemPool_t pool;                                   // keep freed blocks in the pool instead of returning them to the OS
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-    }
-    bildk_amis* h = new bildk_amis();
-    struct Guard { bildk_amis* h; ~Guard() { if (h) bildk_amis_destroy(h); } } guard{h};
-    h->device = device; h->K1 = K1; h->S = S; h->dev = dev;
-    h->transitions.assign(transitions, transitions + static_cast<size_t>(S) * S);
-    CU(cudaMallocAsync(&h->head, (4 + 2 * static_cast<size_t>(K1) + static_cast<size_t>(S) * K1) * sizeof(double), dev->st));
-    guard.h = nullptr;
-    *out = h;
-    return BILDK_OK;
-}
-
-extern "C" int bildk_amis_size(bildk_amis_t h, int* n_samples, int* n_proposals) {
-    if (!h) return fail(BILDK_EINVAL, "NULL handle");
-    if (n_samples) *n_samples = h->n;
-    if (n_proposals) *n_proposals = h->n_par;
-    return BILDK_OK;
-}
-
-// grow the samples / proposals block (stream ordered: the copies queue behind earlier steps, the old block is freed after them)
-static int amis_grow(bildk_amis* h, size_t need_samples, size_t need_par, cudaStream_t st) {
-    const int K1 = h->K1, S = h->S;
-    if (need_samples > h->cap) {
-        bildk_amis old = *h;
-        const size_t cap = std::max<size_t>(std::max<size_t>(need_samples, 2 * h->cap), 1024);
-        char* blk = nullptr;
-        cudaError_t e = cudaMallocAsync(&blk, bildk_amis::sbytes(cap, K1), st);
-        if (e != cudaSuccess) return fail(BILDK_ENOMEM, "cudaMallocAsync(%zu bytes): %s", bildk_amis::sbytes(cap, K1), cudaGetErrorString(e));
-        h->sblock = blk; h->cap = cap;
-        if (old.sblock && old.n) {
-            const size_t n = old.n;
-            CU(cudaMemcpyAsync(h->ss(), old.ss(), n * K1 * 8, cudaMemcpyDeviceToDevice, st));
-            CU(cudaMemcpyAsync(h->logs(), old.logs(), n * K1 * 8, cudaMemcpyDeviceToDevice, st));
-            CU(cudaMemcpyAsync(h->logL(), old.logL(), n * 8, cudaMemcpyDeviceToDevice, st));
-            CU(cudaMemcpyAsync(h->per(), old.per(), 3 * n * 8, cudaMemcpyDeviceToDevice, st));
-            CU(cudaMemcpyAsync(h->thetas(), old.thetas(), n * K1, cudaMemcpyDeviceToDevice, st));
-            CU(cudaMemcpyAsync(h->flags(), old.flags(), n, cudaMemcpyDeviceToDevice, st));
-        }
-        if (old.sblock) CU(cudaFreeAsync(old.sblock, st));
-    }
-    if (need_par > h->capp) {
-        bildk_amis old = *h;
-        const size_t capp = std::max<size_t>(std::max<size_t>(need_par, 2 * h->capp), 32);
-        char* blk = nullptr;
-        cudaError_t e = cudaMallocAsync(&blk, bildk_amis::pbytes(capp, K1, S), st);
-        if (e != cudaSuccess) return fail(BILDK_ENOMEM, "cudaMallocAsync(%zu bytes): %s", bildk_amis::pbytes(capp, K1, S), cudaGetErrorString(e));
-        h->pblock = blk; h->capp = capp;
-        if (old.pblock && old.n_par) {
-            const size_t n = old.n_par, sk = static_cast<size_t>(S) * K1;
-            CU(cudaMemcpyAsync(h->A(), old.A(), n * K1 * 8, cudaMemcpyDeviceToDevice, st));
-            CU(cudaMemcpyAsync(h->lognorm(), old.lognorm(), n * 8, cudaMemcpyDeviceToDevice, st));
-            CU(cudaMemcpyAsync(h->norm0(), old.norm0(), n * 8, cudaMemcpyDeviceToDevice, st));
-            CU(cudaMemcpyAsync(h->logp(), old.logp(), n * sk * 8, cudaMemcpyDeviceToDevice, st));
-            CU(cudaMemcpyAsync(h->reach(), old.reach(), n * sk * 8, cudaMemcpyDeviceToDevice, st));
-        }
-        if (old.pblock) CU(cudaFreeAsync(old.pblock, st));
-    }
-    return BILDK_OK;
-}
-
-extern "C" int bildk_amis_step(bildk_amis_t h, int n_new, const double* ss, const int64_t* thetas, const double* logL,
-                               const double* A_cur, const double* logp_cur, double* head, double* per_sample) {
-    if (!h) return fail(BILDK_EINVAL, "NULL handle");
-    if (n_new < 1 || !ss || !thetas || !logL || !A_cur || !logp_cur || !head) return fail(BILDK_EINVAL, "bad argument");
-    const int K1 = h->K1, S = h->S;
-    const size_t nk = static_cast<size_t>(n_new) * K1, sk = static_cast<size_t>(S) * K1;
-    for (size_t i = 0; i < nk; ++i)
-        if (thetas[i] < 0 || thetas[i] >= S) return fail(BILDK_EINVAL, "state %lld out of range [0,%d)", static_cast<long long>(thetas[i]), S);
-    NvtxRange nvtx("bildk_amis_step");
-    AmisDevice* dev = h->dev;
-    std::lock_guard<std::mutex> lock(dev->mu);
-    CU(cudaSetDevice(h->device));
-    cudaStream_t st = dev->st;
-    const size_t n_old = h->n, n_tot = n_old + n_new, n_par = h->n_par + 1;
-    int rc = amis_grow(h, n_tot, n_par, st);
-    if (rc) return rc;
-    // ---- one packed upload: ss | logL | A | lognorm | norm0 | logp | reach | thetas (bytes)
-    const size_t o_ss = 0, o_ll = o_ss + nk, o_A = o_ll + n_new, o_ln = o_A + K1, o_n0 = o_ln + 1, o_lp = o_n0 + 1, o_rc = o_lp + sk,
-                 o_th = o_rc + sk, in_doubles = o_th + (nk + 7) / 8;
-    const size_t n_head = 4 + 2 * static_cast<size_t>(K1) + sk;
-    const size_t out_doubles = n_head + (per_sample ? 3 * n_tot : 0);
-    const size_t need_pinned = std::max(in_doubles, out_doubles);
-    if (need_pinned > dev->cap_pinned) {
-        if (dev->pinned) cudaFreeHost(dev->pinned);
-        dev->pinned = nullptr; dev->cap_pinned = 0;
-        const size_t want = std::max<size_t>(need_pinned * 2, 1 << 16);
-        cudaError_t e = cudaMallocHost(&dev->pinned, want * sizeof(double));
-        if (e != cudaSuccess) return fail(BILDK_ENOMEM, "cudaMallocHost(%zu bytes): %s", want * sizeof(double), cudaGetErrorString(e));
-        dev->cap_pinned = want;
-    }
-    if (in_doubles > dev->cap_stage) {
-        if (dev->stage) cudaFree(dev->stage);
-        dev->stage = nullptr; dev->cap_stage = 0;
-        const size_t want = std::max<size_t>(in_doubles * 2, 1 << 14);
-        cudaError_t e = cudaMalloc(&dev->stage, want * sizeof(double));
-        if (e != cudaSuccess) return fail(BILDK_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(e));
-        dev->cap_stage = want;
-    }
-    double* pin = dev->pinned;
-    double* stage = dev->stage;
-    std::memcpy(pin + o_ss, ss, nk * sizeof(double));
-    std::memcpy(pin + o_ll, logL, n_new * sizeof(double));
-    std::memcpy(pin + o_A, A_cur, K1 * sizeof(double));
-    {   // normalisers of the joining proposal (amis.py:83-108, 258-281), once per proposal
-        const double inf = std::numeric_limits<double>::infinity();
-        auto lse = [&](const double* v, int stride, const uint8_t* allowed) {
-            double top = -inf;
-            for (int m = 0; m < S; ++m)
-                if (!allowed || allowed[m]) top = std::max(top, v[m * stride]);
-            if (!std::isfinite(top)) top = 0.0;
-            double acc = 0.0;
-            for (int m = 0; m < S; ++m)
-                if (!allowed || allowed[m]) acc += std::exp(v[m * stride] - top);
-            return std::log(acc) + top;
-        };
-        double asum = 0.0, lg = 0.0;
-        for (int c = 0; c < K1; ++c) { asum += A_cur[c]; lg += std::lgamma(A_cur[c]); }
-        pin[o_ln] = std::lgamma(asum) - lg;
-        pin[o_n0] = lse(logp_cur, K1, nullptr);
-        std::memcpy(pin + o_lp, logp_cur, sk * sizeof(double));
-        for (int m = 0; m < S; ++m) {
-            pin[o_rc + static_cast<size_t>(m) * K1] = 0.0;
-            for (int c = 1; c < K1; ++c) pin[o_rc + static_cast<size_t>(m) * K1 + c] = lse(logp_cur + c, K1, h->transitions.data() + static_cast<size_t>(m) * S);
-        }
-    }
-    uint8_t* thb = reinterpret_cast<uint8_t*>(pin + o_th);
-    for (size_t i = 0; i < nk; ++i) thb[i] = static_cast<uint8_t>(thetas[i]);
-    CU(cudaMemcpyAsync(stage, pin, in_doubles * sizeof(double), cudaMemcpyHostToDevice, st));
-    // proposal parameters: device-to-device scatter from the staging block (five small copies)
-    const size_t jp = h->n_par;
-    CU(cudaMemcpyAsync(h->A() + jp * K1, stage + o_A, K1 * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    CU(cudaMemcpyAsync(h->lognorm() + jp, stage + o_ln, sizeof(double), cudaMemcpyDeviceToDevice, st));
-    CU(cudaMemcpyAsync(h->norm0() + jp, stage + o_n0, sizeof(double), cudaMemcpyDeviceToDevice, st));
-    CU(cudaMemcpyAsync(h->logp() + jp * sk, stage + o_lp, sk * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    CU(cudaMemcpyAsync(h->reach() + jp * sk, stage + o_rc, sk * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    k_amis_append<<<(n_new + 127) / 128, 128, 0, st>>>(n_new, K1, stage + o_ss, reinterpret_cast<const uint8_t*>(stage + o_th), stage + o_ll,
-                                                     h->ss() + n_old * K1, h->logs() + n_old * K1, h->thetas() + n_old * K1, h->flags() + n_old,
-                                                     h->logL() + n_old);
-    CU(cudaGetLastError());
-    g_launches++;
-    AmisParams ap{};
-    ap.n_old = static_cast<int>(n_old); ap.n_new = n_new; ap.K1 = K1; ap.S = S; ap.n_par = static_cast<int>(n_par);
-    ap.logs = h->logs(); ap.thetas = h->thetas(); ap.flags = h->flags(); ap.ss = h->ss(); ap.logL = h->logL(); ap.per = h->per();
-    ap.A = h->A(); ap.lognorm = h->lognorm(); ap.logp = h->logp(); ap.reach = h->reach(); ap.norm0 = h->norm0();
-    ap.log_nsteps = std::log(static_cast<double>(n_par));
-    ap.out = h->head;
-    {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(AMIS_CLUSTER);
-        cfg.blockDim = dim3(AMIS_THREADS);
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = AMIS_CLUSTER;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        if (K1 <= 16) CU(cudaLaunchKernelEx(&cfg, k_amis_step<16>, ap));
-        else CU(cudaLaunchKernelEx(&cfg, k_amis_step<32>, ap));
-        g_launches++;
-    }
-    CU(cudaMemcpyAsync(pin, h->head, n_head * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (per_sample) CU(cudaMemcpyAsync(pin + n_head, h->per(), 3 * n_tot * sizeof(double), cudaMemcpyDeviceToHost, st));
-    cudaError_t e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) return fail(BILDK_ECUDA, "AMIS step failed: %s", cudaGetErrorString(e));
-    std::memcpy(head, pin, n_head * sizeof(double));
-    if (per_sample) std::memcpy(per_sample, pin + n_head, 3 * n_tot * sizeof(double));
-    h->n = static_cast<int>(n_tot);
-    h->n_par = static_cast<int>(n_par);
     return BILDK_OK;
 }

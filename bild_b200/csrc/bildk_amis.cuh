@@ -12,7 +12,7 @@
 // HBM; one launch per step does all of the above and returns only the statistics the host needs for the (tiny)
 // proposal refit: 4 evidence sums, 2 K1 moments, S K1 marginals.
 //
-// One thread-block cluster of AMIS_CLUSTER CTAs; CTA r owns a contiguous chunk of the samples in every pass, partial
+// One thread-block cluster of AMIS_CLUSTER CTAs per ensemble; CTA r owns a contiguous chunk of the samples in every pass, partial
 // sums cross CTAs through distributed shared memory in rank order: the result is a function of the ensemble alone
 // (bitwise reproducible, independent of what else runs), as the dataset driver's "identical to one-by-one runs"
 // contract requires.
@@ -72,13 +72,45 @@ __device__ __forceinline__ double amis_logaddexp(double a, double b) {   // np.l
     return hi + log1p(exp(lo - hi));
 }
 
+// One step of one ensemble as the kernels see it.  A launch handles MANY ensembles (blockIdx.y = job): the dataset driver
+// enqueues the steps of all trajectories of a fused likelihood launch behind it with two launches in total.
+struct AmisJob {
+    AmisParams p;
+    const double* stage;       // this step's inputs: ss_new (n_new K1) | A (K1) lognorm norm0 logp (S K1) reach (S K1) | thetas bytes (n_new K1)
+    const double* logL_new;    // (n_new) likelihoods of the new samples (e.g. inside the filter kernel's output)
+};
+
 // New samples join the ensemble: log of the interval lengths (xlogy needs it for every proposal, every later step) and
-// the sample-level rejection flag of scipy's dirichlet (entries outside [0, 1], sum off by more than 1e-9; amis.py:98-108).
-__global__ void k_amis_append(int n_new, int K1, const double* __restrict__ ss_new, const uint8_t* __restrict__ th_new,
-                              const double* __restrict__ logL_new, double* __restrict__ ss, double* __restrict__ logs,
-                              uint8_t* __restrict__ thetas, uint8_t* __restrict__ flags, double* __restrict__ logL) {
+// the sample-level rejection flag of scipy's dirichlet (entries outside [0, 1], sum off by more than 1e-9; amis.py:98-108);
+// the proposal they were drawn from joins the list of proposals.
+__global__ void k_amis_append(const AmisJob* __restrict__ jobs) {
+    const AmisJob& job = jobs[blockIdx.y];
+    const int n_new = job.p.n_new, K1 = job.p.K1, S = job.p.S;
+    if (blockIdx.x * blockDim.x >= n_new) return;
+    const size_t nk = static_cast<size_t>(n_new) * K1, n_old = job.p.n_old;
+    const int sk = S * K1;
+    const double* __restrict__ ss_new = job.stage;
+    const double* __restrict__ prop_new = job.stage + nk;
+    const uint8_t* __restrict__ th_new = reinterpret_cast<const uint8_t*>(prop_new + K1 + 2 + 2 * sk);
+    if (blockIdx.x == 0) {   // the joining proposal, staged as A (K1) | lognorm | norm0 | logp (S K1) | reach (S K1)
+        const size_t jp = job.p.n_par - 1;
+        double* A = const_cast<double*>(job.p.A) + jp * K1;
+        double* logp = const_cast<double*>(job.p.logp) + jp * sk;
+        double* reach = const_cast<double*>(job.p.reach) + jp * sk;
+        for (int e = threadIdx.x; e < K1 + 2 + 2 * sk; e += blockDim.x) {
+            const double v = prop_new[e];
+            if (e < K1) A[e] = v;
+            else if (e == K1) const_cast<double*>(job.p.lognorm)[jp] = v;
+            else if (e == K1 + 1) const_cast<double*>(job.p.norm0)[jp] = v;
+            else if (e < K1 + 2 + sk) logp[e - K1 - 2] = v;
+            else reach[e - K1 - 2 - sk] = v;
+        }
+    }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_new) return;
+    double* ss = const_cast<double*>(job.p.ss) + n_old * K1;
+    double* logs = const_cast<double*>(job.p.logs) + n_old * K1;
+    uint8_t* thetas = const_cast<uint8_t*>(job.p.thetas) + n_old * K1;
     double sum = 0.0;
     bool bad = false;
     for (int c = 0; c < K1; ++c) {
@@ -90,14 +122,19 @@ __global__ void k_amis_append(int n_new, int K1, const double* __restrict__ ss_n
         thetas[static_cast<size_t>(i) * K1 + c] = th_new[static_cast<size_t>(i) * K1 + c];
     }
     if (!(fabs(sum - 1.0) <= 1e-9)) bad = true;
-    flags[i] = bad ? 1 : 0;
-    logL[i] = logL_new[i];
+    const_cast<uint8_t*>(job.p.flags)[n_old + i] = bad ? 1 : 0;
+    const_cast<double*>(job.p.logL)[n_old + i] = job.logL_new[i];
 }
 
 // CPAD: columns per row group (16 or 32, >= K1); a warp covers 32 / CPAD samples per pass-2/3 iteration.
 template <int CPAD>
-__global__ void __launch_bounds__(AMIS_THREADS) k_amis_step(const __grid_constant__ AmisParams p) {
+__global__ void __launch_bounds__(AMIS_THREADS) k_amis_step(const AmisJob* __restrict__ jobs) {
     namespace cg = cooperative_groups;
+    __shared__ AmisParams p;                       // one cluster (gridDim.x CTAs) per job
+    static_assert(sizeof(AmisParams) % 8 == 0, "copied by 64-bit words");
+    if (threadIdx.x < sizeof(AmisParams) / 8)
+        reinterpret_cast<unsigned long long*>(&p)[threadIdx.x] = reinterpret_cast<const unsigned long long*>(&jobs[blockIdx.y].p)[threadIdx.x];
+    __syncthreads();
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = static_cast<int>(cluster.block_rank()), ncta = static_cast<int>(cluster.num_blocks());
     constexpr int NW = AMIS_THREADS / 32;

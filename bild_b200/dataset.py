@@ -45,6 +45,7 @@ class _Lane:
         self.idx, self.traj, self.seed = idx, traj, seed
         self.gen = None
         self.request = None                      # (ss, thetas) waiting for evaluation
+        self.amis = None                         # the AMIS bookkeeping that may ride on that launch (FusedAmisStep)
         self.answer = None
         self.result = None
         self.done = False
@@ -60,8 +61,10 @@ class _Lane:
             np.random.set_state(self.rng_state)
             send, self.answer = self.answer, None
         try:
-            ss, thetas = self.gen.send(send)
+            req = self.gen.send(send)
+            ss, thetas = req
             self.request = (np.asarray(ss, dtype=float), np.asarray(thetas))
+            self.amis = getattr(req, "amis", None)
         except StopIteration as stop:
             self.result = stop.value
             self.done = True
@@ -84,7 +87,7 @@ def store_claimer(n_total, store=None, key="bild_b200/next_trajectory"):
     return claim
 
 
-def sample_many(trajs, model, seeds=None, rank=0, world=1, max_active=None, claim=None, **sample_kw):
+def sample_many(trajs, model, seeds=None, rank=0, world=1, max_active=None, claim=None, fuse_amis=True, **sample_kw):
     """
     Run `sample` on every trajectory, fusing the likelihood batches of all concurrently active trajectories.
 
@@ -101,6 +104,9 @@ def sample_many(trajs, model, seeds=None, rank=0, world=1, max_active=None, clai
     claim : callable, optional
         dynamic partition: ``claim(n)`` returns up to ``n`` not yet assigned trajectory indices (`store_claimer`);
         overrides `rank` / `world`
+    fuse_amis : bool
+        let every sampler's device bookkeeping (`bildk_amis_step`) ride on the fused likelihood launch, in stream order
+        behind the filter kernel, instead of one synchronous call per sampler step (same arithmetic, same bits)
     **sample_kw : forwarded to `sample` (dE, init_runs, sampler_kw, ...)
 
     Returns
@@ -190,7 +196,8 @@ def sample_many(trajs, model, seeds=None, rank=0, world=1, max_active=None, clai
                 stats["t_pack"] += time.perf_counter() - tic
                 tic = time.perf_counter()
                 if n_groups > 1 and len(inflight[g]) == 0:
-                    batch = model.logL_runs_multi_submit([ln.traj for ln in lanes], offsets, all_starts, all_states)
+                    batch = model.logL_runs_multi_submit([ln.traj for ln in lanes], offsets, all_starts, all_states,
+                                                         amis=[ln.amis for ln in lanes] if fuse_amis else None)
                 else:   # synchronous models, and the (rare) second localisation-error batch of a round: one slot per group
                     batch = model.logL_runs_multi([ln.traj for ln in lanes], offsets, all_starts, all_states)
                 inflight[g].append((batch, lanes, offsets))

@@ -15,7 +15,7 @@ import numpy as np
 from . import _lib
 from ._lib import c_double_p, c_int32_p, c_uint8_p, c_uint32_p, as_f64, ptr
 
-__all__ = ["RouseEngine", "TrajectoryHandle", "AmisEnsemble", "st_to_runs", "states_to_runs"]
+__all__ = ["RouseEngine", "TrajectoryHandle", "AmisEnsemble", "FusedAmisStep", "st_to_runs", "states_to_runs"]
 
 
 def st_to_runs(ss, thetas, T):
@@ -121,27 +121,68 @@ class AmisEnsemble:
     def supports(cls, K1, n_states):
         return K1 <= cls.MAX_K1 and n_states <= cls.MAX_STATES
 
+    def _check_batch(self, ss, thetas, a, logp):
+        ss = np.ascontiguousarray(ss, dtype=np.float64)
+        thetas = np.ascontiguousarray(thetas, dtype=np.int64)
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        logp = np.ascontiguousarray(logp, dtype=np.float64)
+        if ss.ndim != 2 or ss.shape[1] != self.K1 or thetas.shape != ss.shape or a.shape != (self.K1,) or logp.shape != (self.S, self.K1):
+            raise ValueError("inconsistent AMIS batch")
+        n_tot = self.n + len(ss)
+        if n_tot > len(self._per):
+            self._per = np.empty((max(n_tot, 2 * len(self._per)), 3))   # contents are rewritten in full by every step
+        return ss, thetas, a, logp, np.empty(4 + 2 * self.K1 + self.S * self.K1)
+
+    def _unpack(self, head, n_tot):
+        K1 = self.K1
+        return tuple(head[:4]), head[4:4 + K1], head[4 + K1:4 + 2 * K1], head[4 + 2 * K1:].reshape(self.S, K1), self._per[:n_tot]
+
     def step(self, ss, thetas, logLs, a, logp):
         """-> ((max, sum w, sum (w - mean)^2, nansum w (logL - log q)), mean (K1,), var (K1,), log marginals (S, K1),
         per-sample array (n, 3): log_w | logdelta | log q_cur of the whole ensemble - a view that later steps overwrite)."""
-        ss = np.ascontiguousarray(ss, dtype=np.float64)
-        thetas = np.ascontiguousarray(thetas, dtype=np.int64)
+        ss, thetas, a, logp, head = self._check_batch(ss, thetas, a, logp)
         logLs = np.ascontiguousarray(logLs, dtype=np.float64)
-        a = np.ascontiguousarray(a, dtype=np.float64)
-        logp = np.ascontiguousarray(logp, dtype=np.float64)
         n_new = len(logLs)
-        if ss.shape != (n_new, self.K1) or thetas.shape != ss.shape or a.shape != (self.K1,) or logp.shape != (self.S, self.K1):
+        if len(ss) != n_new:
             raise ValueError("inconsistent AMIS batch")
-        n_tot = self.n + n_new
-        if n_tot > len(self._per):
-            self._per = np.empty((max(n_tot, 2 * len(self._per)), 3))   # contents are rewritten in full by every step
-        head = np.empty(4 + 2 * self.K1 + self.S * self.K1)
-        _lib.check(_lib.load().bildk_amis_step(self._h, n_new, ptr(ss, c_double_p), thetas.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+        _lib.check(_lib.load().bildk_amis_step(self._h, n_new, ptr(ss, c_double_p), ptr(thetas, _lib.c_int64_p),
                                                ptr(logLs, c_double_p), ptr(a, c_double_p), ptr(logp, c_double_p), ptr(head, c_double_p),
                                                ptr(self._per, c_double_p)))
-        self.n = n_tot
-        K1 = self.K1
-        return tuple(head[:4]), head[4:4 + K1], head[4 + K1:4 + 2 * K1], head[4 + 2 * K1:].reshape(self.S, K1), self._per[:n_tot]
+        self.n += n_new
+        return self._unpack(head, self.n)
+
+    def fused_step(self, ss, thetas, a, logp):
+        """The same step riding on a likelihood launch (``bildk_logl_runs_multi_submit`` with `amis`): the likelihoods go
+        from the filter kernel's output straight into the ensemble on the device.  Returns a `FusedAmisStep`; hand it to
+        `RouseEngine.logl_runs_multi_submit` and read ``.result()`` after the batch's ``wait()``."""
+        return FusedAmisStep(self, *self._check_batch(ss, thetas, a, logp))
+
+
+class FusedAmisStep:
+    """One AMIS step in flight with a likelihood batch; owns the arrays the C side reads and writes until `wait`."""
+
+    def __init__(self, ens, ss, thetas, a, logp, head):
+        self.ens, self.ss, self.thetas, self.a, self.logp, self.head = ens, ss, thetas, a, logp, head
+        self.per = ens._per                    # pinned by this reference: a later growth must not free it under the copy
+        self.submitted = False
+
+    def fill(self, req):
+        """Write the C struct `bildk_amis_req` for this step."""
+        req.ens = self.ens._h
+        req.ss, req.thetas = ptr(self.ss, c_double_p), ptr(self.thetas, _lib.c_int64_p)
+        req.A_cur, req.logp_cur = ptr(self.a, c_double_p), ptr(self.logp, c_double_p)
+        req.head, req.per_sample = ptr(self.head, c_double_p), ptr(self.per, c_double_p)
+
+    def mark_submitted(self):
+        self.submitted = True
+        self.ens.n += len(self.ss)             # the library's ensemble has grown (in stream order)
+        self.n_tot = self.ens.n
+
+    def result(self):
+        """As `AmisEnsemble.step` (valid after the carrying batch's ``wait()``)."""
+        if not self.submitted:
+            raise RuntimeError("this AMIS step was not carried by a launch")
+        return self.ens._unpack(self.head, self.n_tot)
 
 
 class PendingBatch:
@@ -225,7 +266,7 @@ class RouseEngine:
         P, K1 = ss.shape
         out = np.empty(P, dtype=np.float64)
         if P:
-            _lib.check(_lib.load().bildk_logl_st(traj._h, P, K1, ptr(ss, c_double_p), ptr(thetas, ctypes.POINTER(ctypes.c_int64)),
+            _lib.check(_lib.load().bildk_logl_st(traj._h, P, K1, ptr(ss, c_double_p), ptr(thetas, _lib.c_int64_p),
                                                  ptr(out, c_double_p)))
         return out
 
@@ -255,9 +296,11 @@ class RouseEngine:
                                                          ptr(starts, c_int32_p), ptr(run_states, c_uint8_p), ptr(out, c_double_p)))
         return out
 
-    def logl_runs_multi_submit(self, trajs, offsets, starts, run_states):
+    def logl_runs_multi_submit(self, trajs, offsets, starts, run_states, amis=None):
         """Asynchronous `logl_runs_multi`: stages and enqueues the batch (nothing waits for the GPU) and returns a
-        `PendingBatch`; ``.wait()`` returns the (P,) log-likelihoods.  At most two batches in flight per model."""
+        `PendingBatch`; ``.wait()`` returns the (P,) log-likelihoods.  At most two batches in flight per model.
+        ``amis``: per trajectory a `FusedAmisStep` (`AmisEnsemble.fused_step`) or None - the AMIS bookkeeping of that
+        trajectory's batch is enqueued behind the filter kernel in the same stream."""
         starts = np.ascontiguousarray(starts, dtype=np.int32)
         run_states = np.ascontiguousarray(run_states, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.int32)
@@ -265,12 +308,26 @@ class RouseEngine:
             raise ValueError("inconsistent multi-trajectory batch")
         out = np.empty(starts.shape[0], dtype=np.float64)
         ticket = ctypes.c_void_p()
+        reqs, steps = None, []
+        if amis is not None and any(a is not None for a in amis):
+            if len(amis) != len(trajs):
+                raise ValueError("one AMIS entry (or None) per trajectory")
+            reqs = (_lib.AmisReq * len(trajs))()
+            for i, a in enumerate(amis):
+                if a is None:
+                    continue
+                if len(a.ss) != offsets[i + 1] - offsets[i]:
+                    raise ValueError("AMIS step and likelihood batch differ in size")
+                a.fill(reqs[i])
+                steps.append(a)
         if len(out):
             arr = (ctypes.c_void_p * len(trajs))(*[t._h for t in trajs])
             _lib.check(_lib.load().bildk_logl_runs_multi_submit(len(trajs), arr, ptr(offsets, c_int32_p), starts.shape[1],
                                                                 ptr(starts, c_int32_p), ptr(run_states, c_uint8_p), ptr(out, c_double_p),
-                                                                ctypes.byref(ticket)))
-        return PendingBatch(ticket, out, trajs)
+                                                                reqs, ctypes.byref(ticket)))
+            for a in steps:
+                a.mark_submitted()
+        return PendingBatch(ticket, out, (trajs, steps))
 
     def logl_runs_device(self, traj, P, K1, d_starts, d_states, d_out, stream=0):
         """Device pointers (ints); asynchronous on ``stream``."""

@@ -220,10 +220,11 @@ class MultiStateRouse(MultiStateModel):
         to ``trajs[i]`` (used by `bild_b200.dataset.sample_many`)."""
         return self.engine.logl_runs_multi([self._handle(t) for t in trajs], offsets, starts, run_states)
 
-    def logL_runs_multi_submit(self, trajs, offsets, starts, run_states):
+    def logL_runs_multi_submit(self, trajs, offsets, starts, run_states, amis=None):
         """Asynchronous `logL_runs_multi`: returns an object whose ``wait()`` gives the log-likelihoods; the launch runs
-        while the caller does host work (at most two batches in flight)."""
-        return self.engine.logl_runs_multi_submit([self._handle(t) for t in trajs], offsets, starts, run_states)
+        while the caller does host work (at most two batches in flight).  ``amis``: per trajectory the fused AMIS step
+        of its batch (`bild_b200.engine.FusedAmisStep`) or None."""
+        return self.engine.logl_runs_multi_submit([self._handle(t) for t in trajs], offsets, starts, run_states, amis=amis)
 
     def _logL_st_local(self, ss, thetas, traj):
         return self.engine.logl_st(self._handle(traj), ss, thetas)

@@ -113,6 +113,25 @@ int bildk_logl_runs_multi(int n_traj, const bildk_traj_t *trajs, const int32_t *
                           const int32_t *run_starts, const uint8_t *run_states, double *out);
 
 /*
+ * One fused AMIS step of a trajectory's batch (see bildk_amis_step below for the meaning of the fields): with `amis`
+ * given, bildk_logl_runs_multi_submit enqueues, behind the filter kernel and in the same stream, the bookkeeping of every
+ * trajectory whose entry has a non-NULL `ens` - the likelihoods go from the kernel's output into the ensemble on the
+ * device, the statistics come back with the likelihoods at bildk_logl_wait.  All steps of a batch share two launches
+ * (append; one cluster per ensemble).  An ensemble may appear once per batch; every array of a request must stay valid
+ * until bildk_logl_wait.  The result of a step is a function of its ensemble alone (same bits as bildk_amis_step).
+ */
+typedef struct bildk_amis *bildk_amis_t;
+typedef struct bildk_amis_req {
+    bildk_amis_t ens;              /* NULL: no bookkeeping for this trajectory */
+    const double *ss;              /* (n_i, K1 of the ensemble) interval lengths of the batch, n_i = offsets[i+1] - offsets[i] */
+    const int64_t *thetas;         /* (n_i, K1) state traces */
+    const double *A_cur;           /* (K1) */
+    const double *logp_cur;        /* (S, K1) */
+    double *head;                  /* out: 4 + 2 K1 + S K1 statistics */
+    double *per_sample;            /* out: (n_total, 3), or NULL */
+} bildk_amis_req;
+
+/*
  * Asynchronous form of bildk_logl_runs_multi: `submit` stages the batch in pinned memory, enqueues upload, kernel and
  * download on the model's private stream WITHOUT waiting for anything, and returns a ticket; `out` must stay valid until
  * bildk_logl_wait(ticket) has returned (it fills out[]).  A model has two batch slots, i.e. at most two tickets in flight
@@ -120,7 +139,8 @@ int bildk_logl_runs_multi(int n_traj, const bildk_traj_t *trajs, const int32_t *
  * (bild_b200/dataset.py).  An empty batch returns a NULL ticket, which bildk_logl_wait accepts.
  */
 int bildk_logl_runs_multi_submit(int n_traj, const bildk_traj_t *trajs, const int32_t *offsets, int K1,
-                                 const int32_t *run_starts, const uint8_t *run_states, double *out, void **ticket);
+                                 const int32_t *run_starts, const uint8_t *run_states, double *out,
+                                 const bildk_amis_req *amis /* n_traj entries, or NULL */, void **ticket);
 int bildk_logl_wait(void *ticket);
 
 /*
@@ -173,7 +193,6 @@ int bildk_amis_log_proposal(int n_par, int n, int K1, int S, const double *A, co
  *   per_sample (n_total, 3) log_w | logdelta | log q_cur of EVERY sample so far, or NULL
  * Limits: K1 <= 32, S <= 4 (BILDK_EUNSUP otherwise: the caller keeps the bookkeeping on the host).
  */
-typedef struct bildk_amis *bildk_amis_t;
 int bildk_amis_create(int K1, int S, const uint8_t *transitions, int device, bildk_amis_t *out);
 int bildk_amis_destroy(bildk_amis_t h);
 int bildk_amis_size(bildk_amis_t h, int *n_samples, int *n_proposals);

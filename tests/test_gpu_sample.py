@@ -236,3 +236,55 @@ def test_device_ensemble_matches_host_bookkeeping():
             np.testing.assert_allclose(a[ok], b[ok], rtol=1e-11, atol=1e-11)
         assert np.isposinf(np.concatenate([b["logδs"] for b in dev.samples])).sum() >= 1
         np.testing.assert_allclose(np.exp(dev.log_marginal_posterior()), np.exp(host.log_marginal_posterior()), atol=1e-10)
+
+
+def test_fused_amis_steps_match_synchronous_steps_bitwise():
+    """`bildk_logl_runs_multi_submit` with `amis` requests (the bookkeeping of several samplers riding on ONE likelihood
+    launch, two AMIS launches for all of them) against `bildk_amis_step` called sampler by sampler: identical bits in
+    the statistics and in every per-sample array, for both column-width classes (K1 <= 16 and K1 = 18) in one batch,
+    three states, and a rejected sample."""
+    from bild_b200 import amis
+    model = bild.models.MultiStateRouse(12, 1, 5, d=2, looppositions=(None, (0, -1), (2, 8)), localization_error=0.3)
+    np.random.seed(9)
+    truth = bild.Loopingprofile([0] * 15 + [1] * 15 + [2] * 15 + [0] * 15)
+    trajs = [model.trajectory_from_loopingprofile(truth, missing_frames=0.1) for _ in range(3)]
+    ks = (17, 2, 5)                                           # mixed order: the library sorts the width classes itself
+    fused = [amis.FixedkSampler(t, model, k=k, N=48 + 8 * i) for i, (t, k) in enumerate(zip(trajs, ks))]
+    solo = [amis.FixedkSampler(t, model, k=k, N=48 + 8 * i) for i, (t, k) in enumerate(zip(trajs, ks))]
+    for step in range(5):
+        gens, reqs = [], []
+        for i, smp in enumerate(fused):
+            np.random.seed(1000 * step + i)
+            g = smp.step_gen()
+            req = next(g)
+            if step == 2 and i == 1:
+                req[0][0, 0] += req[0][0, 1]; req[0][0, 1] = 0.0      # a rejected sample (zero-length interval)
+            gens.append(g)
+            reqs.append(req)
+        runs = [bild.engine.st_to_runs(r[0], r[1], len(t)) for r, t in zip(reqs, trajs)]
+        K1 = max(a.shape[1] for a, _ in runs)
+        starts = np.concatenate([np.concatenate([a, np.full((len(a), K1 - a.shape[1]), len(t), dtype=a.dtype)], axis=1)
+                                 for (a, _), t in zip(runs, trajs)])
+        states = np.concatenate([np.concatenate([b, np.repeat(b[:, -1:], K1 - b.shape[1], axis=1)], axis=1) for _, b in runs])
+        offsets = np.concatenate([[0], np.cumsum([len(a) for a, _ in runs])])
+        batch = model.logL_runs_multi_submit(trajs, offsets, starts, states, amis=[r.amis for r in reqs])
+        out = batch.wait()
+        for i, (g, smp) in enumerate(zip(gens, fused)):
+            assert reqs[i].amis.submitted
+            try:
+                g.send(out[offsets[i]:offsets[i + 1]])
+            except StopIteration as stop:
+                assert stop.value is True
+            # the same batch through the synchronous call
+            other = solo[i]
+            other.dirichlet.sample = lambda a, N, ss=reqs[i][0]: ss.copy()
+            other.cfc.sample = lambda logp, N, th=reqs[i][1]: th.copy()
+            assert other.step() is True
+            del other.dirichlet.sample, other.cfc.sample
+            assert np.array_equal(smp.evidences[-1], other.evidences[-1])
+            assert np.array_equal(smp.parameters[-1][0], other.parameters[-1][0])
+            assert np.array_equal(smp.parameters[-1][1], other.parameters[-1][1])
+            for key in ("logLs", "log_weights", "logδs", "cur_log_proposal"):
+                a = np.concatenate([b[key] for b in smp.samples])
+                b = np.concatenate([b[key] for b in other.samples])
+                assert np.array_equal(a, b, equal_nan=True), (step, i, key)
