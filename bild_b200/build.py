@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(HERE, "csrc", "bildk.cu")]
 DEPS = SRC + [os.path.join(HERE, "csrc", "bildk_kernels.cuh"), os.path.join(HERE, "csrc", "bildk_mma.cuh"),
-              os.path.join(HERE, "csrc", "bildk_mmar.cuh"), os.path.join(HERE, "csrc", "bildk_mmag2.cuh"), os.path.join(HERE, "csrc", "bildk_mmact.cuh"),
+              os.path.join(HERE, "csrc", "bildk_mmar.cuh"), os.path.join(HERE, "csrc", "bildk_mmar2.cuh"), os.path.join(HERE, "csrc", "bildk_mmag2.cuh"), os.path.join(HERE, "csrc", "bildk_mmact.cuh"),
               os.path.join(HERE, "csrc", "bildk_amis.cuh"),
               os.path.join(os.path.dirname(HERE), "include", "bild_b200.h")]
 OUT = os.path.join(HERE, "libbild_b200.so")
@@ -52,6 +52,8 @@ def build(force=False, verbose=False):
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    # one translation unit, ~40 kernel instantiations: let nvcc optimise them in parallel (3.7 min -> 1 min on 8 cores)
+    flags += ["--split-compile", str(min(16, os.cpu_count() or 1))]
     cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

@@ -7,6 +7,7 @@
 #include "bildk_kernels.cuh"
 #include "bildk_mma.cuh"
 #include "bildk_mmar.cuh"
+#include "bildk_mmar2.cuh"
 #include "bildk_mmag2.cuh"
 #include "bildk_mmact.cuh"
 #include "bildk_amis.cuh"
@@ -120,6 +121,7 @@ struct bildk_model {
     double *dBm = nullptr, *dSigm = nullptr, *dC0m = nullptr;
     // register-chained tensor-core kernel (k_mmar): GT <= 4 and N mod 8 in 1..4
     bool mmar_ok = false;
+    bool mmar2_ok = false;   // the same with two warps per filter (k_mmar2): GT 5..7
     int r_last = 0, LDr = 0, fstride_r = 0;
     double* dBr = nullptr;
     // per-model scratch of the launcher: partial logL of the d* sub-filters; covariance workspace of the N > 112 kernels
@@ -371,7 +373,7 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
             m->mma_ok = 16 + matb * 8 * S + fbytes <= static_cast<size_t>(m->max_smem_optin);
             // register-chained kernel: the last tile-row block must have room for M^T (and a zero row)
             const int rl = N - 8 * (GT - 1);
-            if (GT <= 4 && rl >= 1 && rl <= 4 && d <= 4 && m->wz_idx[0] == 0 && m->wz_idx[1] == N - 1 && N >= 2) {   // end-to-end measurement only
+            if (GT <= 7 && rl >= 1 && rl <= 4 && d <= 4 && m->wz_idx[0] == 0 && m->wz_idx[1] == N - 1 && N >= 2) {   // end-to-end measurement only
                 const int R = 8 * GT;
                 const int LDr = (R % 16 == 8) ? R : R + 8;
                 const size_t matr = static_cast<size_t>(R) * LDr;
@@ -384,7 +386,9 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
                 if ((rc = upload(&m->dBr, pad.data(), S * matr))) return rc;
                 m->r_last = rl; m->LDr = LDr;
                 m->fstride_r = static_cast<int>(matr) + 2 * R + 8;
-                m->mmar_ok = 16 + matr * 8 * S + static_cast<size_t>(m->fstride_r) * 8 * 4 <= static_cast<size_t>(m->max_smem_optin);
+                const bool fits = 16 + matr * 8 * S + static_cast<size_t>(m->fstride_r) * 8 * 4 <= static_cast<size_t>(m->max_smem_optin);
+                m->mmar_ok = fits && GT <= 4;
+                m->mmar2_ok = fits && GT >= 5;
             }
         }
     }
@@ -473,6 +477,7 @@ struct Plan {
     bool mmact = false;    // ... and P2 / update / write-back dealt out as tile slots (k_mmact)
     bool mma2 = false;     // tensor-core kernel, two warps per filter (GT 5..7)
     bool mmar = false;     // tensor-core kernel, one warp per filter, T chained through registers (GT <= 4)
+    bool mmar2 = false;    // the same with two warps per filter splitting the tile rows (GT 5..7, N mod 8 in 1..4)
     int nb = 0;            // ... its variant: resident 4-warp CTAs per SM it is compiled for
     unsigned char colmap[40] = {0};
     int WPC = 0;
@@ -542,6 +547,23 @@ static cudaError_t mmar_launch_for(int GT, int NB, const RParams& rp, dim3 grid,
 #define X(G_, N_) if (GT == G_ && NB == N_) return mmar_launch<G_, N_>(rp, grid, threads, smem, st);
     MMAR_VARIANTS(X)
 #undef X
+    return cudaErrorInvalidValue;
+}
+
+template <int GT, int MAXF>
+static cudaError_t mmar2_launch(const R2Params& rp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    {
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&k_mmar2<GT, MAXF>), smem);
+        if (e != cudaSuccess) return e;
+    }
+    k_mmar2<GT, MAXF><<<grid, threads, smem, st>>>(rp);
+    return cudaGetLastError();
+}
+constexpr int MMAR2_MAXF = 4;   // filters per CTA: 8 warps at 255 registers (spill-free; 5 or 6 filters spill, see bildk_mmar2.cuh)
+static cudaError_t mmar2_launch_for(int GT, const R2Params& rp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    if (GT == 5) return mmar2_launch<5, MMAR2_MAXF>(rp, grid, threads, smem, st);
+    if (GT == 6) return mmar2_launch<6, MMAR2_MAXF>(rp, grid, threads, smem, st);
+    if (GT == 7) return mmar2_launch<7, MMAR2_MAXF>(rp, grid, threads, smem, st);
     return cudaErrorInvalidValue;
 }
 
@@ -718,6 +740,36 @@ static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
     Plan pl{};
     {
         const char* force0 = getenv("BILDK_KERNEL");
+        if (m->mmar2_ok && !force0 && !env_int("BILDK_FORCE_GENERIC", 0) && env_int("BILDK_MMAR2", 1)) {
+            const size_t matb = static_cast<size_t>(8 * m->GT) * m->LDr * 8;
+            const size_t fbytes = static_cast<size_t>(m->fstride_r) * 8;
+            int f = env_int("BILDK_FPC2", 0);
+            if (f <= 0) {
+                // filters per CTA by  waves x time per wave.  Measured at N = 50 (T = 200, P = 16384, profiles/r02_mmar2_variants.txt):
+                // 4 filters in one CTA per SM 52.3 ms, 2 filters x 2 CTAs per SM 53.1, 3 filters (one scheduler pair carries
+                // two warps) 69.2, 1 filter x 3 CTAs per SM 59.3 - relative time of one full wave (all resident slots busy):
+                static const double wave_time[5] = {0.0, 0.85, 1.016, 0.99, 1.0};
+                const long long P = std::max(1, P_per_traj_hint);
+                double best = 1e300;
+                for (int c = MMAR2_MAXF; c >= 1; --c) {
+                    const size_t smem_c = 16 + matb * m->S + fbytes * c;
+                    const int per_sm = std::max<int>(1, std::min<int>(static_cast<int>((228 * 1024) / (smem_c + 1024)), MMAR2_MAXF / c));
+                    const long long n_cta = (P + c - 1) / c, slots = static_cast<long long>(m->n_sm) * per_sm;
+                    const double cost = static_cast<double>((n_cta + slots - 1) / slots) * wave_time[c];
+                    if (cost < best - 1e-9) { best = cost; f = c; }
+                }
+            }
+            f = std::max(1, std::min(f, MMAR2_MAXF));
+            pl.mmar2 = true;
+            pl.tile = false;
+            pl.FPC = f;
+            pl.WPC = f;
+            pl.threads = 64 * f;
+            pl.smem = 16 + matb * m->S + fbytes * f;
+            pl.fstride = m->fstride_r;
+            pl.bstride = static_cast<int>(matb / 8);
+            return pl;
+        }
         if (m->mma_ok && m->GT >= 5 && m->GT <= 7 && !(force0 && (!strcmp(force0, "tile") || !strcmp(force0, "mma1") || !strcmp(force0, "mmag"))) &&
             !env_int("BILDK_FORCE_GENERIC", 0) && m->GT < env_int("BILDK_MMAC_MIN_GT", 8)) {
             const size_t matb = static_cast<size_t>(m->NPm) * m->LDBm * 8;
@@ -976,6 +1028,9 @@ static std::string plan_string(const bildk_model* m, const Plan& pl) {
         snprintf(buf, sizeof buf, "%s (DMMA m8n8k4) GT=%d %s cta-per-filter %s%s B=%s threads=%d smem=%zu", pl.mmact ? "mmact" : "mmac", m->GT,
                  m->mma_mx ? "mean-in-extra-tile" : "mean-in-padding", pl.mmact ? "tile-slots-per-warp" : "warp-per-tile-column",
                  pl.nhelp ? " +3-P1-helper-warps" : "", pl.b_all ? "all" : "one", pl.threads, pl.smem);
+    else if (pl.mmar2)
+        snprintf(buf, sizeof buf, "mmar2 (DMMA m8n8k4) GT=%d register-chained two-warps-per-filter (tile rows split) FPC=%d threads=%d smem=%zu", m->GT,
+                 pl.FPC, pl.threads, pl.smem);
     else if (pl.mmar)
         snprintf(buf, sizeof buf, "mmar (DMMA m8n8k4) GT=%d register-chained warp-per-filter WPC=%d CTAs/SM=%d threads=%d smem=%zu", m->GT,
                  pl.WPC, pl.nb, pl.threads, pl.smem);
@@ -1043,7 +1098,7 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
         if (rc) return rc;
         d_part = m->part.p;
     }
-    if (pl.mma || pl.mmar || pl.mma2 || pl.mmac || pl.mmag || pl.tile) {
+    if (pl.mma || pl.mmar || pl.mmar2 || pl.mma2 || pl.mmac || pl.mmag || pl.tile) {
         KParams kp{};
         kp.N = m->N; kp.D = m->D; kp.S = m->S; kp.G = m->G; kp.LD = m->LD; kp.NP = m->NP;
         kp.Bpad = m->dBpad; kp.Sigpad = m->dSigpad; kp.C0pad = m->dC0pad; kp.Gm = m->dG; kp.M0 = m->dM0; kp.w = m->dw;
@@ -1117,6 +1172,16 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
             rp.ww00 = m->wz_val[0] * m->wz_val[0]; rp.ww11 = m->wz_val[1] * m->wz_val[1]; rp.ww01 = 2.0 * m->wz_val[0] * m->wz_val[1];
             for (int e = 0; e < dstar; ++e) mmar_tables(m->GT, m->r_last, t0->ncols[e], rp.lastrow[e], rp.mrow[e]);
             CU(mmar_launch_for(m->GT, pl.nb, rp, grid, pl.threads, pl.smem, st));
+        } else if (pl.mmar2) {
+            R2Params r2{};
+            RParams& rp = r2.r;
+            rp.k = kp;
+            rp.Br = m->dBr; rp.Sigm = m->dSigm; rp.C0m = m->dC0m;
+            rp.WPC = pl.FPC; rp.fstride = pl.fstride; rp.r = m->r_last;
+            rp.ww00 = m->wz_val[0] * m->wz_val[0]; rp.ww11 = m->wz_val[1] * m->wz_val[1]; rp.ww01 = 2.0 * m->wz_val[0] * m->wz_val[1];
+            for (int e = 0; e < dstar; ++e) mmar_tables(m->GT, m->r_last, t0->ncols[e], rp.lastrow[e], rp.mrow[e]);
+            r2.FPC2 = pl.FPC;
+            CU(mmar2_launch_for(m->GT, r2, grid, pl.threads, pl.smem, st));
         } else if (pl.mma2) {
             M2Params m2{};
             MParams& mp = m2.m;

@@ -1,0 +1,356 @@
+// k_mmar2 - the register-chained FP64 tensor-core filter (k_mmar) for 33 <= N <= 56, TWO WARPS PER FILTER
+// (5 <= GT <= 7 with N mod 8 in 1..4: the north-star shape N = 50 is GT = 7, r = 2).
+//
+// Why: ncu of k_mma2<7> on the N = 50 target (profiles/r02_ncu_n50.txt, source view) shows the tensor pipe 79 % busy
+// and each warp away from it 40-55 % of its time: k_mma2 splits the work of a frame by tile COLUMNS - P1 (T = B C, in
+// place in shared memory) 28 : 21 tiles, a pair barrier, P2 (C' = T B) 10 : 18 tiles, a pair barrier, update, a pair
+// barrier - so each warp waits ~20 % of the frame for its partner at the barrier in the middle, T makes a round trip
+// through shared memory, and the three warps per scheduler cannot cover each other.
+//
+// Here the pair splits the frame by tile ROWS, as k_mmar does inside one warp: row block ti of T = B_s [C | M] is
+// produced in registers (GT tiles) and consumed on the spot by the upper tiles of row ti of C' = T B_s + Sig.  Rows are
+// independent, so there is NO barrier between the two products; the rows are dealt out so that the DMMA counts match
+// (GT = 7: rows {0,1,2} = 39 tile products, rows {3,4,5,6} = 38).  Per frame: two pair barriers (everybody done reading
+// C / published columns visible; C+ complete), no T traffic.  Fragment layout, the permuted last tile column (even slots
+// = covariance columns, odd slots = mean columns), the swizzle and the update are those of k_mmar (bildk_mmar.cuh).
+#pragma once
+#include "bildk_mmar.cuh"
+
+namespace bildk {
+
+struct R2Params {
+    RParams r;
+    int FPC2;   // filters per CTA (two warps each)
+};
+
+template <int GT>
+struct Mmar2Rows {
+    // role (0 / 1) that owns tile-row block ti; cost of a row = GT (P1) + GT - ti (P2) tile products
+    __host__ __device__ static constexpr int role(int ti) {
+        return GT == 7 ? (ti <= 2 ? 0 : 1)                       // 14+13+12 = 39 | 11+10+9+8 = 38
+             : GT == 6 ? ((ti == 0 || ti == 3 || ti == 5) ? 0 : 1)   // 12+9+7 = 28 | 11+10+8 = 29
+             : (ti <= 1 ? 0 : 1);                                // GT = 5: 10+9 = 19 | 8+7+6 = 21
+    }
+    __host__ __device__ static constexpr int nacc(int r) {          // upper tiles owned by role r
+        int n = 0;
+        for (int ti = 0; ti < GT; ++ti) if (role(ti) == r) n += GT - ti;
+        return n;
+    }
+    __host__ __device__ static constexpr int nrows(int r) {
+        int n = 0;
+        for (int ti = 0; ti < GT; ++ti) if (role(ti) == r) ++n;
+        return n;
+    }
+    __host__ __device__ static constexpr int first(int r) {          // lowest row of role r
+        for (int ti = 0; ti < GT; ++ti) if (role(ti) == r) return ti;
+        return GT;
+    }
+    __host__ __device__ static constexpr int aidx(int ti, int tj) {  // accumulator slot of upper tile (ti, tj) within its owner
+        int n = 0;
+        for (int t = 0; t < ti; ++t) if (role(t) == role(ti)) n += GT - t;
+        return n + tj - ti;
+    }
+    __host__ __device__ static constexpr int ridx(int ti) {          // slot of row ti within its owner (mu, kr)
+        int n = 0;
+        for (int t = 0; t < ti; ++t) if (role(t) == role(ti)) ++n;
+        return n;
+    }
+};
+
+template <int GT, int ROLE>
+__device__ __forceinline__ void mmar2_run(const RParams& rp, const double* __restrict__ Bsm, double* __restrict__ Cb, int pidx, int tjx,
+                                          int e_sub, int barid, int lane) {
+    using G = MmarGeom<GT>;
+    using RW = Mmar2Rows<GT>;
+    constexpr int R = G::R, LD = G::LD, MAT = G::MAT;
+    constexpr int KT = GT - 1;
+    constexpr int NACC = RW::nacc(ROLE), NROW = RW::nrows(ROLE);
+    constexpr bool OWN_FIRST = RW::role(0) == ROLE, OWN_LAST = RW::role(GT - 1) == ROLE;
+    constexpr int FIRSTROW = RW::first(ROLE);
+#define MINE(ti) (RW::role(ti) == ROLE)
+#define AIDX(ti, tjj) (RW::aidx(ti, tjj))
+#define RIDX(ti) (RW::ridx(ti))
+    const KParams& p = rp.k;
+    const int g = lane >> 2, c4 = lane & 3;
+    const int N = p.N, D = p.D;
+    double* const colb = Cb + MAT;              // [2][R] the two columns of C' that w touches
+    double* const mpub = colb + 2 * R;          // [2][4] prior mean rows 0 and N - 1
+
+    const int T = p.T[tjx];
+    const double* __restrict__ xg = p.x[tjx];
+    const uint32_t* __restrict__ vbits = reinterpret_cast<const uint32_t*>(p.valid[tjx] + (T + 3) / 4 * 4);
+    uint32_t vword = 0;
+    const int ncols = p.ncols[e_sub];
+    const double s2 = p.s2[e_sub];
+    const double w0 = p.wz_val[0], w1 = p.wz_val[1];
+    const int rr = rp.r;
+    const int cj1 = rr - 1;                     // column N - 1 = 8 (GT - 1) + cj1
+    const bool e1 = cj1 & 1;
+
+    // lane-constant fragment offsets (doubles); rows 8 t + g flip column bit 2 when (g >> 1) & 1  (bildk_mmar.cuh)
+    const int fx = 4 * ((g >> 1) & 1);
+    const int offP = g * LD + ((2 * c4) ^ fx);
+    const int offS = g * LD + 8 * KT + c4 + fx;
+    const int lr = rp.lastrow[e_sub][g];
+    const int lx = 4 * ((lr >> 1) & 1);
+    const int offLP = lr * LD + ((2 * c4) ^ lx);
+    const int offLS = lr * LD + 8 * KT + c4 + lx;
+    const int offMir = 2 * c4 * LD + (g ^ (4 * (c4 & 1)));
+    const bool hasq = c4 < ncols;
+    const int mr = rp.mrow[e_sub][hasq ? c4 : 0];
+    const int offM = mr * LD + (g ^ (4 * ((mr >> 1) & 1)));
+    const int xcol = p.cols[e_sub][hasq ? c4 : 0];
+    const bool lastrow_ok = g < rr;
+    const bool mir0_ok = 2 * c4 < rr, mir1_ok = 2 * c4 + 1 < rr;
+
+    double quad = 0.0, lmant = 1.0;             // role 1 accumulates the log-likelihood
+    int lexp = 0;
+
+    int r_cur = 0;
+    int s = p.run_states[static_cast<size_t>(pidx) * p.K1];
+    int next_sw = (p.K1 > 1) ? p.run_starts[static_cast<size_t>(pidx) * p.K1 + 1] : 0x7fffffff;
+
+    double acc[NACC][2];
+    double mu[NROW];
+
+    for (int t = 0; t < T; ++t) {
+        while (t >= next_sw) {
+            ++r_cur;
+            s = p.run_states[static_cast<size_t>(pidx) * p.K1 + r_cur];
+            next_sw = (r_cur + 1 < p.K1) ? p.run_starts[static_cast<size_t>(pidx) * p.K1 + r_cur + 1] : 0x7fffffff;
+        }
+        if ((t & 31) == 0) vword = __ldg(vbits + (t >> 5));
+        const bool is_valid = (vword >> (t & 31)) & 1u;
+
+        if (t > 0) {
+            const double* __restrict__ Bs = Bsm + s * MAT;
+            const double* __restrict__ Gs = rp.Sigm + static_cast<size_t>(R * R) * s + g * R + 2 * c4;
+            // ---------------- P1, this warp's tile-row blocks: T[ti][:] = B_s[ti][:] [C | M]   (MSRouse_logL.pyx:206-241)
+            // k-tile outermost: the GT fragments of [C | M] of a k-tile are loaded once and serve all of this warp's rows
+            double Tt[NROW][GT][2];
+#pragma unroll
+            for (int r = 0; r < NROW; ++r)
+#pragma unroll
+                for (int tj = 0; tj < GT; ++tj) Tt[r][tj][0] = Tt[r][tj][1] = 0.0;
+#pragma unroll
+            for (int kt = 0; kt < KT; ++kt) {
+                double2 b[GT];
+#pragma unroll
+                for (int tj = 0; tj < GT; ++tj)
+                    b[tj] = *reinterpret_cast<const double2*>(tj < GT - 1 ? Cb + offP + 8 * tj * LD + 8 * kt : Cb + offLP + 8 * kt);
+#pragma unroll
+                for (int ti = 0; ti < GT; ++ti) {
+                    if (!MINE(ti)) continue;
+                    const double2 a = *reinterpret_cast<const double2*>(Bs + offP + 8 * ti * LD + 8 * kt);
+#pragma unroll
+                    for (int tj = 0; tj < GT; ++tj) dmma884(Tt[RIDX(ti)][tj], a.x, b[tj].x);
+#pragma unroll
+                    for (int tj = 0; tj < GT; ++tj) dmma884(Tt[RIDX(ti)][tj], a.y, b[tj].y);
+                }
+            }
+            {
+                double b[GT];
+#pragma unroll
+                for (int tj = 0; tj < GT; ++tj) b[tj] = tj < GT - 1 ? Cb[offS + 8 * tj * LD] : Cb[offLS];
+#pragma unroll
+                for (int ti = 0; ti < GT; ++ti) {
+                    if (!MINE(ti)) continue;
+                    const double a = Bs[offS + 8 * ti * LD];
+#pragma unroll
+                    for (int tj = 0; tj < GT; ++tj) dmma884(Tt[RIDX(ti)][tj], a, b[tj]);
+                }
+            }
+            // ---------------- P2, upper tiles of this warp's rows: C'[ti][tj] = Sig + T[ti][:] B_s[:][tj]; again k-tile outermost
+#pragma unroll
+            for (int ti = 0; ti < GT; ++ti) {
+                if (!MINE(ti)) continue;
+                mu[RIDX(ti)] = Tt[RIDX(ti)][GT - 1][1];   // M'[8 ti + g][c4]
+#pragma unroll
+                for (int tj = ti; tj < GT; ++tj) {
+                    const double2 v = __ldg(reinterpret_cast<const double2*>(Gs + 8 * ti * R + 8 * tj));
+                    acc[AIDX(ti, tj)][0] = v.x;
+                    acc[AIDX(ti, tj)][1] = v.y;
+                }
+            }
+#pragma unroll
+            for (int kt = 0; kt < KT; ++kt) {
+                double2 b[GT];
+#pragma unroll
+                for (int tj = FIRSTROW; tj < GT; ++tj) b[tj] = *reinterpret_cast<const double2*>(Bs + offP + 8 * tj * LD + 8 * kt);
+#pragma unroll
+                for (int ti = 0; ti < GT; ++ti) {
+                    if (!MINE(ti)) continue;
+#pragma unroll
+                    for (int tj = ti; tj < GT; ++tj) dmma884(acc[AIDX(ti, tj)], Tt[RIDX(ti)][kt][0], b[tj].x);
+#pragma unroll
+                    for (int tj = ti; tj < GT; ++tj) dmma884(acc[AIDX(ti, tj)], Tt[RIDX(ti)][kt][1], b[tj].y);
+                }
+            }
+            {
+                double b[GT];
+#pragma unroll
+                for (int tj = FIRSTROW; tj < GT; ++tj) b[tj] = Bs[offS + 8 * tj * LD];
+#pragma unroll
+                for (int ti = 0; ti < GT; ++ti) {
+                    if (!MINE(ti)) continue;
+#pragma unroll
+                    for (int tj = ti; tj < GT; ++tj) dmma884(acc[AIDX(ti, tj)], Tt[RIDX(ti)][GT - 1][0], b[tj]);
+                }
+            }
+            if (p.hasG) {   // M' = B M + G  (pyx:209-214)
+#pragma unroll
+                for (int ti = 0; ti < GT; ++ti)
+                    if (MINE(ti) && hasq && 8 * ti + g < N) mu[RIDX(ti)] += __ldg(p.Gm + (s * N + 8 * ti + g) * D + xcol);
+            }
+        } else {
+            // frame 0: steady state of the first state (pyx:160-163), no propagation
+            const double* __restrict__ Gs = rp.C0m + static_cast<size_t>(R * R) * s + g * R + 2 * c4;
+#pragma unroll
+            for (int ti = 0; ti < GT; ++ti) {
+                if (!MINE(ti)) continue;
+#pragma unroll
+                for (int tj = ti; tj < GT; ++tj) {
+                    const double2 v = __ldg(reinterpret_cast<const double2*>(Gs + 8 * ti * R + 8 * tj));
+                    acc[AIDX(ti, tj)][0] = v.x;
+                    acc[AIDX(ti, tj)][1] = v.y;
+                }
+                mu[RIDX(ti)] = (hasq && 8 * ti + g < N) ? __ldg(p.M0 + (s * N + 8 * ti + g) * D + xcol) : 0.0;
+            }
+        }
+
+        double x = 0.0;
+        if (is_valid) {
+            if (hasq) x = __ldg(xg + t * D + xcol);
+            // publish the two columns of C' that w touches (bildk_mmar.cuh): column 0 comes from tile row 0 alone (its owner
+            // publishes it), column N - 1 from the last tile of every row (each warp publishes its rows)
+            if (OWN_FIRST) {
+                if (c4 == 0) colb[g] = acc[AIDX(0, 0)][0];
+                if (g == 0) {
+#pragma unroll
+                    for (int ti = 1; ti < GT; ++ti)
+                        *reinterpret_cast<double2*>(colb + 8 * ti + 2 * c4) = make_double2(acc[AIDX(0, ti)][0], acc[AIDX(0, ti)][1]);
+                    mpub[c4] = mu[RIDX(0)];
+                }
+            }
+            if (c4 == (cj1 >> 1)) {
+#pragma unroll
+                for (int ti = 0; ti < GT; ++ti)
+                    if (MINE(ti)) colb[R + 8 * ti + g] = e1 ? acc[AIDX(ti, GT - 1)][1] : acc[AIDX(ti, GT - 1)][0];
+            }
+            if (OWN_LAST && g == cj1) mpub[4 + c4] = mu[RIDX(GT - 1)];
+        }
+        pair_sync(barid);   // both warps are done reading C / M^T; published columns and mean rows visible
+
+        if (is_valid) {
+            // S = s2 + w^T C' w from the 2x2 block of C' at (0, N-1) (pyx:55-63)
+            const double Sinv = rcp3(fma(rp.ww11, colb[R + 8 * (GT - 1) + cj1], fma(rp.ww00, colb[0], s2)) + rp.ww01 * colb[R]);
+            double kr[NROW];
+#pragma unroll
+            for (int ti = 0; ti < GT; ++ti)
+                if (MINE(ti)) kr[RIDX(ti)] = fma(w1, colb[R + 8 * ti + g], w0 * colb[8 * ti + g]) * Sinv;   // K = C' w / S (pyx:66-67)
+#pragma unroll
+            for (int tjj = 0; tjj < GT; ++tjj) {
+                bool any = false;
+#pragma unroll
+                for (int ti = 0; ti <= tjj; ++ti) any |= MINE(ti);
+                if (!any) continue;
+                const double2 u = *reinterpret_cast<const double2*>(colb + 8 * tjj + 2 * c4);
+                const double2 v = *reinterpret_cast<const double2*>(colb + R + 8 * tjj + 2 * c4);
+                const double c0v = fma(w1, v.x, w0 * u.x), c1v = fma(w1, v.y, w0 * u.y);   // (C' w)[column pair]
+#pragma unroll
+                for (int ti = 0; ti <= tjj; ++ti) {
+                    if (!MINE(ti)) continue;
+                    acc[AIDX(ti, tjj)][0] = fma(-kr[RIDX(ti)], c0v, acc[AIDX(ti, tjj)][0]);   // pyx:71-75
+                    acc[AIDX(ti, tjj)][1] = fma(-kr[RIDX(ti)], c1v, acc[AIDX(ti, tjj)][1]);
+                }
+            }
+            // innovation (pyx:79) and mean update (pyx:82-85) of this lane's dimension
+            const double xm = x - fma(w1, mpub[4 + c4], w0 * mpub[c4]);
+#pragma unroll
+            for (int ti = 0; ti < GT; ++ti)
+                if (MINE(ti)) mu[RIDX(ti)] = fma(kr[RIDX(ti)], xm, mu[RIDX(ti)]);
+            if (ROLE == 1) {
+                quad = fma(xm * xm, Sinv, quad);
+                lmant *= Sinv;   // running product of Sinv with the exponent split off
+                const int ex = ((__double2hiint(lmant) >> 20) & 0x7ff) - 1023;
+                lmant = __hiloint2double(__double2hiint(lmant) - (ex << 20), __double2loint(lmant));
+                lexp += ex;
+            }
+        }
+        // ---------------- C+ and M+^T become the operands of the next propagation
+        if (t + 1 < T) {
+#pragma unroll
+            for (int ti = 0; ti < GT; ++ti) {
+                if (!MINE(ti)) continue;
+#pragma unroll
+                for (int tj = ti; tj < GT; ++tj) {
+                    const double v0 = acc[AIDX(ti, tj)][0], v1 = acc[AIDX(ti, tj)][1];
+                    if (tj > ti) {   // C[8 tj + 2 c4 + e][8 ti + g] = C[8 ti + g][8 tj + 2 c4 + e]
+                        if (tj < GT - 1 || mir0_ok) Cb[offMir + (8 * tj) * LD + 8 * ti] = v0;
+                        if (tj < GT - 1 || mir1_ok) Cb[offMir + (8 * tj + 1) * LD + 8 * ti] = v1;
+                    }
+                    if (ti < GT - 1 || lastrow_ok) *reinterpret_cast<double2*>(Cb + offP + 8 * ti * LD + 8 * tj) = make_double2(v0, v1);
+                }
+                if (hasq) Cb[offM + 8 * ti] = mu[RIDX(ti)];
+            }
+        }
+        pair_sync(barid);   // C+ / M+^T complete before the next frame's fragment loads
+    }
+
+    if (ROLE == 1) {
+        // logL = -1/2 [ sum xmm^2 Sinv - ncols * sum_t log Sinv_t + nvalid * ncols * log 2 pi ]   (pyx:88, 251-256)
+        quad += __shfl_xor_sync(0xffffffffu, quad, 1);
+        quad += __shfl_xor_sync(0xffffffffu, quad, 2);
+        if (lane == 0) {
+            int nvalid = 0;
+            for (int wv = 0; wv < (T + 31) / 32; ++wv) nvalid += __popc(__ldg(vbits + wv));
+            const double logdet = log(lmant) + lexp * 0.6931471805599453;
+            p.out[static_cast<size_t>(e_sub) * p.P + pidx] = -0.5 * (quad - ncols * logdet + static_cast<double>(nvalid) * ncols * LOG_2PI);
+        }
+    }
+#undef MINE
+#undef AIDX
+#undef RIDX
+}
+
+// MAXF: filters per CTA the kernel is compiled for (registers per thread = 65536 / (64 MAXF)).
+template <int GT, int MAXF>
+__global__ void __launch_bounds__(64 * MAXF, 1) k_mmar2(const __grid_constant__ R2Params rp2) {
+    constexpr int MAT = MmarGeom<GT>::MAT;
+    const RParams& rp = rp2.r;
+    const KParams& p = rp.k;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
+    double* Bsm = reinterpret_cast<double*>(smem_raw + 16);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int fl = wid >> 1;                          // filter within the CTA
+    const int role = (wid & 1) ^ ((fl >> 1) & 1);     // roles alternate so that every scheduler holds warps of either role
+    const int tjx = p.cta_traj ? p.cta_traj[blockIdx.x] : 0;
+    const int first = p.cta_first ? p.cta_first[blockIdx.x] : blockIdx.x * rp2.FPC2;
+    const int pend = p.traj_first[tjx + 1];
+    const int pidx = first + fl;
+    const bool alive = (fl < rp2.FPC2) && (pidx < pend);
+
+    if (tid == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(mbar, static_cast<uint32_t>(MAT * p.S * sizeof(double)));
+        for (int st = 0; st < p.S; ++st) {
+            constexpr uint32_t CH = 32768;
+            constexpr uint32_t bytes = MAT * sizeof(double);
+            for (uint32_t off = 0; off < bytes; off += CH)
+                tma_load_1d(reinterpret_cast<char*>(Bsm + st * MAT) + off, reinterpret_cast<const char*>(rp.Br + static_cast<size_t>(MAT) * st) + off,
+                            bytes - off < CH ? bytes - off : CH, mbar);
+        }
+    }
+    if (!alive) return;   // both warps of a pair leave together; the named barriers below are per pair
+    double* Cb = Bsm + MAT * p.S + fl * rp.fstride;
+    // padding columns, zero rows and M^T rows must start finite / zero: the pair clears its filter's buffer
+    for (int i = (wid & 1) * 32 + lane; i < rp.fstride; i += 64) Cb[i] = 0.0;
+    pair_sync(1 + fl);
+    mbar_wait(mbar, 0);
+    if (role == 0) mmar2_run<GT, 0>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, 1 + fl, lane);
+    else mmar2_run<GT, 1>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, 1 + fl, lane);
+}
+
+}  // namespace bildk

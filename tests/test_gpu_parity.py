@@ -146,6 +146,47 @@ def test_register_chained_kernel(N, d, noise, loops, nb, monkeypatch):
     assert rel_err(eng.logl_st(traj, ss, thetas), got) < 1e-12
 
 
+MMAR2_CASES = [
+    # N, d, noise, loops                      register-chained kernel with two warps per filter: GT 5..7, N mod 8 in 1..4
+    (33, 3, 0.3, (None, [(0, -1)])),          # GT=5, r=1
+    (36, 2, [0.1, 0.4], (None, [(0, -1)])),   # GT=5, r=4, d*=2
+    (41, 1, 0.3, (None, [(0, -1)])),          # GT=6, r=1, d=1 (rows dealt out 0,3,5 | 1,2,4)
+    (44, 4, 0.4, (None, [(0, -1)])),          # GT=6, r=4, d=4: every spare row carries a mean column
+    (49, 3, 0.3, (None, [(0, -1)])),          # GT=7, r=1
+    (50, 3, 0.3, (None, [(0, -1)], [(5, 30), (12, 44, 0.5)])),   # GT=7, r=2 (north-star N=50), 3 states
+    (50, 3, [0.2, 0.2, 0.5], (None, [(0, -1)])),                 # ... anisotropic error: sub-filters with 2 and 1 columns
+    (51, 3, 0.3, (None, [(0, -1)])),          # GT=7, r=3
+    (52, 3, 0.3, (None, [(0, -1)])),          # GT=7, r=4
+]
+
+
+@pytest.mark.parametrize("fpc", [0, 1, 3], ids=["default", "one-pair-per-cta", "three-pairs"])
+@pytest.mark.parametrize("N,d,noise,loops", MMAR2_CASES)
+def test_register_chained_two_warp_kernel(N, d, noise, loops, fpc, monkeypatch):
+    """k_mmar2 (tile rows of a filter split over a warp pair, T chained through registers) vs the C oracle and vs k_mma2
+    (tile columns split, T through shared memory) on the same inputs."""
+    rng = np.random.default_rng(177 + N)
+    mod = oracle_model(N, d=d, loops=loops)
+    T, P = 45, 23
+    x, _ = synth_traj(mod, T, rng, noise, p_nan=0.15)
+    x[0] = np.nan if N % 2 else x[0]                     # odd N: first frame missing
+    ss, thetas = random_profiles(rng, P, T, len(loops), 6)
+    err = np.broadcast_to(np.asarray(noise, dtype=float), (d,))
+    s2, Cind = ko.noise_to_s2_cind(err)
+    states = np.array([ko.st2states(s, th, T) for s, th in zip(ss, thetas)])
+    want = ko.logl_c(*(mod[k] for k in MODEL_KEYS), x, s2, Cind, states)
+    eng = engine_for(mod)
+    traj = eng.trajectory(x, err)
+    if fpc:
+        monkeypatch.setenv("BILDK_FPC2", str(fpc))
+    assert traj.describe_plan(P).split()[0] == "mmar2"
+    got = eng.logl_st(traj, ss, thetas)
+    assert rel_err(got, want) < TOL
+    monkeypatch.setenv("BILDK_MMAR2", "0")               # the column-split kernel on the same inputs
+    assert traj.describe_plan(P).split()[0] == "mma2"
+    assert rel_err(eng.logl_st(traj, ss, thetas), got) < 1e-12
+
+
 @pytest.mark.parametrize("N,nz", [
     (20, {3: -1.0, 14: 1.0}),            # two interior monomers (k_mma)
     (20, {7: 0.5, 8: -2.0}),             # neighbours in one tile, unequal weights
