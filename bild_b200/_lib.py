@@ -46,6 +46,7 @@ SYMBOLS = {
     "bildk_logl_runs_multi_submit": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), c_int32_p, ctypes.c_int, c_int32_p,
                                                      c_uint8_p, c_double_p, ctypes.POINTER(AmisReq), ctypes.POINTER(ctypes.c_void_p)]),
     "bildk_logl_wait": (ctypes.c_int, [ctypes.c_void_p]),
+    "bildk_logl_ready": (ctypes.c_int, [ctypes.c_void_p]),
     "bildk_amis_weights": (ctypes.c_int, [ctypes.c_int, c_double_p, c_double_p, c_double_p, ctypes.c_double, c_double_p,
                                            c_double_p, ctypes.c_int]),
     "bildk_marginal_posterior": (ctypes.c_int, [ctypes.c_int] * 4 + [c_int32_p, c_uint8_p, c_double_p, c_double_p, ctypes.c_int]),

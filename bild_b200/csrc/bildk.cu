@@ -147,8 +147,10 @@ struct bildk_model {
         size_t off_out = 0;
         int P = 0;
         bool busy = false;
+        cudaStream_t st = nullptr;         // stream of the batch in flight (the model's, or this slot's own)
     } slots[2];
     cudaStream_t st = nullptr;
+    cudaStream_t st2 = nullptr;            // second stream: batches in different slots overlap on the device when they share no scratch
 };
 
 struct bildk_traj {
@@ -247,6 +249,7 @@ extern "C" int bildk_model_destroy(bildk_model_t m) {
         if (sl.done) cudaEventDestroy(sl.done);
     }
     if (m->st) cudaStreamDestroy(m->st);
+    if (m->st2) cudaStreamDestroy(m->st2);
     delete m;
     return BILDK_OK;
 }
@@ -278,6 +281,7 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
     CU(cudaDeviceGetAttribute(&m->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CU(cudaDeviceGetAttribute(&m->n_sm, cudaDevAttrMultiProcessorCount, device));
     CU(cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&m->st2, cudaStreamNonBlocking));
     for (auto& sl : m->slots) {
         sl.owner = m;
         CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
@@ -385,7 +389,7 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
                                 B[s * NN + static_cast<size_t>(std::max(i, j)) * N + std::min(i, j)];
                 if ((rc = upload(&m->dBr, pad.data(), S * matr))) return rc;
                 m->r_last = rl; m->LDr = LDr;
-                m->fstride_r = static_cast<int>(matr) + 2 * R + 8;
+                m->fstride_r = static_cast<int>(matr) + 2 * R + 8 + (GT >= 5 ? 2 * R : 0);   // k_mmar2: one C' w vector per warp
                 const bool fits = 16 + matr * 8 * S + static_cast<size_t>(m->fstride_r) * 8 * 4 <= static_cast<size_t>(m->max_smem_optin);
                 m->mmar_ok = fits && GT <= 4;
                 m->mmar2_ok = fits && GT >= 5;
@@ -1596,6 +1600,16 @@ extern "C" int bildk_logl_wait(void* ticket) {
     return rc;
 }
 
+extern "C" int bildk_logl_ready(void* ticket) {
+    if (!ticket) return 1;                             // an empty batch is always done
+    bildk_model::Slot* sl = static_cast<bildk_model::Slot*>(ticket);
+    if (!sl->busy) return fail(BILDK_EINVAL, "ticket is not in flight");
+    cudaError_t e = cudaEventQuery(sl->done);
+    if (e == cudaSuccess) return 1;
+    if (e == cudaErrorNotReady) return 0;
+    return fail(BILDK_ECUDA, "kernel or copy-back failed: %s", cudaGetErrorString(e));
+}
+
 extern "C" int bildk_logl_runs_multi_submit(int n_traj, const bildk_traj_t* trajs, const int32_t* offsets, int K1,
                                             const int32_t* starts, const uint8_t* states, double* out,
                                             const bildk_amis_req* amis, void** ticket) {
@@ -1689,7 +1703,16 @@ extern "C" int bildk_logl_runs_multi_submit(int n_traj, const bildk_traj_t* traj
     const uint8_t** hv = reinterpret_cast<const uint8_t**>(sl->pin + o_v);
     for (int i = 0; i < n_traj; ++i) { hT[i] = trajs[i]->T; hx[i] = trajs[i]->dx; hv[i] = trajs[i]->dvalid; }
     for (int i = 0; i <= n_traj; ++i) hfirst[i] = hf[i];
-    cudaStream_t st = m->st;
+    // Two batches in flight run CONCURRENTLY on the device (one stream per slot) when they share no per-model scratch:
+    // d* = 1 (no partial-logL buffer) and a kernel that keeps its filter state on chip (no L2 workspace).  Otherwise
+    // both slots use the model's stream and the second batch queues behind the first.
+    bool own_stream = trajs[0]->dstar == 1 && sl == &m->slots[1];
+    if (own_stream) {
+        const Plan pl = make_plan(m, P / n_traj);
+        own_stream = pl.mma || pl.mmar || pl.mmar2 || pl.mma2 || pl.mmac || pl.tile;
+    }
+    cudaStream_t st = own_stream ? m->st2 : m->st;
+    sl->st = st;
     // ---- fused AMIS bookkeeping: every trajectory's step consumes its likelihoods straight from the kernel's output,
     //      in stream order behind the filter kernel - no host round trip, no extra synchronisation
     sl->amis.clear();

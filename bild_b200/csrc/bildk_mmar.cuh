@@ -261,21 +261,24 @@ __global__ void __launch_bounds__(128, NB) k_mmar(const __grid_constant__ RParam
         __syncwarp();   // every lane is done reading C / M^T (P1); published columns and mean rows visible
 
         if (is_valid) {
-            // S = s2 + w^T C' w from the 2x2 block of C' at (0, N-1) (pyx:55-63); three parallel terms, then 1/S
-            const double Sinv = rcp3(fma(rp.ww11, colb[R + 8 * (GT - 1) + cj1], fma(rp.ww00, colb[0], s2)) + rp.ww01 * colb[R]);
+            // C' w once per row instead of once per use: lane i < R combines the two published columns in place
+            // (colb[i] <- w0 C'[i][0] + w1 C'[i][N-1]); every later use - the gain, the column pairs of the rank-1 update, S -
+            // reads the finished vector.  Scalar FP64 instructions queue behind the other warps' DMMAs in the one FP64 pipe
+            // (ncu: 50 of them cost 30 % of the warp time of k_mmar<3>), so their NUMBER is what matters: 50 -> 31 per frame.
+            if (lane < R) colb[lane] = fma(w1, colb[R + lane], w0 * colb[lane]);
+            __syncwarp();
+            // S = s2 + w^T C' w = s2 + w0 (C' w)[0] + w1 (C' w)[N-1]  (pyx:55-63), then 1/S
+            const double Sinv = rcp3(fma(w1, colb[8 * (GT - 1) + cj1], fma(w0, colb[0], s2)));
             double kr[GT];
 #pragma unroll
-            for (int ti = 0; ti < GT; ++ti)
-                kr[ti] = fma(w1, colb[R + 8 * ti + g], w0 * colb[8 * ti + g]) * Sinv;   // K = C' w / S (pyx:66-67)
+            for (int ti = 0; ti < GT; ++ti) kr[ti] = colb[8 * ti + g] * Sinv;   // K = C' w / S (pyx:66-67)
 #pragma unroll
             for (int tjj = 0; tjj < GT; ++tjj) {
-                const double2 u = *reinterpret_cast<const double2*>(colb + 8 * tjj + 2 * c4);
-                const double2 v = *reinterpret_cast<const double2*>(colb + R + 8 * tjj + 2 * c4);
-                const double c0v = fma(w1, v.x, w0 * u.x), c1v = fma(w1, v.y, w0 * u.y);   // (C' w)[column pair]
+                const double2 cw = *reinterpret_cast<const double2*>(colb + 8 * tjj + 2 * c4);   // (C' w)[column pair]
 #pragma unroll
                 for (int ti = 0; ti <= tjj; ++ti) {
-                    acc[UIDX(ti, tjj)][0] = fma(-kr[ti], c0v, acc[UIDX(ti, tjj)][0]);   // pyx:71-75
-                    acc[UIDX(ti, tjj)][1] = fma(-kr[ti], c1v, acc[UIDX(ti, tjj)][1]);
+                    acc[UIDX(ti, tjj)][0] = fma(-kr[ti], cw.x, acc[UIDX(ti, tjj)][0]);   // pyx:71-75
+                    acc[UIDX(ti, tjj)][1] = fma(-kr[ti], cw.y, acc[UIDX(ti, tjj)][1]);
                 }
             }
             // innovation (pyx:79) and mean update (pyx:82-85) of this lane's dimension

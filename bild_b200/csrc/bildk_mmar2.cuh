@@ -75,6 +75,7 @@ __device__ __forceinline__ void mmar2_run(const RParams& rp, const double* __res
     const int N = p.N, D = p.D;
     double* const colb = Cb + MAT;              // [2][R] the two columns of C' that w touches
     double* const mpub = colb + 2 * R;          // [2][4] prior mean rows 0 and N - 1
+    double* const cwb = mpub + 8 + ROLE * R;    // [R] this warp's copy of C' w
 
     const int T = p.T[tjx];
     const double* __restrict__ xg = p.x[tjx];
@@ -242,26 +243,25 @@ __device__ __forceinline__ void mmar2_run(const RParams& rp, const double* __res
         pair_sync(barid);   // both warps are done reading C / M^T; published columns and mean rows visible
 
         if (is_valid) {
-            // S = s2 + w^T C' w from the 2x2 block of C' at (0, N-1) (pyx:55-63)
-            const double Sinv = rcp3(fma(rp.ww11, colb[R + 8 * (GT - 1) + cj1], fma(rp.ww00, colb[0], s2)) + rp.ww01 * colb[R]);
+            // C' w once per row (bildk_mmar.cuh): each warp combines the two published columns into its own copy of the vector
+            // (a shared copy would need a third pair barrier), then reads gains and column pairs from it
+#pragma unroll
+            for (int i = lane; i < R; i += 32) cwb[i] = fma(w1, colb[R + i], w0 * colb[i]);
+            __syncwarp();
+            // S = s2 + w^T C' w = s2 + w0 (C' w)[0] + w1 (C' w)[N-1]  (pyx:55-63), then 1/S
+            const double Sinv = rcp3(fma(w1, cwb[8 * (GT - 1) + cj1], fma(w0, cwb[0], s2)));
             double kr[NROW];
 #pragma unroll
             for (int ti = 0; ti < GT; ++ti)
-                if (MINE(ti)) kr[RIDX(ti)] = fma(w1, colb[R + 8 * ti + g], w0 * colb[8 * ti + g]) * Sinv;   // K = C' w / S (pyx:66-67)
+                if (MINE(ti)) kr[RIDX(ti)] = cwb[8 * ti + g] * Sinv;   // K = C' w / S (pyx:66-67)
 #pragma unroll
-            for (int tjj = 0; tjj < GT; ++tjj) {
-                bool any = false;
-#pragma unroll
-                for (int ti = 0; ti <= tjj; ++ti) any |= MINE(ti);
-                if (!any) continue;
-                const double2 u = *reinterpret_cast<const double2*>(colb + 8 * tjj + 2 * c4);
-                const double2 v = *reinterpret_cast<const double2*>(colb + R + 8 * tjj + 2 * c4);
-                const double c0v = fma(w1, v.x, w0 * u.x), c1v = fma(w1, v.y, w0 * u.y);   // (C' w)[column pair]
+            for (int tjj = FIRSTROW; tjj < GT; ++tjj) {
+                const double2 cw = *reinterpret_cast<const double2*>(cwb + 8 * tjj + 2 * c4);   // (C' w)[column pair]
 #pragma unroll
                 for (int ti = 0; ti <= tjj; ++ti) {
                     if (!MINE(ti)) continue;
-                    acc[AIDX(ti, tjj)][0] = fma(-kr[RIDX(ti)], c0v, acc[AIDX(ti, tjj)][0]);   // pyx:71-75
-                    acc[AIDX(ti, tjj)][1] = fma(-kr[RIDX(ti)], c1v, acc[AIDX(ti, tjj)][1]);
+                    acc[AIDX(ti, tjj)][0] = fma(-kr[RIDX(ti)], cw.x, acc[AIDX(ti, tjj)][0]);   // pyx:71-75
+                    acc[AIDX(ti, tjj)][1] = fma(-kr[RIDX(ti)], cw.y, acc[AIDX(ti, tjj)][1]);
                 }
             }
             // innovation (pyx:79) and mean update (pyx:82-85) of this lane's dimension

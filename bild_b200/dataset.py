@@ -22,7 +22,16 @@ plane only) whenever one finishes.  The cost of a trajectory is data dependent (
 run of round 1, where the static partition left the slowest rank 1.8x behind the fastest); a result does not depend on
 the rank that computed it (private RNG stream per trajectory).
 
-Overlap: two groups of state machines take turns; the fused launch of one group is submitted asynchronously
+Scheduling (models that launch asynchronously): event driven, most-advanced trajectory first.  The state machines whose
+likelihoods have arrived wait in a priority queue ordered by the number of AMIS steps they have taken; the driver advances
+the first one (host code of ONE step), adds its request to the pending batch, and hands the pending batch to the library
+whenever one of its two slots is free (``bildk_logl_runs_multi_submit``; finished batches are noticed with the
+non-blocking ``bildk_logl_ready``).  The cost of a trajectory is data dependent with a heavy tail (20 to 950 AMIS steps in
+the 1024-trajectory run); in the round-based scheme below every trajectory advances one step per round of ALL active
+trajectories, so the longest one sets the wall time (8 GPUs: slowest rank 20.5 s, fastest 9.5 s).  Here a trajectory that
+has come far runs at the speed of its own critical path (host step + one launch) while the others fill the gaps.
+
+Round-based scheme (``schedule="rounds"``, and all synchronous models): two groups of state machines take turns; the fused launch of one group is submitted asynchronously
 (``bildk_logl_runs_multi_submit``: pinned staging, no stream synchronisation) and runs while the host code of the other
 group advances, in ONE thread.  (Round 1 tried this with a worker thread inside the GIL-free C call: the launch time
 was hidden but the lane threads lost as much to GIL hand-overs as was gained.)
@@ -49,6 +58,7 @@ class _Lane:
         self.answer = None
         self.result = None
         self.done = False
+        self.steps = 0                           # likelihood batches answered so far (scheduling priority)
         self.rng_state = None
 
     def advance(self, model, sample_kw):
@@ -87,7 +97,100 @@ def store_claimer(n_total, store=None, key="bild_b200/next_trajectory"):
     return claim
 
 
-def sample_many(trajs, model, seeds=None, rank=0, world=1, max_active=None, claim=None, fuse_amis=True, **sample_kw):
+def _pack(lanes, model, stats):
+    """Run-length arrays of the requests of `lanes` (one localisation error): (offsets, starts, states).  Profiles with
+    fewer runs are padded with empty runs (start = T), which vanish exactly like the empty slices of st2profile."""
+    K1 = max(ln.request[0].shape[1] for ln in lanes)
+    starts, states, offsets = [], [], [0]
+    for ln in lanes:
+        ss, thetas = ln.request
+        if thetas.size and (thetas.min() < 0 or thetas.max() >= model.nStates):
+            raise ValueError("state index out of range")
+        a, b = st_to_runs(ss, thetas, len(ln.traj))
+        if a.shape[1] < K1:
+            extra = K1 - a.shape[1]
+            a = np.concatenate([a, np.full((len(a), extra), len(ln.traj), dtype=a.dtype)], axis=1)
+            b = np.concatenate([b, np.repeat(b[:, -1:], extra, axis=1)], axis=1)
+        starts.append(a)
+        states.append(b)
+        offsets.append(offsets[-1] + len(a))
+        stats["frame_steps"] += len(a) * (len(ln.traj) - 1)
+    return offsets, np.concatenate(starts), np.concatenate(states)
+
+
+def _noise_key(model, traj):
+    return tuple(np.asarray(model._get_noise(traj), dtype=float).ravel())
+
+
+def _sample_many_priority(trajs, model, seeds, pending_lanes, claim, limit, fuse_amis, sample_kw, stats):
+    """Event-driven driver (module docstring): most-advanced state machine first, at most two batches in flight."""
+    import heapq
+    results = {}
+    more = claim is not None
+    n_active = 0
+    ready = []                  # heap of (-steps taken, trajectory index, lane): lanes whose answer has arrived / new lanes
+    waiting = []                # lanes with a request that has not been submitted yet
+    inflight = []               # (batch, lanes, offsets), oldest first; the library holds at most two
+    while True:
+        # ---- top up the set of running state machines (static list first, then the shared counter)
+        room = limit - n_active
+        if more and room > len(pending_lanes):
+            got = claim(room - len(pending_lanes))
+            pending_lanes.extend(_Lane(i, trajs[i], seeds[i]) for i in got)
+            more = bool(got)
+        while pending_lanes and n_active < limit:
+            ln = pending_lanes.pop(0)
+            ln.steps = 0
+            heapq.heappush(ready, (0, ln.idx, ln))
+            n_active += 1
+        if n_active == 0:
+            break
+        # ---- answers: take every finished batch; block only when there is nothing else to do
+        tic = time.perf_counter()
+        while inflight:
+            done = [i for i, item in enumerate(inflight) if item[0].ready()]      # the two slots may finish in either order
+            if not done and (ready or (waiting and len(inflight) < 2)):
+                break
+            batch, lanes, offsets = inflight.pop(done[0] if done else 0)
+            out = batch.wait()
+            for ln, lo, hi in zip(lanes, offsets[:-1], offsets[1:]):
+                ln.answer = out[lo:hi]
+                ln.request = None
+                heapq.heappush(ready, (-ln.steps, ln.idx, ln))
+        stats["t_gpu"] += time.perf_counter() - tic
+        # ---- host code of ONE step of the most advanced ready lane
+        if ready:
+            tic = time.perf_counter()
+            _, _, lane = heapq.heappop(ready)
+            lane.advance(model, sample_kw)
+            lane.steps += 1
+            stats["t_host_lanes"] += time.perf_counter() - tic
+            if lane.done:
+                results[lane.idx] = lane.result
+                n_active -= 1
+            else:
+                waiting.append(lane)
+        # ---- a free slot takes everything that is waiting (one localisation error per launch)
+        if waiting and len(inflight) < 2:
+            tic = time.perf_counter()
+            key = _noise_key(model, waiting[0].traj)
+            lanes = [ln for ln in waiting if _noise_key(model, ln.traj) == key] if model.localization_error is None else waiting
+            waiting = [ln for ln in waiting if ln not in lanes] if len(lanes) < len(waiting) else []
+            offsets, starts, states = _pack(lanes, model, stats)
+            stats["t_pack"] += time.perf_counter() - tic
+            tic = time.perf_counter()
+            batch = model.logL_runs_multi_submit([ln.traj for ln in lanes], offsets, starts, states,
+                                                 amis=[ln.amis for ln in lanes] if fuse_amis else None)
+            inflight.append((batch, lanes, offsets))
+            stats["t_gpu"] += time.perf_counter() - tic
+            stats["launches"] += 1
+            stats["rounds"] += 1
+            stats["profiles"] += offsets[-1]
+    return results
+
+
+def sample_many(trajs, model, seeds=None, rank=0, world=1, max_active=None, claim=None, fuse_amis=True, schedule="priority",
+                **sample_kw):
     """
     Run `sample` on every trajectory, fusing the likelihood batches of all concurrently active trajectories.
 
@@ -107,6 +210,9 @@ def sample_many(trajs, model, seeds=None, rank=0, world=1, max_active=None, clai
     fuse_amis : bool
         let every sampler's device bookkeeping (`bildk_amis_step`) ride on the fused likelihood launch, in stream order
         behind the filter kernel, instead of one synchronous call per sampler step (same arithmetic, same bits)
+    schedule : "priority" (default) or "rounds"
+        for models that launch asynchronously: event driven, most-advanced trajectory first - or the round-based scheme
+        of two alternating groups (module docstring); synchronous models always run in rounds
     **sample_kw : forwarded to `sample` (dE, init_runs, sampler_kw, ...)
 
     Returns
@@ -123,6 +229,11 @@ def sample_many(trajs, model, seeds=None, rank=0, world=1, max_active=None, clai
              "t_host_lanes": 0.0, "t_pack": 0.0, "t_gpu": 0.0}      # wall seconds: AMIS host code / run-length packing / fused launches
     pending = [_Lane(i, trajs[i], seeds[i]) for i in mine]
     limit = max_active or (len(pending) if claim is None else 64) or 1
+    if hasattr(model, "logL_runs_multi_submit") and schedule == "priority":
+        try:
+            return _sample_many_priority(trajs, model, seeds, pending, claim, limit, fuse_amis, sample_kw, stats), stats
+        finally:
+            np.random.set_state(outer_rng)
     results = {}
     more = claim is not None
     # Two groups of state machines take turns when the model can launch asynchronously (C ABI bildk_logl_runs_multi_submit /
@@ -173,26 +284,10 @@ def sample_many(trajs, model, seeds=None, rank=0, world=1, max_active=None, clai
             stats["rounds"] += 1
             by_noise = {}
             for ln in waiting:
-                key = tuple(np.asarray(model._get_noise(ln.traj), dtype=float).ravel())
-                by_noise.setdefault(key, []).append(ln)
+                by_noise.setdefault(_noise_key(model, ln.traj), []).append(ln)
             for lanes in by_noise.values():
                 tic = time.perf_counter()
-                K1 = max(ln.request[0].shape[1] for ln in lanes)
-                starts, states, offsets = [], [], [0]
-                for ln in lanes:
-                    ss, thetas = ln.request
-                    if thetas.size and (thetas.min() < 0 or thetas.max() >= model.nStates):
-                        raise ValueError("state index out of range")
-                    a, b = st_to_runs(ss, thetas, len(ln.traj))
-                    if a.shape[1] < K1:
-                        extra = K1 - a.shape[1]
-                        a = np.concatenate([a, np.full((len(a), extra), len(ln.traj), dtype=a.dtype)], axis=1)
-                        b = np.concatenate([b, np.repeat(b[:, -1:], extra, axis=1)], axis=1)
-                    starts.append(a)
-                    states.append(b)
-                    offsets.append(offsets[-1] + len(a))
-                    stats["frame_steps"] += len(a) * (len(ln.traj) - 1)
-                all_starts, all_states = np.concatenate(starts), np.concatenate(states)
+                offsets, all_starts, all_states = _pack(lanes, model, stats)
                 stats["t_pack"] += time.perf_counter() - tic
                 tic = time.perf_counter()
                 if n_groups > 1 and len(inflight[g]) == 0:

@@ -191,6 +191,15 @@ class PendingBatch:
     def __init__(self, ticket, out, keep):
         self._ticket, self._out, self._keep = ticket, out, keep      # `keep`: the handles must outlive the launch
 
+    def ready(self):
+        """True once `wait` will not block."""
+        if self._ticket is None or not self._ticket.value:
+            return True
+        rc = _lib.load().bildk_logl_ready(self._ticket)
+        if rc < 0:
+            _lib.check(rc)
+        return bool(rc)
+
     def wait(self):
         if self._ticket is not None:
             ticket, self._ticket = self._ticket, None

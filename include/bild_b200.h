@@ -142,6 +142,9 @@ int bildk_logl_runs_multi_submit(int n_traj, const bildk_traj_t *trajs, const in
                                  const int32_t *run_starts, const uint8_t *run_states, double *out,
                                  const bildk_amis_req *amis /* n_traj entries, or NULL */, void **ticket);
 int bildk_logl_wait(void *ticket);
+/* Non-blocking: 1 if the batch behind `ticket` has finished (bildk_logl_wait will not block), 0 if it is still running,
+ * < 0 on error.  The two batches a model may have in flight run concurrently on the device when they share no scratch. */
+int bildk_logl_ready(void *ticket);
 
 /*
  * AMIS weight normalisation (amis.py:843-845, 878-900), deterministic fixed-order reduction:

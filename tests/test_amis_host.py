@@ -422,6 +422,68 @@ def test_sample_many_equals_sequential_runs():
     assert all(np.array_equal(r2[i].evidence, res[i].evidence) for i in range(4))
 
 
+class _FinishedLater:
+    """Stand-in for a batch in flight: `ready()` turns true after a few polls (batches of the two slots finish in either order)."""
+
+    def __init__(self, out, polls):
+        self.out, self.polls = out, polls
+
+    def ready(self):
+        self.polls -= 1
+        return self.polls <= 0
+
+    def wait(self):
+        return self.out
+
+
+class AsyncOracleBackedRouse(OracleBackedRouse):
+    """`OracleBackedRouse` with the asynchronous launch interface of the engine (submit -> object with ready() / wait())."""
+    submits = 0
+
+    def __getattribute__(self, name):
+        if name in ("amis_weights", "marginal_posterior", "amis_ensemble"):
+            raise AttributeError(name)
+        return object.__getattribute__(self, name)
+
+    def logL_runs_multi_submit(self, trajs, offsets, starts, run_states, amis=None):
+        type(self).submits += 1
+        assert amis is None or all(a is None for a in amis)        # no device ensembles in the CPU suite
+        return _FinishedLater(self.logL_runs_multi(trajs, offsets, starts, run_states), 1 + (type(self).submits * 7) % 4)
+
+
+def test_priority_scheduler_equals_sequential_runs():
+    """The event-driven dataset driver (most-advanced trajectory first, two batches in flight, batches of whatever is
+    waiting) gives every trajectory the result of its own sequential run, whatever the batching and the completion order."""
+    from bild_b200.dataset import sample_many
+    model = AsyncOracleBackedRouse(8, 1, 5, d=2, localization_error=0.3)
+    np.random.seed(21)
+    trajs = [model.trajectory_from_loopingprofile(bild.Loopingprofile([0] * a + [1] * b + [0] * c))
+             for a, b, c in [(8, 9, 7), (12, 10, 0), (5, 5, 9), (20, 0, 0), (6, 8, 8)]]
+    kw = dict(init_runs=4, sampler_kw={"N": 20, "max_fcomplete": 50}, k_max=4, certainty_in_k=0.9)
+    seeds = [101, 102, 103, 104, 105]
+    outer = np.random.get_state()[1].copy()
+    res, stats = sample_many(trajs, model, seeds=seeds, max_active=3, **kw)
+    assert np.array_equal(np.random.get_state()[1], outer)                     # the caller's RNG stream is restored
+    assert sorted(res) == list(range(5)) and stats["launches"] == AsyncOracleBackedRouse.submits > 5
+    ref, _ = sample_many(trajs, model, seeds=seeds, schedule="rounds", **kw)   # the round-based scheme
+    for i, tr in enumerate(trajs):
+        np.random.seed(seeds[i])
+        solo = bild.sample(tr, OracleBackedRouse(8, 1, 5, d=2, localization_error=0.3), **kw)
+        for other in (res[i], ref[i]):
+            assert np.array_equal(solo.log["k"], other.log["k"])
+            assert np.array_equal(solo.evidence, other.evidence)
+            assert solo.best_profile() == other.best_profile()
+    # two localisation errors: one launch carries one error
+    model.localization_error = None
+    for i, tr in enumerate(trajs):
+        tr.localization_error = np.array([0.3, 0.3]) if i % 2 else np.array([0.2, 0.4])
+    res2, stats2 = sample_many(trajs, model, seeds=seeds, **kw)
+    for i, tr in enumerate(trajs):
+        np.random.seed(seeds[i])
+        solo = bild.sample(tr, OracleBackedRouse(8, 1, 5, d=2), **kw)
+        assert np.array_equal(solo.evidence, res2[i].evidence)
+
+
 def test_generator_api_equals_synchronous_api():
     """`sample_gen` / `FixedkSampler.step_gen` yield exactly the batches `sample` / `step` evaluate: driving them by hand
     with the model's own batched likelihood reproduces the synchronous run bit for bit, and the requests are the

@@ -97,6 +97,7 @@ def _claim_worker(rank, world, port, out_dir):
     trajs = [model.trajectory_from_loopingprofile(bild.Loopingprofile([0] * a + [1] * b + [0] * c))
              for a, b, c in [(8, 9, 7), (12, 10, 0), (5, 5, 9), (20, 0, 0), (6, 8, 6), (9, 9, 4), (3, 14, 5)]]
     kw = dict(init_runs=3, sampler_kw={"N": 15, "max_fcomplete": 40}, k_max=3, certainty_in_k=0.9)
+    dist.barrier()      # both ranks start claiming together (imports and model set-up take different times per process)
     res, stats = sample_many(trajs, model, seeds=list(range(300, 307)), claim=store_claimer(len(trajs)), max_active=2, **kw)
     np.savez(os.path.join(out_dir, f"claim{rank}.npz"), idx=np.array(sorted(res), dtype=int),
              **{f"ev{i}": res[i].evidence for i in res})

@@ -27,6 +27,7 @@ ap.add_argument("--profile", action="store_true", help="cProfile the driver on r
 ap.add_argument("--static", action="store_true", help="static round-robin partition instead of dynamic claims from a shared counter")
 ap.add_argument("--max-active", type=int, default=0, help="concurrent state machines per rank (default: 64 dynamic / all static)")
 ap.add_argument("--no-fuse-amis", action="store_true", help="one synchronous bildk_amis_step per sampler step instead of riding on the likelihood launch")
+ap.add_argument("--schedule", default="priority", choices=["priority", "rounds"], help="dataset driver scheduling (bild_b200/dataset.py)")
 a = ap.parse_args()
 rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 local = int(os.environ.get("LOCAL_RANK", 0))
@@ -55,7 +56,7 @@ if a.profile and rank == 0:
     import cProfile
     prof = cProfile.Profile()
     prof.enable()
-res, stats = sample_many(trajs, model, seeds=seeds, rank=rank, world=world, claim=claim, max_active=a.max_active or None, fuse_amis=not a.no_fuse_amis)
+res, stats = sample_many(trajs, model, seeds=seeds, rank=rank, world=world, claim=claim, max_active=a.max_active or None, fuse_amis=not a.no_fuse_amis, schedule=a.schedule)
 if prof is not None:
     import io
     import pstats
@@ -94,7 +95,7 @@ if rank == 0:
                                     "parallelism": f"trajectories partitioned over {world} rank(s), fused likelihood batches"},
         "frame_steps": summary[1], "frame_steps_per_s": summary[1] / summary[0], "profiles": summary[2],
         "fused_rounds_max": summary[3], "rank_wall_min_s": -summary[6], "rank_imbalance": summary[0] / max(-summary[6], 1e-9) - 1.0,
-        "partition": "static round-robin" if (a.static or world == 1) else "dynamic (shared counter)", "launches_rank0": int(launches), "amis_bookkeeping": "synchronous per step" if a.no_fuse_amis else "fused into the likelihood launch", "trajectories": int(summary[4]),
+        "partition": "static round-robin" if (a.static or world == 1) else "dynamic (shared counter)", "launches_rank0": int(launches), "schedule": a.schedule, "amis_bookkeeping": "synchronous per step" if a.no_fuse_amis else "fused into the likelihood launch", "trajectories": int(summary[4]),
         "truth_recovered_exactly": int(summary[5]), "check": check,
         "rank0_wall_split_s": {k: round(stats[k], 3) for k in ("t_host_lanes", "t_pack", "t_gpu")}, "data": "synthetic", "dtype": "f64"}), flush=True)
 if world > 1:
