@@ -52,6 +52,8 @@ SYMBOLS = {
     "bildk_marginal_posterior": (ctypes.c_int, [ctypes.c_int] * 4 + [c_int32_p, c_uint8_p, c_double_p, c_double_p, ctypes.c_int]),
     "bildk_amis_log_proposal": (ctypes.c_int, [ctypes.c_int] * 4 + [c_double_p, c_double_p, c_uint8_p, c_double_p,
                                                 ctypes.POINTER(ctypes.c_int64), c_double_p]),
+    "bildk_choice_pick": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, ctypes.c_double, c_int64_p]),
+    "bildk_choice_dn": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, c_double_p, ctypes.c_double, c_int64_p]),
     "bildk_amis_weights_device": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,
                                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "bildk_amis_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_uint8_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),

@@ -59,10 +59,19 @@ class _Lane:
         self.result = None
         self.done = False
         self.steps = 0                           # likelihood batches answered so far (scheduling priority)
+        self.host_s, self.n_advance = 0.0, 0     # host seconds / calls spent in this lane's state machine
         self.rng_state = None
 
     def advance(self, model, sample_kw):
         """Run until the next likelihood request (stored in `request`) or the end (`result`, `done`)."""
+        tic = time.perf_counter()
+        try:
+            self._advance(model, sample_kw)
+        finally:
+            self.host_s += time.perf_counter() - tic
+            self.n_advance += 1
+
+    def _advance(self, model, sample_kw):
         if self.gen is None:
             np.random.seed(self.seed)
             self.gen = sample_gen(self.traj, model, **sample_kw)
@@ -167,6 +176,7 @@ def _sample_many_priority(trajs, model, seeds, pending_lanes, claim, limit, fuse
             stats["t_host_lanes"] += time.perf_counter() - tic
             if lane.done:
                 results[lane.idx] = lane.result
+                stats["lanes"].append((lane.idx, lane.n_advance, round(lane.host_s, 4)))
                 n_active -= 1
             else:
                 waiting.append(lane)
@@ -183,6 +193,7 @@ def _sample_many_priority(trajs, model, seeds, pending_lanes, claim, limit, fuse
                                                  amis=[ln.amis for ln in lanes] if fuse_amis else None)
             inflight.append((batch, lanes, offsets))
             stats["t_gpu"] += time.perf_counter() - tic
+            stats["t_submit"] += time.perf_counter() - tic
             stats["launches"] += 1
             stats["rounds"] += 1
             stats["profiles"] += offsets[-1]
@@ -226,7 +237,8 @@ def sample_many(trajs, model, seeds=None, rank=0, world=1, max_active=None, clai
     mine = list(range(rank, len(trajs), world)) if claim is None else []
     outer_rng = np.random.get_state()
     stats = {"launches": 0, "profiles": 0, "frame_steps": 0, "rounds": 0,
-             "t_host_lanes": 0.0, "t_pack": 0.0, "t_gpu": 0.0}      # wall seconds: AMIS host code / run-length packing / fused launches
+             "t_host_lanes": 0.0, "t_pack": 0.0, "t_gpu": 0.0, "t_submit": 0.0,   # wall seconds: AMIS host code / run-length packing / fused launches
+             "lanes": []}                                            # per finished trajectory: (index, likelihood batches, host seconds)
     pending = [_Lane(i, trajs[i], seeds[i]) for i in mine]
     limit = max_active or (len(pending) if claim is None else 64) or 1
     if hasattr(model, "logL_runs_multi_submit") and schedule == "priority":
@@ -273,6 +285,7 @@ def sample_many(trajs, model, seeds=None, rank=0, world=1, max_active=None, clai
             stats["t_host_lanes"] += time.perf_counter() - tic
             for lane in [ln for ln in active if ln.done]:
                 results[lane.idx] = lane.result
+                stats["lanes"].append((lane.idx, lane.n_advance, round(lane.host_s, 4)))
                 active.remove(lane)
             waiting = [ln for ln in active if ln.request is not None]
             if not waiting:

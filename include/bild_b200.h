@@ -184,6 +184,18 @@ int bildk_amis_log_proposal(int n_par, int n, int K1, int S, const double *A, co
                             const uint8_t *transitions, const double *ss, const int64_t *thetas, double *out);
 
 /*
+ * ChoiceSampler arithmetic (reference bild/choicesampler.py:112-175), host side, no GPU, no random numbers: the selection
+ * rule "first k within dE of the row maximum" on the Monte-Carlo draws scaled_rvs (samplesize, kmax) + mu (kmax).
+ *   bildk_choice_pick: picks (samplesize) for one mean vector; NaN entries of mu mark omitted k (choicesampler.py:128-133)
+ *   bildk_choice_dn  : dn (kmax, kmax), dn[k1][k2] = change of the count of k2 when muhat[k1] moves from -Dmu[k1]/2 to
+ *                      +Dmu[k1]/2 (choicesampler.py:135-160) - 2 kmax evaluations of the rule in one pass over the draws.
+ * Same double additions and comparisons as the numpy statement, hence the same integers (tests compare them).
+ */
+int bildk_choice_pick(int samplesize, int kmax, const double *scaled_rvs, const double *mu, double dE, int64_t *picks);
+int bildk_choice_dn(int samplesize, int kmax, const double *scaled_rvs, const double *muhat, const double *Dmu, double dE,
+                    int64_t *dn);
+
+/*
  * Device-resident AMIS ensemble: the whole per-iteration bookkeeping of FixedkSampler.step (amis.py:824-845 mixture
  * denominators and weights, :878-900 evidence statistics, :137-151 Dirichlet moments, :300-303 CFC marginals) in ONE call.
  * The ensemble (interval lengths, state traces, likelihoods, mixture denominators, weights) and all past proposals stay

@@ -573,3 +573,31 @@ def test_sample_many_groups_by_localization_error_and_restores_rng():
     with pytest.raises(RuntimeError, match="boom"):
         sample_many(trajs, bad, seeds=seeds, **kw)
     assert np.array_equal(np.random.get_state()[1], before)
+
+
+def test_native_choice_sampler_equals_numpy_statement():
+    """`bildk_choice_pick` / `bildk_choice_dn` (one pass over the Monte-Carlo draws) give exactly the integers of the numpy
+    statement of choicesampler.py:112-160 - including -inf evidences, exhausted samplers (N = inf), omitted k, ties."""
+    from bild_b200.choicesampler import ChoiceSampler
+    import bild_b200.choicesampler as cs_mod
+    rng = np.random.default_rng(3)
+    for kmax, dE in [(1, 2.0), (2, 0.0), (3, 2.0), (6, 0.5), (11, 2.0), (17, 3.0)]:
+        logE = -100 + 5 * rng.random(kmax)
+        var = 0.2 * rng.random(kmax) ** 2
+        steps = rng.integers(1, 50, size=kmax).astype(float)
+        if kmax >= 3:
+            logE[-1] = -np.inf          # a sampler with more switches than frames (amis.py: evidence -inf)
+            steps[0] = np.inf           # an exhausted sampler
+            logE[1] = logE[2]           # a tie in the point estimates
+        np.random.seed(kmax)
+        cs = ChoiceSampler(logE, var, steps, dE, samplesize=2000)
+        assert cs_mod._native()
+        mu = cs.muhat.copy()
+        assert np.array_equal(cs.evaluate(), cs._evaluate_numpy(mu))
+        assert np.array_equal(cs.Dn(), cs._Dn_numpy())
+        if kmax >= 3:
+            mu2 = cs.muhat.copy()
+            mu2[[0, kmax - 2]] = np.nan
+            assert np.array_equal(cs.evaluate(omit_k=np.array([0, kmax - 2])), cs._evaluate_numpy(mu2))
+            assert np.isfinite(cs.KLD_omitK(np.array([kmax - 2, kmax - 1])))
+        assert np.all(np.isfinite(cs.KLD_moreSamples()))

@@ -48,6 +48,11 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dist.barrier()
 from bild_b200 import _lib  # noqa: E402
+tic = time.perf_counter()
+model.engine          # CUDA context, library load and model upload happen before the timed region (reported as setup_s)
+setup_s = time.perf_counter() - tic
+if world > 1:
+    dist.barrier()
 l0 = _lib.load().bildk_launch_count()
 t0 = time.perf_counter()
 claim = store_claimer(len(trajs)) if (world > 1 and not a.static) else None
@@ -78,6 +83,14 @@ if world > 1:
     summary[3] = float(tmax[3])
     summary[6] = float(tmax[6])          # max of -wall = -(fastest rank's wall)
 
+per_rank = None
+if world > 1:
+    mine = torch.tensor([wall, stats["t_host_lanes"], stats["t_gpu"], stats["t_pack"], stats["launches"], stats["profiles"], len(res),
+                         max((len(r.log["k"]) for r in res.values()), default=0)], dtype=torch.float64).cuda()
+    allr = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allr, mine)
+    per_rank = [dict(zip(("wall_s", "t_host_lanes", "t_gpu", "t_pack", "launches", "profiles", "trajectories", "longest_run_steps"),
+                         [round(float(v), 3) for v in t.cpu()])) for t in allr]
 check = {}
 if rank == 0 and a.check:
     worst = 0.0
@@ -95,8 +108,8 @@ if rank == 0:
                                     "parallelism": f"trajectories partitioned over {world} rank(s), fused likelihood batches"},
         "frame_steps": summary[1], "frame_steps_per_s": summary[1] / summary[0], "profiles": summary[2],
         "fused_rounds_max": summary[3], "rank_wall_min_s": -summary[6], "rank_imbalance": summary[0] / max(-summary[6], 1e-9) - 1.0,
-        "partition": "static round-robin" if (a.static or world == 1) else "dynamic (shared counter)", "launches_rank0": int(launches), "schedule": a.schedule, "amis_bookkeeping": "synchronous per step" if a.no_fuse_amis else "fused into the likelihood launch", "trajectories": int(summary[4]),
+        "partition": "static round-robin" if (a.static or world == 1) else "dynamic (shared counter)", "launches_rank0": int(launches), "setup_s_rank0": round(setup_s, 3), "schedule": a.schedule, "amis_bookkeeping": "synchronous per step" if a.no_fuse_amis else "fused into the likelihood launch", "trajectories": int(summary[4]),
         "truth_recovered_exactly": int(summary[5]), "check": check,
-        "rank0_wall_split_s": {k: round(stats[k], 3) for k in ("t_host_lanes", "t_pack", "t_gpu")}, "data": "synthetic", "dtype": "f64"}), flush=True)
+        "rank0_wall_split_s": {k: round(stats[k], 3) for k in ("t_host_lanes", "t_pack", "t_gpu", "t_submit")}, "per_rank": per_rank, "heaviest_trajectories_rank0": sorted(stats["lanes"], key=lambda t: -t[2])[:5], "data": "synthetic", "dtype": "f64"}), flush=True)
 if world > 1:
     dist.destroy_process_group()
