@@ -66,6 +66,13 @@ WORKLOADS = {
     "n150": dict(N=150, T=100, P=2048, p_nan=0.0, desc="N=150, T=100, 2048 profiles"),
     "n20big": dict(N=20, T=500, P=65536, p_nan=0.0, desc="N=20, T=500, 64k profiles"),
     "n50small": dict(N=50, T=1000, P=1024, p_nan=0.0, desc="N=50, T=1000, 1024 profiles"),
+    # polymer sizes with N mod 8 in {0, 5, 6, 7} (the mean does not fit the padding of the last 8x8 tile)
+    "n16": dict(N=16, T=500, P=65536, p_nan=0.0, desc="N=16, T=500, 64k profiles"),
+    "n24": dict(N=24, T=500, P=65536, p_nan=0.0, desc="N=24, T=500, 64k profiles"),
+    "n32": dict(N=32, T=500, P=32768, p_nan=0.0, desc="N=32, T=500, 32k profiles"),
+    "n40": dict(N=40, T=500, P=16384, p_nan=0.0, desc="N=40, T=500, 16384 profiles"),
+    "n48": dict(N=48, T=500, P=16384, p_nan=0.0, desc="N=48, T=500, 16384 profiles"),
+    "n56": dict(N=56, T=500, P=16384, p_nan=0.0, desc="N=56, T=500, 16384 profiles"),
 }
 D_SPATIAL, DIFF, KSPRING, LOC_ERR, KMAX = 3, 1.0, 5.0, 0.3, 10
 SEED = 685441950   # /root/reference/tests/test_bild.py:9

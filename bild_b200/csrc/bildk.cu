@@ -122,6 +122,7 @@ struct bildk_model {
     // register-chained tensor-core kernel (k_mmar): GT <= 4 and N mod 8 in 1..4
     bool mmar_ok = false;
     bool mmar2_ok = false;   // the same with two warps per filter (k_mmar2): GT 5..7
+    bool mmar_mx = false;    // N mod 8 in {0, 5, 6, 7}: M^T in an extra row block of the filter buffer
     int r_last = 0, LDr = 0, fstride_r = 0;
     double* dBr = nullptr;
     // per-model scratch of the launcher: partial logL of the d* sub-filters; covariance workspace of the N > 112 kernels
@@ -375,9 +376,10 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
             if (GT > 7) m->mma_ok = false;
             else
             m->mma_ok = 16 + matb * 8 * S + fbytes <= static_cast<size_t>(m->max_smem_optin);
-            // register-chained kernel: the last tile-row block must have room for M^T (and a zero row)
+            // register-chained kernels: M^T rides in the spare rows of the last tile-row block (rl <= 4: room for d <= 4 mean
+            // rows and a zero row) or, for rl >= 5, in an extra row block of the filter buffer ("MX", bildk_mmar.cuh)
             const int rl = N - 8 * (GT - 1);
-            if (GT <= 7 && rl >= 1 && rl <= 4 && d <= 4 && m->wz_idx[0] == 0 && m->wz_idx[1] == N - 1 && N >= 2) {   // end-to-end measurement only
+            if (GT <= 7 && rl >= 1 && rl <= 8 && d <= 4 && m->wz_idx[0] == 0 && m->wz_idx[1] == N - 1 && N >= 2) {   // end-to-end measurement only
                 const int R = 8 * GT;
                 const int LDr = (R % 16 == 8) ? R : R + 8;
                 const size_t matr = static_cast<size_t>(R) * LDr;
@@ -389,7 +391,8 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
                                 B[s * NN + static_cast<size_t>(std::max(i, j)) * N + std::min(i, j)];
                 if ((rc = upload(&m->dBr, pad.data(), S * matr))) return rc;
                 m->r_last = rl; m->LDr = LDr;
-                m->fstride_r = static_cast<int>(matr) + 2 * R + 8 + (GT >= 5 ? 2 * R : 0);   // k_mmar2: one C' w vector per warp
+                m->mmar_mx = rl > 4;
+                m->fstride_r = static_cast<int>(matr) + (m->mmar_mx ? 8 * LDr : 0) + 2 * R + 8 + (GT >= 5 ? 2 * R : 0);   // k_mmar2: one C' w vector per warp
                 const bool fits = 16 + matr * 8 * S + static_cast<size_t>(m->fstride_r) * 8 * 4 <= static_cast<size_t>(m->max_smem_optin);
                 m->mmar_ok = fits && GT <= 4;
                 m->mmar2_ok = fits && GT >= 5;
@@ -530,44 +533,49 @@ static cudaError_t mma_launch_for(int GT, bool MX, const MParams& mp, dim3 grid,
     return cudaErrorInvalidValue;
 }
 
-template <int GT, int NB>
+template <int GT, int NB, bool MX>
 static cudaError_t mmar_launch(const RParams& rp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
     {
-        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&k_mmar<GT, NB>), smem);
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&k_mmar<GT, NB, MX>), smem);
         if (e != cudaSuccess) return e;
     }
-    k_mmar<GT, NB><<<grid, threads, smem, st>>>(rp);
+    k_mmar<GT, NB, MX><<<grid, threads, smem, st>>>(rp);
     return cudaGetLastError();
 }
-// compiled register budgets (resident 4-warp CTAs per SM = warps per scheduler)
-#define MMAR_VARIANTS(X) X(1, 4) X(1, 7) X(2, 4) X(2, 5) X(2, 7) X(3, 4) X(3, 5) X(3, 7) X(4, 3) X(4, 4) X(4, 5)
-static bool mmar_has(int GT, int NB) {
-#define X(G_, N_) if (GT == G_ && NB == N_) return true;
+// compiled register budgets (resident 4-warp CTAs per SM = warps per scheduler); MX = mean in an extra row block
+#define MMAR_VARIANTS(X) X(1, 4, false) X(1, 7, false) X(2, 4, false) X(2, 5, false) X(2, 7, false) X(3, 4, false) X(3, 5, false) X(3, 7, false) \
+                         X(4, 3, false) X(4, 4, false) X(4, 5, false) \
+                         X(1, 4, true) X(2, 4, true) X(3, 4, true) X(3, 3, true) X(4, 3, true)
+static bool mmar_has(int GT, int NB, bool MX) {
+#define X(G_, N_, M_) if (GT == G_ && NB == N_ && MX == M_) return true;
     MMAR_VARIANTS(X)
 #undef X
     return false;
 }
-static cudaError_t mmar_launch_for(int GT, int NB, const RParams& rp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-#define X(G_, N_) if (GT == G_ && NB == N_) return mmar_launch<G_, N_>(rp, grid, threads, smem, st);
+static cudaError_t mmar_launch_for(int GT, int NB, bool MX, const RParams& rp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+#define X(G_, N_, M_) if (GT == G_ && NB == N_ && MX == M_) return mmar_launch<G_, N_, M_>(rp, grid, threads, smem, st);
     MMAR_VARIANTS(X)
 #undef X
     return cudaErrorInvalidValue;
 }
 
-template <int GT, int MAXF>
+template <int GT, int MAXF, bool MX>
 static cudaError_t mmar2_launch(const R2Params& rp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
     {
-        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&k_mmar2<GT, MAXF>), smem);
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&k_mmar2<GT, MAXF, MX>), smem);
         if (e != cudaSuccess) return e;
     }
-    k_mmar2<GT, MAXF><<<grid, threads, smem, st>>>(rp);
+    k_mmar2<GT, MAXF, MX><<<grid, threads, smem, st>>>(rp);
     return cudaGetLastError();
 }
 constexpr int MMAR2_MAXF = 4;   // filters per CTA: 8 warps at 255 registers (spill-free; 5 or 6 filters spill, see bildk_mmar2.cuh)
-static cudaError_t mmar2_launch_for(int GT, const R2Params& rp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-    if (GT == 5) return mmar2_launch<5, MMAR2_MAXF>(rp, grid, threads, smem, st);
-    if (GT == 6) return mmar2_launch<6, MMAR2_MAXF>(rp, grid, threads, smem, st);
-    if (GT == 7) return mmar2_launch<7, MMAR2_MAXF>(rp, grid, threads, smem, st);
+static cudaError_t mmar2_launch_for(int GT, bool MX, const R2Params& rp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    if (GT == 5 && !MX) return mmar2_launch<5, MMAR2_MAXF, false>(rp, grid, threads, smem, st);
+    if (GT == 6 && !MX) return mmar2_launch<6, MMAR2_MAXF, false>(rp, grid, threads, smem, st);
+    if (GT == 7 && !MX) return mmar2_launch<7, MMAR2_MAXF, false>(rp, grid, threads, smem, st);
+    if (GT == 5 && MX) return mmar2_launch<5, MMAR2_MAXF, true>(rp, grid, threads, smem, st);
+    if (GT == 6 && MX) return mmar2_launch<6, MMAR2_MAXF, true>(rp, grid, threads, smem, st);
+    if (GT == 7 && MX) return mmar2_launch<7, MMAR2_MAXF, true>(rp, grid, threads, smem, st);
     return cudaErrorInvalidValue;
 }
 
@@ -575,6 +583,18 @@ static cudaError_t mmar2_launch_for(int GT, const R2Params& rp, dim3 grid, int t
 // permuted last tile column are bank-conflict free: a 128-bit load is served per quarter warp (lanes g = 2i, 2i+1:
 // the two rows must differ in parity), a 64-bit load per half warp (lanes g = 4h..4h+3: rows distinct mod 4).
 static void mmar_tables(int GT, int r, int ncols, unsigned char* lastrow, unsigned char* mrow) {
+    if (r > 4) {
+        // MX: M^T row q = buffer row 8 GT + 2 q + 1, zero row = 8 GT.  The permuted (mean) tile column is only ever read with
+        // 128-bit loads, served per quarter warp (lanes g = 2i, 2i+1): the zero row is even, the mean rows are odd, and the
+        // row stride is == 8 (mod 16) doubles, so the two rows of a quarter warp fall into opposite halves of the banks
+        const int Z = 8 * GT;
+        for (int i = 0; i < 4; ++i) {
+            lastrow[2 * i] = static_cast<unsigned char>(Z);
+            lastrow[2 * i + 1] = static_cast<unsigned char>(i < ncols ? Z + 2 * i + 1 : Z);
+            mrow[i] = static_cast<unsigned char>(i < ncols ? Z + 2 * i + 1 : Z);
+        }
+        return;
+    }
     const int base = 8 * (GT - 1);
     std::vector<int> avail;
     for (int i = r; i < 8; ++i) avail.push_back(base + i);
@@ -744,7 +764,7 @@ static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
     Plan pl{};
     {
         const char* force0 = getenv("BILDK_KERNEL");
-        if (m->mmar2_ok && !force0 && !env_int("BILDK_FORCE_GENERIC", 0) && env_int("BILDK_MMAR2", 1)) {
+        if (m->mmar2_ok && !force0 && !env_int("BILDK_FORCE_GENERIC", 0) && env_int("BILDK_MMAR2", 1) && (!m->mmar_mx || env_int("BILDK_MMAR_MX", 1))) {
             const size_t matb = static_cast<size_t>(8 * m->GT) * m->LDr * 8;
             const size_t fbytes = static_cast<size_t>(m->fstride_r) * 8;
             int f = env_int("BILDK_FPC2", 0);
@@ -888,12 +908,13 @@ static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
     }
     {
         const char* force = getenv("BILDK_KERNEL");
-        const bool want_mmar = m->mmar_ok && !(force && strcmp(force, "mmar")) && !env_int("BILDK_FORCE_GENERIC", 0) && env_int("BILDK_MMAR", 1);
+        const bool want_mmar = m->mmar_ok && !(force && strcmp(force, "mmar")) && !env_int("BILDK_FORCE_GENERIC", 0) && env_int("BILDK_MMAR", 1) &&
+                               (!m->mmar_mx || env_int("BILDK_MMAR_MX", 1));
         if (want_mmar) {
             // measured on B200 (profiles/r01_mmar_variants.txt): 4 warps per scheduler with ~128 registers beat 7 warps
             // with 72 (spills) for every GT; GT = 4 needs 3 per scheduler to stay spill-free
             int nb = env_int("BILDK_MMAR_NB", m->GT <= 3 ? 4 : 3);
-            if (!mmar_has(m->GT, nb)) nb = m->GT <= 3 ? 4 : 3;
+            if (!mmar_has(m->GT, nb, m->mmar_mx)) nb = m->GT <= 3 ? 4 : 3;
             const size_t matb = static_cast<size_t>(8 * m->GT) * m->LDr * 8;
             const size_t fbytes = static_cast<size_t>(m->fstride_r) * 8;
             pl.mmar = true;
@@ -1033,11 +1054,11 @@ static std::string plan_string(const bildk_model* m, const Plan& pl) {
                  m->mma_mx ? "mean-in-extra-tile" : "mean-in-padding", pl.mmact ? "tile-slots-per-warp" : "warp-per-tile-column",
                  pl.nhelp ? " +3-P1-helper-warps" : "", pl.b_all ? "all" : "one", pl.threads, pl.smem);
     else if (pl.mmar2)
-        snprintf(buf, sizeof buf, "mmar2 (DMMA m8n8k4) GT=%d register-chained two-warps-per-filter (tile rows split) FPC=%d threads=%d smem=%zu", m->GT,
-                 pl.FPC, pl.threads, pl.smem);
+        snprintf(buf, sizeof buf, "mmar2 (DMMA m8n8k4) GT=%d%s register-chained two-warps-per-filter (tile rows split) FPC=%d threads=%d smem=%zu", m->GT,
+                 m->mmar_mx ? " mean-in-extra-rows" : "", pl.FPC, pl.threads, pl.smem);
     else if (pl.mmar)
-        snprintf(buf, sizeof buf, "mmar (DMMA m8n8k4) GT=%d register-chained warp-per-filter WPC=%d CTAs/SM=%d threads=%d smem=%zu", m->GT,
-                 pl.WPC, pl.nb, pl.threads, pl.smem);
+        snprintf(buf, sizeof buf, "mmar (DMMA m8n8k4) GT=%d%s register-chained warp-per-filter WPC=%d CTAs/SM=%d threads=%d smem=%zu", m->GT,
+                 m->mmar_mx ? " mean-in-extra-rows" : "", pl.WPC, pl.nb, pl.threads, pl.smem);
     else if (pl.mma)
         snprintf(buf, sizeof buf, "mma (DMMA m8n8k4) GT=%d %s warp-per-filter WPC=%d threads=%d smem=%zu", m->GT,
                  m->mma_mx ? "mean-in-extra-tile" : "mean-in-padding", pl.WPC, pl.threads, pl.smem);
@@ -1059,7 +1080,7 @@ extern "C" const char* bildk_describe_plan(bildk_traj_t t, int P) {
 extern "C" int bildk_debug_tables(int kernel, int GT, int r, int ncols, unsigned char* out) {
     if (!out) return fail(BILDK_EINVAL, "out is NULL");
     if (kernel == 0) {
-        if (GT < 1 || GT > 4 || r < 1 || r > 4 || ncols < 1 || ncols > 4) return fail(BILDK_EINVAL, "k_mmar tables need GT in 1..4, r in 1..4, ncols in 1..4");
+        if (GT < 1 || GT > 7 || r < 1 || r > 8 || ncols < 1 || ncols > 4) return fail(BILDK_EINVAL, "k_mmar tables need GT in 1..7, r in 1..8, ncols in 1..4");
         mmar_tables(GT, r, ncols, out, out + 8);
         return 12;
     }
@@ -1175,7 +1196,7 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
             rp.WPC = pl.WPC; rp.fstride = pl.fstride; rp.r = m->r_last;
             rp.ww00 = m->wz_val[0] * m->wz_val[0]; rp.ww11 = m->wz_val[1] * m->wz_val[1]; rp.ww01 = 2.0 * m->wz_val[0] * m->wz_val[1];
             for (int e = 0; e < dstar; ++e) mmar_tables(m->GT, m->r_last, t0->ncols[e], rp.lastrow[e], rp.mrow[e]);
-            CU(mmar_launch_for(m->GT, pl.nb, rp, grid, pl.threads, pl.smem, st));
+            CU(mmar_launch_for(m->GT, pl.nb, m->mmar_mx, rp, grid, pl.threads, pl.smem, st));
         } else if (pl.mmar2) {
             R2Params r2{};
             RParams& rp = r2.r;
@@ -1185,7 +1206,7 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
             rp.ww00 = m->wz_val[0] * m->wz_val[0]; rp.ww11 = m->wz_val[1] * m->wz_val[1]; rp.ww01 = 2.0 * m->wz_val[0] * m->wz_val[1];
             for (int e = 0; e < dstar; ++e) mmar_tables(m->GT, m->r_last, t0->ncols[e], rp.lastrow[e], rp.mrow[e]);
             r2.FPC2 = pl.FPC;
-            CU(mmar2_launch_for(m->GT, r2, grid, pl.threads, pl.smem, st));
+            CU(mmar2_launch_for(m->GT, m->mmar_mx, r2, grid, pl.threads, pl.smem, st));
         } else if (pl.mma2) {
             M2Params m2{};
             MParams& mp = m2.m;

@@ -41,12 +41,20 @@ struct RParams {
     unsigned char mrow[DMAX][4];      // per sub-filter: buffer row of mean column q (M^T)
 };
 
-template <int GT>
+// MX ("mean in an extra row block", N mod 8 in {0, 5, 6, 7}): the last tile-row block has no room for M^T next to its
+// r = N - 8 (GT - 1) >= 5 covariance rows, so the filter buffer gets eight more rows R .. R+7 (M^T in the odd ones, zeros
+// in the even ones), T one more tile column - again read with its columns permuted, even slots = the zero row, odd slots
+// = the mean columns, so that element 1 of its D fragment is the lane's prior mean exactly as without MX - and every
+// k-tile of both products is a full one (no single k-step).
+template <int GT, bool MX = false>
 struct MmarGeom {
     static constexpr int R = 8 * GT;
     static constexpr int LD = (R % 16 == 8) ? R : R + 8;   // == 8 (mod 16)
-    static constexpr int MAT = R * LD;
-    static constexpr int FSTRIDE = MAT + 2 * R + 8;        // buffer | two published columns | published means
+    static constexpr int MAT = R * LD;                     // one propagator
+    static constexpr int MATC = (R + (MX ? 8 : 0)) * LD;   // the filter buffer [C ; M^T]
+    static constexpr int KT = MX ? GT : GT - 1;            // full k-tiles (two DMMAs per 128-bit fragment pair)
+    static constexpr int GTC = GT + (MX ? 1 : 0);          // tile columns of T = B_s [C | M]
+    static constexpr int FSTRIDE = MATC + 2 * R + 8;       // buffer | two published columns | published means
 };
 
 // 1 / S to within an ulp or two in three dependent FMAs: y0 = rcp.approx (relative error <= 2^-23), e = 1 - S y0,
@@ -61,11 +69,13 @@ __device__ __forceinline__ double rcp3(double S) {
 // CTAs are 4 warps (one per warp scheduler; measured best: fine-grained CTA scheduling keeps the four schedulers of
 // an SM evenly loaded).  NB = resident CTAs per SM the kernel is compiled for, i.e. warps per scheduler; registers per
 // thread = 65536 / (128 NB).  HIDE: re-read the fragments for every tile row instead of keeping them in registers.
-template <int GT, int NB>
+template <int GT, int NB, bool MX = false>
 __global__ void __launch_bounds__(128, NB) k_mmar(const __grid_constant__ RParams rp) {
     constexpr bool HIDE = (65536 / (128 * NB)) / 8 * 8 < 40 + 12 * GT * GT / 3 + 28;
-    constexpr int R = MmarGeom<GT>::R, LD = MmarGeom<GT>::LD, MAT = MmarGeom<GT>::MAT;
-    constexpr int KT = GT - 1;                     // full k-tiles (two DMMAs per 128-bit fragment pair)
+    using G = MmarGeom<GT, MX>;
+    constexpr int R = G::R, LD = G::LD, MAT = G::MAT, MATC = G::MATC;
+    constexpr int KT = G::KT;                      // full k-tiles (two DMMAs per 128-bit fragment pair)
+    constexpr int GTC = G::GTC;                    // tile columns of T; the last one is read with permuted columns
     constexpr int NU = GT * (GT + 1) / 2;          // upper tiles of C'
 #define UIDX(ti, tjj) ((ti) * GT - (ti) * ((ti) - 1) / 2 + ((tjj) - (ti)))
     const KParams& p = rp.k;
@@ -99,7 +109,7 @@ __global__ void __launch_bounds__(128, NB) k_mmar(const __grid_constant__ RParam
     if (!alive) return;   // warps are independent from here on (warp-scope barriers only)
 
     double* const Cb = Bsm + MAT * p.S + wid * rp.fstride;   // [R][LD]: rows < N covariance, spare rows of the last block M^T / zero
-    double* const colb = Cb + MAT;                            // [2][R] the two columns of C' that w touches
+    double* const colb = Cb + MATC;                           // [2][R] the two columns of C' that w touches
     double* const mpub = colb + 2 * R;                        // [2][4] prior mean rows j0, j1
     for (int i = lane; i < rp.fstride; i += 32) Cb[i] = 0.0;  // padding columns and zero rows must stay finite / zero
 
@@ -170,22 +180,22 @@ __global__ void __launch_bounds__(128, NB) k_mmar(const __grid_constant__ RParam
                 if (HIDE) asm volatile("" : "+r"(oq));
                 const double* Cq = Cb + oq;
                 const double* Bq = Bs + oq;
-                double Tt[GT][2];
+                double Tt[GTC][2];
 #pragma unroll
-                for (int tj = 0; tj < GT; ++tj) Tt[tj][0] = Tt[tj][1] = 0.0;
+                for (int tj = 0; tj < GTC; ++tj) Tt[tj][0] = Tt[tj][1] = 0.0;
 #pragma unroll
                 for (int kt = 0; kt < KT; ++kt) {
                     const double2 a = *reinterpret_cast<const double2*>(Bq + offP + 8 * ti * LD + 8 * kt);
-                    double2 b[GT];
+                    double2 b[GTC];
 #pragma unroll
-                    for (int tj = 0; tj < GT; ++tj)
-                        b[tj] = *reinterpret_cast<const double2*>(tj < GT - 1 ? Cq + offP + 8 * tj * LD + 8 * kt : Cq + offLP + 8 * kt);
+                    for (int tj = 0; tj < GTC; ++tj)
+                        b[tj] = *reinterpret_cast<const double2*>(tj < GTC - 1 ? Cq + offP + 8 * tj * LD + 8 * kt : Cq + offLP + 8 * kt);
 #pragma unroll
-                    for (int tj = 0; tj < GT; ++tj) dmma884(Tt[tj], a.x, b[tj].x);
+                    for (int tj = 0; tj < GTC; ++tj) dmma884(Tt[tj], a.x, b[tj].x);
 #pragma unroll
-                    for (int tj = 0; tj < GT; ++tj) dmma884(Tt[tj], a.y, b[tj].y);
+                    for (int tj = 0; tj < GTC; ++tj) dmma884(Tt[tj], a.y, b[tj].y);
                 }
-                {
+                if constexpr (!MX) {
                     const double a = Bq[offS + 8 * ti * LD];
                     double b[GT];
 #pragma unroll
@@ -193,7 +203,7 @@ __global__ void __launch_bounds__(128, NB) k_mmar(const __grid_constant__ RParam
 #pragma unroll
                     for (int tj = 0; tj < GT; ++tj) dmma884(Tt[tj], a, b[tj]);
                 }
-                mu[ti] = Tt[GT - 1][1];   // M'[8 ti + g][c4]  (zero for lanes without a mean column)
+                mu[ti] = Tt[GTC - 1][1];   // M'[8 ti + g][c4]  (zero for lanes without a mean column)
                 // ---------------- P2, upper tiles of tile row ti: C'[ti][tj] = Sig + T[ti][:] B_s[:][tj]
 #pragma unroll
                 for (int tj = ti; tj < GT; ++tj) {
@@ -211,7 +221,7 @@ __global__ void __launch_bounds__(128, NB) k_mmar(const __grid_constant__ RParam
 #pragma unroll
                     for (int tj = ti; tj < GT; ++tj) dmma884(acc[UIDX(ti, tj)], Tt[kt][1], b[tj].y);
                 }
-                {
+                if constexpr (!MX) {
                     double b[GT];
 #pragma unroll
                     for (int tj = ti; tj < GT; ++tj) b[tj] = Bq[offS + 8 * tj * LD];

@@ -26,10 +26,11 @@ struct R2Params {
 template <int GT>
 struct Mmar2Rows {
     // role (0 / 1) that owns tile-row block ti; cost of a row = GT (P1) + GT - ti (P2) tile products
+    // (with the mean in an extra tile column, MX, every row costs one more: the same splits stay the balanced ones)
     __host__ __device__ static constexpr int role(int ti) {
-        return GT == 7 ? (ti <= 2 ? 0 : 1)                       // 14+13+12 = 39 | 11+10+9+8 = 38
-             : GT == 6 ? ((ti == 0 || ti == 3 || ti == 5) ? 0 : 1)   // 12+9+7 = 28 | 11+10+8 = 29
-             : (ti <= 1 ? 0 : 1);                                // GT = 5: 10+9 = 19 | 8+7+6 = 21
+        return GT == 7 ? (ti <= 2 ? 0 : 1)                       // 14+13+12 = 39 | 11+10+9+8 = 38      MX: 42 | 42
+             : GT == 6 ? ((ti == 0 || ti == 3 || ti == 5) ? 0 : 1)   // 12+9+7 = 28 | 11+10+8 = 29          MX: 31 | 32
+             : (ti <= 1 ? 0 : 1);                                // GT = 5: 10+9 = 19 | 8+7+6 = 21      MX: 21 | 24
     }
     __host__ __device__ static constexpr int nacc(int r) {          // upper tiles owned by role r
         int n = 0;
@@ -57,13 +58,13 @@ struct Mmar2Rows {
     }
 };
 
-template <int GT, int ROLE>
+template <int GT, int ROLE, bool MX>
 __device__ __forceinline__ void mmar2_run(const RParams& rp, const double* __restrict__ Bsm, double* __restrict__ Cb, int pidx, int tjx,
                                           int e_sub, int barid, int lane) {
-    using G = MmarGeom<GT>;
+    using G = MmarGeom<GT, MX>;
     using RW = Mmar2Rows<GT>;
-    constexpr int R = G::R, LD = G::LD, MAT = G::MAT;
-    constexpr int KT = GT - 1;
+    constexpr int R = G::R, LD = G::LD, MAT = G::MAT, MATC = G::MATC;
+    constexpr int KT = G::KT, GTC = G::GTC;
     constexpr int NACC = RW::nacc(ROLE), NROW = RW::nrows(ROLE);
     constexpr bool OWN_FIRST = RW::role(0) == ROLE, OWN_LAST = RW::role(GT - 1) == ROLE;
     constexpr int FIRSTROW = RW::first(ROLE);
@@ -73,7 +74,7 @@ __device__ __forceinline__ void mmar2_run(const RParams& rp, const double* __res
     const KParams& p = rp.k;
     const int g = lane >> 2, c4 = lane & 3;
     const int N = p.N, D = p.D;
-    double* const colb = Cb + MAT;              // [2][R] the two columns of C' that w touches
+    double* const colb = Cb + MATC;             // [2][R] the two columns of C' that w touches
     double* const mpub = colb + 2 * R;          // [2][4] prior mean rows 0 and N - 1
     double* const cwb = mpub + 8 + ROLE * R;    // [R] this warp's copy of C' w
 
@@ -128,28 +129,28 @@ __device__ __forceinline__ void mmar2_run(const RParams& rp, const double* __res
             const double* __restrict__ Gs = rp.Sigm + static_cast<size_t>(R * R) * s + g * R + 2 * c4;
             // ---------------- P1, this warp's tile-row blocks: T[ti][:] = B_s[ti][:] [C | M]   (MSRouse_logL.pyx:206-241)
             // k-tile outermost: the GT fragments of [C | M] of a k-tile are loaded once and serve all of this warp's rows
-            double Tt[NROW][GT][2];
+            double Tt[NROW][GTC][2];
 #pragma unroll
             for (int r = 0; r < NROW; ++r)
 #pragma unroll
-                for (int tj = 0; tj < GT; ++tj) Tt[r][tj][0] = Tt[r][tj][1] = 0.0;
+                for (int tj = 0; tj < GTC; ++tj) Tt[r][tj][0] = Tt[r][tj][1] = 0.0;
 #pragma unroll
             for (int kt = 0; kt < KT; ++kt) {
-                double2 b[GT];
+                double2 b[GTC];
 #pragma unroll
-                for (int tj = 0; tj < GT; ++tj)
-                    b[tj] = *reinterpret_cast<const double2*>(tj < GT - 1 ? Cb + offP + 8 * tj * LD + 8 * kt : Cb + offLP + 8 * kt);
+                for (int tj = 0; tj < GTC; ++tj)
+                    b[tj] = *reinterpret_cast<const double2*>(tj < GTC - 1 ? Cb + offP + 8 * tj * LD + 8 * kt : Cb + offLP + 8 * kt);
 #pragma unroll
                 for (int ti = 0; ti < GT; ++ti) {
                     if (!MINE(ti)) continue;
                     const double2 a = *reinterpret_cast<const double2*>(Bs + offP + 8 * ti * LD + 8 * kt);
 #pragma unroll
-                    for (int tj = 0; tj < GT; ++tj) dmma884(Tt[RIDX(ti)][tj], a.x, b[tj].x);
+                    for (int tj = 0; tj < GTC; ++tj) dmma884(Tt[RIDX(ti)][tj], a.x, b[tj].x);
 #pragma unroll
-                    for (int tj = 0; tj < GT; ++tj) dmma884(Tt[RIDX(ti)][tj], a.y, b[tj].y);
+                    for (int tj = 0; tj < GTC; ++tj) dmma884(Tt[RIDX(ti)][tj], a.y, b[tj].y);
                 }
             }
-            {
+            if constexpr (!MX) {
                 double b[GT];
 #pragma unroll
                 for (int tj = 0; tj < GT; ++tj) b[tj] = tj < GT - 1 ? Cb[offS + 8 * tj * LD] : Cb[offLS];
@@ -165,7 +166,7 @@ __device__ __forceinline__ void mmar2_run(const RParams& rp, const double* __res
 #pragma unroll
             for (int ti = 0; ti < GT; ++ti) {
                 if (!MINE(ti)) continue;
-                mu[RIDX(ti)] = Tt[RIDX(ti)][GT - 1][1];   // M'[8 ti + g][c4]
+                mu[RIDX(ti)] = Tt[RIDX(ti)][GTC - 1][1];   // M'[8 ti + g][c4]
 #pragma unroll
                 for (int tj = ti; tj < GT; ++tj) {
                     const double2 v = __ldg(reinterpret_cast<const double2*>(Gs + 8 * ti * R + 8 * tj));
@@ -187,7 +188,7 @@ __device__ __forceinline__ void mmar2_run(const RParams& rp, const double* __res
                     for (int tj = ti; tj < GT; ++tj) dmma884(acc[AIDX(ti, tj)], Tt[RIDX(ti)][kt][1], b[tj].y);
                 }
             }
-            {
+            if constexpr (!MX) {
                 double b[GT];
 #pragma unroll
                 for (int tj = FIRSTROW; tj < GT; ++tj) b[tj] = Bs[offS + 8 * tj * LD];
@@ -314,9 +315,9 @@ __device__ __forceinline__ void mmar2_run(const RParams& rp, const double* __res
 }
 
 // MAXF: filters per CTA the kernel is compiled for (registers per thread = 65536 / (64 MAXF)).
-template <int GT, int MAXF>
+template <int GT, int MAXF, bool MX = false>
 __global__ void __launch_bounds__(64 * MAXF, 1) k_mmar2(const __grid_constant__ R2Params rp2) {
-    constexpr int MAT = MmarGeom<GT>::MAT;
+    constexpr int MAT = MmarGeom<GT, MX>::MAT;
     const RParams& rp = rp2.r;
     const KParams& p = rp.k;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -349,8 +350,8 @@ __global__ void __launch_bounds__(64 * MAXF, 1) k_mmar2(const __grid_constant__ 
     for (int i = (wid & 1) * 32 + lane; i < rp.fstride; i += 64) Cb[i] = 0.0;
     pair_sync(1 + fl);
     mbar_wait(mbar, 0);
-    if (role == 0) mmar2_run<GT, 0>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, 1 + fl, lane);
-    else mmar2_run<GT, 1>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, 1 + fl, lane);
+    if (role == 0) mmar2_run<GT, 0, MX>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, 1 + fl, lane);
+    else mmar2_run<GT, 1, MX>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, 1 + fl, lane);
 }
 
 }  // namespace bildk

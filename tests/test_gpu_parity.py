@@ -187,6 +187,52 @@ def test_register_chained_two_warp_kernel(N, d, noise, loops, fpc, monkeypatch):
     assert rel_err(eng.logl_st(traj, ss, thetas), got) < 1e-12
 
 
+MX_CASES = [
+    # N, d, noise, loops, kernel             register-chained kernels with the mean in an extra row block: N mod 8 in {0, 5, 6, 7}
+    (5, 3, 0.5, (None, [(0, -1)]), "mmar"),            # GT=1, r=5
+    (8, 4, 0.4, (None, [(0, -1)]), "mmar"),            # GT=1, r=8, d=4: all four mean rows in use
+    (14, 2, [0.1, 0.4], (None, [(0, -1)]), "mmar"),    # GT=2, r=6, d*=2
+    (16, 3, 0.2, (None, [(0, -1)]), "mmar"),           # GT=2, r=8
+    (23, 1, 0.3, (None, [(0, -1)]), "mmar"),           # GT=3, r=7, d=1
+    (24, 3, 0.3, (None, [(0, -1)], [(2, 9), (5, 15, 0.5)]), "mmar"),   # GT=3, r=8, 3 states
+    (24, 3, [0.2, 0.2, 0.5], (None, [(0, -1)]), "mmar"),               # ... anisotropic error: sub-filters with 2 and 1 columns
+    (29, 3, 0.3, (None, [(0, -1)]), "mmar"),           # GT=4, r=5
+    (32, 3, 0.3, (None, [(0, -1)]), "mmar"),           # GT=4, r=8
+    (37, 3, 0.3, (None, [(0, -1)]), "mmar2"),          # GT=5, r=5
+    (40, 2, [0.1, 0.4], (None, [(0, -1)]), "mmar2"),   # GT=5, r=8, d*=2
+    (46, 1, 0.3, (None, [(0, -1)]), "mmar2"),          # GT=6, r=6, d=1
+    (48, 4, 0.4, (None, [(0, -1)]), "mmar2"),          # GT=6, r=8, d=4
+    (55, 3, 0.3, (None, [(0, -1)], [(5, 30), (12, 44, 0.5)]), "mmar2"),   # GT=7, r=7, 3 states
+    (56, 3, 0.3, (None, [(0, -1)]), "mmar2"),          # GT=7, r=8
+]
+
+
+@pytest.mark.parametrize("N,d,noise,loops,kernel", MX_CASES)
+def test_register_chained_kernels_mean_in_extra_rows(N, d, noise, loops, kernel, monkeypatch):
+    """k_mmar / k_mmar2 with M^T in an extra row block of the filter buffer (every k-tile full, the mean tile column read
+    with permuted columns) vs the C oracle and vs the shared-memory round-trip kernels (k_mma / k_mma2) on the same inputs."""
+    rng = np.random.default_rng(277 + N)
+    mod = oracle_model(N, d=d, loops=loops)
+    T, P = 50, 29
+    x, _ = synth_traj(mod, T, rng, noise, p_nan=0.15)
+    x[0] = np.nan if N % 2 else x[0]                     # odd N: first frame missing
+    ss, thetas = random_profiles(rng, P, T, len(loops), 6)
+    err = np.broadcast_to(np.asarray(noise, dtype=float), (d,))
+    s2, Cind = ko.noise_to_s2_cind(err)
+    states = np.array([ko.st2states(s, th, T) for s, th in zip(ss, thetas)])
+    want = ko.logl_c(*(mod[k] for k in MODEL_KEYS), x, s2, Cind, states)
+    eng = engine_for(mod)
+    traj = eng.trajectory(x, err)
+    plan = traj.describe_plan(P)
+    assert plan.split()[0] == kernel and "mean-in-extra-rows" in plan
+    got = eng.logl_st(traj, ss, thetas)
+    assert rel_err(got, want) < TOL
+    assert np.array_equal(got, eng.logl_states(traj, states))
+    monkeypatch.setenv("BILDK_MMAR_MX", "0")             # the older kernels on the same inputs
+    assert traj.describe_plan(P).split()[0] in ("mma", "mma2")
+    assert rel_err(eng.logl_st(traj, ss, thetas), got) < 1e-12
+
+
 @pytest.mark.parametrize("N,nz", [
     (20, {3: -1.0, 14: 1.0}),            # two interior monomers (k_mma)
     (20, {7: 0.5, 8: -2.0}),             # neighbours in one tile, unequal weights
