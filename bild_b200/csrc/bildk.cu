@@ -484,7 +484,8 @@ struct Plan {
     bool mmact = false;    // ... and P2 / update / write-back dealt out as tile slots (k_mmact)
     bool mma2 = false;     // tensor-core kernel, two warps per filter (GT 5..7)
     bool mmar = false;     // tensor-core kernel, one warp per filter, T chained through registers (GT <= 4)
-    bool mmar2 = false;    // the same with two warps per filter splitting the tile rows (GT 5..7, N mod 8 in 1..4)
+    bool mmar2 = false;    // the same with two warps per filter splitting the tile rows (GT 5..7)
+    int maxf = 4;          // k_mmar2: filters per CTA the launched instantiation is compiled for
     int nb = 0;            // ... its variant: resident 4-warp CTAs per SM it is compiled for
     unsigned char colmap[40] = {0};
     int WPC = 0;
@@ -568,14 +569,27 @@ static cudaError_t mmar2_launch(const R2Params& rp, dim3 grid, int threads, size
     k_mmar2<GT, MAXF, MX><<<grid, threads, smem, st>>>(rp);
     return cudaGetLastError();
 }
-constexpr int MMAR2_MAXF = 4;   // filters per CTA: 8 warps at 255 registers (spill-free; 5 or 6 filters spill, see bildk_mmar2.cuh)
-static cudaError_t mmar2_launch_for(int GT, bool MX, const R2Params& rp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-    if (GT == 5 && !MX) return mmar2_launch<5, MMAR2_MAXF, false>(rp, grid, threads, smem, st);
-    if (GT == 6 && !MX) return mmar2_launch<6, MMAR2_MAXF, false>(rp, grid, threads, smem, st);
-    if (GT == 7 && !MX) return mmar2_launch<7, MMAR2_MAXF, false>(rp, grid, threads, smem, st);
-    if (GT == 5 && MX) return mmar2_launch<5, MMAR2_MAXF, true>(rp, grid, threads, smem, st);
-    if (GT == 6 && MX) return mmar2_launch<6, MMAR2_MAXF, true>(rp, grid, threads, smem, st);
-    if (GT == 7 && MX) return mmar2_launch<7, MMAR2_MAXF, true>(rp, grid, threads, smem, st);
+// MAXF = filters per CTA the kernel is compiled for (registers per thread = 65536 / (64 MAXF)): GT = 7 is spill-free only at
+// 4 (8 warps, 255 registers; 5 or 6 filters spill, see bildk_mmar2.cuh); the smaller tile grids leave room for more warps.
+constexpr int MMAR2_MAXF = 4;
+#define MMAR2_VARIANTS(X) X(5, 4, false) X(6, 4, false) X(7, 4, false) X(5, 4, true) X(6, 4, true) X(7, 4, true) \
+                          X(5, 6, false) X(5, 6, true)
+static bool mmar2_has(int GT, int MAXF, bool MX) {
+#define X(G_, F_, M_) if (GT == G_ && MAXF == F_ && MX == M_) return true;
+    MMAR2_VARIANTS(X)
+#undef X
+    return false;
+}
+static int mmar2_maxf(int GT, bool MX) {
+    // GT = 5: 12 warps at 168 registers (spill-free without MX, 76 bytes with) beat 8 warps at 194 / 210 by 3-4 %
+    // (profiles/r02_mx_variants.txt); GT = 6 spills at 168 registers and loses 18 %
+    const int want = env_int("BILDK_MMAR2_MAXF", GT == 5 ? 6 : MMAR2_MAXF);
+    return mmar2_has(GT, want, MX) ? want : MMAR2_MAXF;
+}
+static cudaError_t mmar2_launch_for(int GT, int MAXF, bool MX, const R2Params& rp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+#define X(G_, F_, M_) if (GT == G_ && MAXF == F_ && MX == M_) return mmar2_launch<G_, F_, M_>(rp, grid, threads, smem, st);
+    MMAR2_VARIANTS(X)
+#undef X
     return cudaErrorInvalidValue;
 }
 
@@ -767,24 +781,34 @@ static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
         if (m->mmar2_ok && !force0 && !env_int("BILDK_FORCE_GENERIC", 0) && env_int("BILDK_MMAR2", 1) && (!m->mmar_mx || env_int("BILDK_MMAR_MX", 1))) {
             const size_t matb = static_cast<size_t>(8 * m->GT) * m->LDr * 8;
             const size_t fbytes = static_cast<size_t>(m->fstride_r) * 8;
+            const int maxf = mmar2_maxf(m->GT, m->mmar_mx);
             int f = env_int("BILDK_FPC2", 0);
             if (f <= 0) {
                 // filters per CTA by  waves x time per wave.  Measured at N = 50 (T = 200, P = 16384, profiles/r02_mmar2_variants.txt):
                 // 4 filters in one CTA per SM 52.3 ms, 2 filters x 2 CTAs per SM 53.1, 3 filters (one scheduler pair carries
                 // two warps) 69.2, 1 filter x 3 CTAs per SM 59.3 - relative time of one full wave (all resident slots busy):
-                static const double wave_time[5] = {0.0, 0.85, 1.016, 0.99, 1.0};
+                // relative time of one full wave (all resident slots busy), per tile-grid size: GT = 7 as above; GT = 6
+                // (N = 48, profiles/r02_mx_variants.txt) 2 filters x 2 CTAs per SM 0.977 of 4 x 1; GT = 5 (N = 40, 36; compiled for
+                // 6 filters) 2 x 3 CTAs 0.983, 3 x 2 CTAs 0.985 of 6 x 1.  Counts that do not divide the compiled maximum leave
+                // register file unused and are not candidates for GT < 7.
+                static const double wt7[7] = {0.0, 0.85, 1.016, 0.99, 1.0, 1.0, 1.0};
+                static const double wt6[7] = {0.0, 1.0, 0.977, 1.0, 1.0, 1.0, 1.0};
+                static const double wt5[7] = {0.0, 1.0, 0.983, 0.985, 1.0, 1.0, 1.0};
+                const double* wave_time = m->GT == 7 ? wt7 : (m->GT == 6 ? wt6 : wt5);
                 const long long P = std::max(1, P_per_traj_hint);
                 double best = 1e300;
-                for (int c = MMAR2_MAXF; c >= 1; --c) {
+                for (int c = maxf; c >= 1; --c) {
+                    if (m->GT < 7 && maxf % c) continue;
                     const size_t smem_c = 16 + matb * m->S + fbytes * c;
-                    const int per_sm = std::max<int>(1, std::min<int>(static_cast<int>((228 * 1024) / (smem_c + 1024)), MMAR2_MAXF / c));
+                    const int per_sm = std::max<int>(1, std::min<int>(static_cast<int>((228 * 1024) / (smem_c + 1024)), maxf / c));
                     const long long n_cta = (P + c - 1) / c, slots = static_cast<long long>(m->n_sm) * per_sm;
                     const double cost = static_cast<double>((n_cta + slots - 1) / slots) * wave_time[c];
                     if (cost < best - 1e-9) { best = cost; f = c; }
                 }
             }
-            f = std::max(1, std::min(f, MMAR2_MAXF));
+            f = std::max(1, std::min(f, maxf));
             pl.mmar2 = true;
+            pl.maxf = maxf;
             pl.tile = false;
             pl.FPC = f;
             pl.WPC = f;
@@ -1054,8 +1078,8 @@ static std::string plan_string(const bildk_model* m, const Plan& pl) {
                  m->mma_mx ? "mean-in-extra-tile" : "mean-in-padding", pl.mmact ? "tile-slots-per-warp" : "warp-per-tile-column",
                  pl.nhelp ? " +3-P1-helper-warps" : "", pl.b_all ? "all" : "one", pl.threads, pl.smem);
     else if (pl.mmar2)
-        snprintf(buf, sizeof buf, "mmar2 (DMMA m8n8k4) GT=%d%s register-chained two-warps-per-filter (tile rows split) FPC=%d threads=%d smem=%zu", m->GT,
-                 m->mmar_mx ? " mean-in-extra-rows" : "", pl.FPC, pl.threads, pl.smem);
+        snprintf(buf, sizeof buf, "mmar2 (DMMA m8n8k4) GT=%d%s register-chained two-warps-per-filter (tile rows split) FPC=%d of %d threads=%d smem=%zu", m->GT,
+                 m->mmar_mx ? " mean-in-extra-rows" : "", pl.FPC, pl.maxf, pl.threads, pl.smem);
     else if (pl.mmar)
         snprintf(buf, sizeof buf, "mmar (DMMA m8n8k4) GT=%d%s register-chained warp-per-filter WPC=%d CTAs/SM=%d threads=%d smem=%zu", m->GT,
                  m->mmar_mx ? " mean-in-extra-rows" : "", pl.WPC, pl.nb, pl.threads, pl.smem);
@@ -1206,7 +1230,7 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
             rp.ww00 = m->wz_val[0] * m->wz_val[0]; rp.ww11 = m->wz_val[1] * m->wz_val[1]; rp.ww01 = 2.0 * m->wz_val[0] * m->wz_val[1];
             for (int e = 0; e < dstar; ++e) mmar_tables(m->GT, m->r_last, t0->ncols[e], rp.lastrow[e], rp.mrow[e]);
             r2.FPC2 = pl.FPC;
-            CU(mmar2_launch_for(m->GT, m->mmar_mx, r2, grid, pl.threads, pl.smem, st));
+            CU(mmar2_launch_for(m->GT, pl.maxf, m->mmar_mx, r2, grid, pl.threads, pl.smem, st));
         } else if (pl.mma2) {
             M2Params m2{};
             MParams& mp = m2.m;
