@@ -72,6 +72,9 @@ WORKLOADS = {
     "n32": dict(N=32, T=500, P=32768, p_nan=0.0, desc="N=32, T=500, 32k profiles"),
     "n40": dict(N=40, T=500, P=16384, p_nan=0.0, desc="N=40, T=500, 16384 profiles"),
     "n48": dict(N=48, T=500, P=16384, p_nan=0.0, desc="N=48, T=500, 16384 profiles"),
+    "n17": dict(N=17, T=500, P=65536, p_nan=0.0, desc="N=17, T=500, 64k profiles"),
+    "n18": dict(N=18, T=500, P=65536, p_nan=0.0, desc="N=18, T=500, 64k profiles"),
+    "n26": dict(N=26, T=500, P=65536, p_nan=0.0, desc="N=26, T=500, 64k profiles"),
     "n36": dict(N=36, T=500, P=16384, p_nan=0.0, desc="N=36, T=500, 16384 profiles"),
     "n56": dict(N=56, T=500, P=16384, p_nan=0.0, desc="N=56, T=500, 16384 profiles"),
 }

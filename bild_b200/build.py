@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(HERE, "csrc", "bildk.cu")]
 DEPS = SRC + [os.path.join(HERE, "csrc", "bildk_kernels.cuh"), os.path.join(HERE, "csrc", "bildk_mma.cuh"),
-              os.path.join(HERE, "csrc", "bildk_mmar.cuh"), os.path.join(HERE, "csrc", "bildk_mmar2.cuh"), os.path.join(HERE, "csrc", "bildk_mmag2.cuh"), os.path.join(HERE, "csrc", "bildk_mmact.cuh"),
+              os.path.join(HERE, "csrc", "bildk_mmar.cuh"), os.path.join(HERE, "csrc", "bildk_mmar2.cuh"), os.path.join(HERE, "csrc", "bildk_mmarb.cuh"), os.path.join(HERE, "csrc", "bildk_mmag2.cuh"), os.path.join(HERE, "csrc", "bildk_mmact.cuh"),
               os.path.join(HERE, "csrc", "bildk_amis.cuh"),
               os.path.join(os.path.dirname(HERE), "include", "bild_b200.h")]
 OUT = os.path.join(HERE, "libbild_b200.so")

@@ -8,6 +8,7 @@
 #include "bildk_mma.cuh"
 #include "bildk_mmar.cuh"
 #include "bildk_mmar2.cuh"
+#include "bildk_mmarb.cuh"
 #include "bildk_mmag2.cuh"
 #include "bildk_mmact.cuh"
 #include "bildk_amis.cuh"
@@ -123,6 +124,7 @@ struct bildk_model {
     bool mmar_ok = false;
     bool mmar2_ok = false;   // the same with two warps per filter (k_mmar2): GT 5..7
     bool mmar_mx = false;    // N mod 8 in {0, 5, 6, 7}: M^T in an extra row block of the filter buffer
+    bool mmarb_ok = false;   // N mod 8 in {1, 2}, GT 2..4: border rows / columns in DFMAs (k_mmarb)
     int r_last = 0, LDr = 0, fstride_r = 0;
     double* dBr = nullptr;
     // per-model scratch of the launcher: partial logL of the d* sub-filters; covariance workspace of the N > 112 kernels
@@ -396,6 +398,7 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
                 const bool fits = 16 + matr * 8 * S + static_cast<size_t>(m->fstride_r) * 8 * 4 <= static_cast<size_t>(m->max_smem_optin);
                 m->mmar_ok = fits && GT <= 4;
                 m->mmar2_ok = fits && GT >= 5;
+                m->mmarb_ok = m->mmar_ok && rl <= 2 && GT >= 2 && N + d <= 32;   // k_mmarb: + [2][R] doubles per filter for t = C b
             }
         }
     }
@@ -484,6 +487,7 @@ struct Plan {
     bool mmact = false;    // ... and P2 / update / write-back dealt out as tile slots (k_mmact)
     bool mma2 = false;     // tensor-core kernel, two warps per filter (GT 5..7)
     bool mmar = false;     // tensor-core kernel, one warp per filter, T chained through registers (GT <= 4)
+    bool mmarb = false;    // k_mmar with the N mod 8 in {1, 2} border rows / columns in DFMAs (k_mmarb; set together with mmar)
     bool mmar2 = false;    // the same with two warps per filter splitting the tile rows (GT 5..7)
     int maxf = 4;          // k_mmar2: filters per CTA the launched instantiation is compiled for
     int nb = 0;            // ... its variant: resident 4-warp CTAs per SM it is compiled for
@@ -556,6 +560,29 @@ static bool mmar_has(int GT, int NB, bool MX) {
 static cudaError_t mmar_launch_for(int GT, int NB, bool MX, const RParams& rp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
 #define X(G_, N_, M_) if (GT == G_ && NB == N_ && MX == M_) return mmar_launch<G_, N_, M_>(rp, grid, threads, smem, st);
     MMAR_VARIANTS(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+template <int GT, int NB, int RB>
+static cudaError_t mmarb_launch(const RParams& rp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    {
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&k_mmarb<GT, NB, RB>), smem);
+        if (e != cudaSuccess) return e;
+    }
+    k_mmarb<GT, NB, RB><<<grid, threads, smem, st>>>(rp);
+    return cudaGetLastError();
+}
+#define MMARB_VARIANTS(X) X(2, 4, 1) X(2, 4, 2) X(3, 4, 1) X(3, 4, 2) X(4, 3, 1) X(4, 3, 2)
+static bool mmarb_has(int GT, int NB, int RB) {
+#define X(G_, N_, R_) if (GT == G_ && NB == N_ && RB == R_) return true;
+    MMARB_VARIANTS(X)
+#undef X
+    return false;
+}
+static cudaError_t mmarb_launch_for(int GT, int NB, int RB, const RParams& rp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+#define X(G_, N_, R_) if (GT == G_ && NB == N_ && RB == R_) return mmarb_launch<G_, N_, R_>(rp, grid, threads, smem, st);
+    MMARB_VARIANTS(X)
 #undef X
     return cudaErrorInvalidValue;
 }
@@ -938,15 +965,18 @@ static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
             // measured on B200 (profiles/r01_mmar_variants.txt): 4 warps per scheduler with ~128 registers beat 7 warps
             // with 72 (spills) for every GT; GT = 4 needs 3 per scheduler to stay spill-free
             int nb = env_int("BILDK_MMAR_NB", m->GT <= 3 ? 4 : 3);
-            if (!mmar_has(m->GT, nb, m->mmar_mx)) nb = m->GT <= 3 ? 4 : 3;
+            // border kernel: selected for r = 1, GT >= 3 (N = 17, 25: +5 %, +14 %); r = 2 and GT = 2 lose against k_mmar
+            // (profiles/r02_border_variants.txt) - compiled and tested (BILDK_MMARB=2), not selected
+            pl.mmarb = m->mmarb_ok && env_int("BILDK_MMARB", 1) >= ((m->GT >= 3 && m->r_last == 1) ? 1 : 2);
+            if (pl.mmarb ? !mmarb_has(m->GT, nb, m->r_last) : !mmar_has(m->GT, nb, m->mmar_mx)) nb = m->GT <= 3 ? 4 : 3;
             const size_t matb = static_cast<size_t>(8 * m->GT) * m->LDr * 8;
-            const size_t fbytes = static_cast<size_t>(m->fstride_r) * 8;
+            const size_t fbytes = (static_cast<size_t>(m->fstride_r) + (pl.mmarb ? 16 * m->GT : 0)) * 8;
             pl.mmar = true;
             pl.nb = nb;
             pl.WPC = 4;
             pl.threads = 128;
             pl.smem = 16 + matb * m->S + fbytes * 4;
-            pl.fstride = m->fstride_r;
+            pl.fstride = static_cast<int>(fbytes / 8);
             pl.bstride = static_cast<int>(matb / 8);
             pl.tile = false;
             return pl;
@@ -1082,7 +1112,7 @@ static std::string plan_string(const bildk_model* m, const Plan& pl) {
                  m->mmar_mx ? " mean-in-extra-rows" : "", pl.FPC, pl.maxf, pl.threads, pl.smem);
     else if (pl.mmar)
         snprintf(buf, sizeof buf, "mmar (DMMA m8n8k4) GT=%d%s register-chained warp-per-filter WPC=%d CTAs/SM=%d threads=%d smem=%zu", m->GT,
-                 m->mmar_mx ? " mean-in-extra-rows" : "", pl.WPC, pl.nb, pl.threads, pl.smem);
+                 m->mmar_mx ? " mean-in-extra-rows" : (pl.mmarb ? " border-in-DFMA" : ""), pl.WPC, pl.nb, pl.threads, pl.smem);
     else if (pl.mma)
         snprintf(buf, sizeof buf, "mma (DMMA m8n8k4) GT=%d %s warp-per-filter WPC=%d threads=%d smem=%zu", m->GT,
                  m->mma_mx ? "mean-in-extra-tile" : "mean-in-padding", pl.WPC, pl.threads, pl.smem);
@@ -1220,7 +1250,8 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
             rp.WPC = pl.WPC; rp.fstride = pl.fstride; rp.r = m->r_last;
             rp.ww00 = m->wz_val[0] * m->wz_val[0]; rp.ww11 = m->wz_val[1] * m->wz_val[1]; rp.ww01 = 2.0 * m->wz_val[0] * m->wz_val[1];
             for (int e = 0; e < dstar; ++e) mmar_tables(m->GT, m->r_last, t0->ncols[e], rp.lastrow[e], rp.mrow[e]);
-            CU(mmar_launch_for(m->GT, pl.nb, m->mmar_mx, rp, grid, pl.threads, pl.smem, st));
+            if (pl.mmarb) CU(mmarb_launch_for(m->GT, pl.nb, m->r_last, rp, grid, pl.threads, pl.smem, st));
+            else CU(mmar_launch_for(m->GT, pl.nb, m->mmar_mx, rp, grid, pl.threads, pl.smem, st));
         } else if (pl.mmar2) {
             R2Params r2{};
             RParams& rp = r2.r;

@@ -135,9 +135,10 @@ def test_register_chained_kernel(N, d, noise, loops, nb, monkeypatch):
     want = ko.logl_c(*(mod[k] for k in MODEL_KEYS), x, s2, Cind, states)
     eng = engine_for(mod)
     traj = eng.trajectory(x, err)
+    monkeypatch.setenv("BILDK_MMARB", "0")               # N mod 8 in {1, 2}: the all-tensor-core kernel, not k_mmarb
     if nb:   # most resident CTAs per SM = fewest registers (fragments re-read per tile row, some spills)
         monkeypatch.setenv("BILDK_MMAR_NB", "7" if N <= 24 else "5")
-    assert traj.describe_plan(P).split()[0] == "mmar"
+    assert traj.describe_plan(P).split()[0] == "mmar" and "border" not in traj.describe_plan(P)
     assert f"CTAs/SM={(7 if N <= 24 else 5) if nb else (4 if N <= 24 else 3)}" in traj.describe_plan(P)
     got = eng.logl_st(traj, ss, thetas)
     assert rel_err(got, want) < TOL
@@ -184,6 +185,47 @@ def test_register_chained_two_warp_kernel(N, d, noise, loops, fpc, monkeypatch):
     assert rel_err(got, want) < TOL
     monkeypatch.setenv("BILDK_MMAR2", "0")               # the column-split kernel on the same inputs
     assert traj.describe_plan(P).split()[0] == "mma2"
+    assert rel_err(eng.logl_st(traj, ss, thetas), got) < 1e-12
+
+
+BORDER_CASES = [
+    # N, d, noise, loops                      k_mmarb: N mod 8 in {1, 2}, GT 2..4 - border rows / columns of C in DFMAs
+    (9, 3, 0.4, (None, [(0, -1)])),           # GT=2, r=1
+    (10, 3, 0.2, (None, [(0, -1)])),          # GT=2, r=2 (sweep size N=10)
+    (10, 4, 0.3, (None, [(0, -1)])),          # ... d=4: four mean lanes
+    (17, 1, 0.3, (None, [(0, -1)])),          # GT=3, r=1, d=1
+    (18, 2, [0.1, 0.4], (None, [(0, -1)])),   # GT=3, r=2, d*=2
+    (18, 3, 0.3, (None, [(0, -1)], [(2, 9), (5, 15, 0.5)])),   # GT=3, r=2, 3 states
+    (25, 3, 0.3, (None, [(0, -1)])),          # GT=4, r=1 (sweep size N=25)
+    (25, 3, [0.2, 0.2, 0.5], (None, [(0, -1)])),               # ... anisotropic error: sub-filters with 2 and 1 columns
+    (26, 4, 0.3, (None, [(0, -1)])),          # GT=4, r=2, d=4: lanes 26..29 carry the border means
+]
+
+
+@pytest.mark.parametrize("N,d,noise,loops", BORDER_CASES)
+def test_border_kernel(N, d, noise, loops, monkeypatch):
+    """k_mmarb (tensor cores on the 8 (GT - 1) core rows, the N mod 8 border rows / columns as two DFMA matrix-vector
+    products per frame) vs the C oracle and vs k_mmar (everything on padded 8x8 tiles) on the same inputs."""
+    rng = np.random.default_rng(377 + N)
+    mod = oracle_model(N, d=d, loops=loops)
+    T, P = 70, 37
+    x, _ = synth_traj(mod, T, rng, noise, p_nan=0.15)
+    x[0] = np.nan if N % 2 else x[0]                     # odd N: first frame missing
+    ss, thetas = random_profiles(rng, P, T, len(loops), 6)
+    err = np.broadcast_to(np.asarray(noise, dtype=float), (d,))
+    s2, Cind = ko.noise_to_s2_cind(err)
+    states = np.array([ko.st2states(s, th, T) for s, th in zip(ss, thetas)])
+    want = ko.logl_c(*(mod[k] for k in MODEL_KEYS), x, s2, Cind, states)
+    eng = engine_for(mod)
+    traj = eng.trajectory(x, err)
+    if N not in (17, 25):
+        monkeypatch.setenv("BILDK_MMARB", "2")           # compiled, but selected by default for r = 1, GT >= 3 only (elsewhere k_mmar is faster)
+    assert traj.describe_plan(P).split()[0] == "mmar" and "border-in-DFMA" in traj.describe_plan(P)
+    got = eng.logl_st(traj, ss, thetas)
+    assert rel_err(got, want) < TOL
+    assert np.array_equal(got, eng.logl_states(traj, states))
+    monkeypatch.setenv("BILDK_MMARB", "0")
+    assert "border" not in traj.describe_plan(P)
     assert rel_err(eng.logl_st(traj, ss, thetas), got) < 1e-12
 
 
@@ -279,7 +321,7 @@ def test_dense_measurement_vector():
     assert rel_err(got, want) < TOL
 
 
-@pytest.mark.parametrize("N", [15, 19, 100])   # 15: k_mma; 19: k_mmar (G added to the chained mean); 100: k_mmact
+@pytest.mark.parametrize("N", [15, 18, 19, 25, 40, 100])   # 15, 40: k_mmar / k_mmar2 with the mean in extra rows; 18, 25: k_mmarb (border means); 19: k_mmar; 100: k_mmact
 def test_external_force_mean_offset(N):
     """G != 0 (pyx:209): constant force on the chain ends."""
     rng = np.random.default_rng(6)
