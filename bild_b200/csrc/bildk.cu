@@ -965,9 +965,9 @@ static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
             // measured on B200 (profiles/r01_mmar_variants.txt): 4 warps per scheduler with ~128 registers beat 7 warps
             // with 72 (spills) for every GT; GT = 4 needs 3 per scheduler to stay spill-free
             int nb = env_int("BILDK_MMAR_NB", m->GT <= 3 ? 4 : 3);
-            // border kernel: selected for r = 1, GT >= 3 (N = 17, 25: +5 %, +14 %); r = 2 and GT = 2 lose against k_mmar
-            // (profiles/r02_border_variants.txt) - compiled and tested (BILDK_MMARB=2), not selected
-            pl.mmarb = m->mmarb_ok && env_int("BILDK_MMARB", 1) >= ((m->GT >= 3 && m->r_last == 1) ? 1 : 2);
+            // border kernel: selected for N = 17, 25 (r = 1: +20 %, +23 %) and N = 26 (r = 2, GT = 4: +8 %); N = 18 and GT = 2 lose
+            // against k_mmar (profiles/r02_border_variants.txt) - compiled and tested (BILDK_MMARB=2), not selected
+            pl.mmarb = m->mmarb_ok && env_int("BILDK_MMARB", 1) >= (((m->GT >= 3 && m->r_last == 1) || (m->GT == 4 && m->r_last == 2)) ? 1 : 2);
             if (pl.mmarb ? !mmarb_has(m->GT, nb, m->r_last) : !mmar_has(m->GT, nb, m->mmar_mx)) nb = m->GT <= 3 ? 4 : 3;
             const size_t matb = static_cast<size_t>(8 * m->GT) * m->LDr * 8;
             const size_t fbytes = (static_cast<size_t>(m->fstride_r) + (pl.mmarb ? 16 * m->GT : 0)) * 8;

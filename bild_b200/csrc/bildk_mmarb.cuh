@@ -12,14 +12,14 @@
 //     C'[core][core] = T[core][:] B_s[:][core] + Sig            (upper tiles, contraction over all N)
 // and column a = N - r + j of C' (all N rows, corner included) is two matrix-vector products in plain DFMAs, one lane per row,
 // using the symmetry of B_s and C:
-//     t_j = C b_a  (b_a = row a of B_s; also t_j[N + q] = M^T[q] . b_a = prior mean of border row a, dimension q)
+//     t_j = [C | M]^T b_a  (b_a = row a of B_s; t_j[N + q] = M[:, q] . b_a = prior mean of border row a, dimension q)
 //     C'[:, a] = B_s t_j + Sig[:, a]
 // 2 r N DFMAs per lane-row and frame instead of 2 GT tile products: N = 25: 126 DMMAs + 52 DFMAs (182 DMMAs before).
-// Measured (B200, profiles/r02_border_variants.txt): N = 25 0.674 -> 0.772 of the DMMA peak, N = 17 0.503 -> 0.529; with r = 2
-// the doubled DFMA work loses (N = 26 0.751 -> 0.714, N = 18 0.595 -> 0.486) and so does GT = 2 (N = 10: 0.33 -> 0.20, nine
-// DMMAs per frame cannot hide two dependent DFMA chains): a scalar DFMA occupies the FP64 pipe for 2 cycles but has to win
-// it against 16-cycle DMMAs of the other warps each time.  The library therefore selects this kernel for r = 1, GT >= 3 only
-// (N = 17, 25); the other instantiations are compiled for the parity tests (BILDK_MMARB=2).  The border lives in "lane = row" registers (cbv[j] = C'[lane][a_j]); lanes N .. N + ncols - 1
+// Measured (B200, profiles/r02_border_variants.txt): N = 25 0.674 -> 0.826 of the DMMA peak, N = 17 0.503 -> 0.604, N = 26
+// (r = 2) 0.751 -> 0.809; it loses at N = 18 (r = 2, GT = 3: 0.595 -> 0.563) and at GT = 2 (N = 10: 0.33 -> 0.20, nine DMMAs
+// per frame cannot hide two dependent DFMA chains): a scalar DFMA occupies the FP64 pipe for 2 cycles but has to win it
+// against 16-cycle DMMAs of the other warps each time.  The library therefore selects this kernel for N = 17, 25, 26; the
+// other instantiations are compiled for the parity tests (BILDK_MMARB=2).  The border lives in "lane = row" registers (cbv[j] = C'[lane][a_j]); lanes N .. N + ncols - 1
 // own the mean of the border rows.  The fragment layouts, the permuted last tile column, the swizzle and the update of the
 // core are those of k_mmar (bildk_mmar.cuh).
 #pragma once
@@ -27,6 +27,13 @@
 
 namespace bildk {
 
+// The two matrix-vector products read their matrix COLUMN-wise (lane = column, one row per step: 32 consecutive doubles,
+// conflict-free).  A first version read row-wise (lane = row, k contiguous: 128-bit loads with a 2-way bank conflict between rows
+// i and i + 4); ncu (profiles/r02_ncu_n25.txt) showed the shared-memory pipe 68 % busy with a quarter of its wavefronts
+// conflicts - column-wise: N = 25 0.781 -> 0.826, N = 17 0.552 -> 0.604, and r = 2 at GT = 4 now beats k_mmar too (N = 26
+// 0.751 -> 0.809).  For this the mean rides as d extra COLUMNS N .. N+d-1 of the buffer rows (padding columns of the last
+// tile, which every tensor-core operand multiplies by zero rows / columns of B_s) next to the M^T rows that the permuted tile
+// column reads.
 template <int GT, int NB, int RB>
 __global__ void __launch_bounds__(128, NB) k_mmarb(const __grid_constant__ RParams rp) {
     static_assert(GT >= 2 && GT <= 4 && (RB == 1 || RB == 2), "border kernel: N = 8 (GT - 1) + RB, GT 2..4");
@@ -103,10 +110,9 @@ __global__ void __launch_bounds__(128, NB) k_mmarb(const __grid_constant__ RPara
     const int rowi = brow ? lane : 0;
     const int fi = 4 * ((rowi >> 1) & 1);
     const int mrb = rp.mrow[e_sub][bmean ? bq : 0];
-    const int trow = brow ? lane : mrb;                           // buffer row this lane contracts with b_a in the t product
-    const int ft = 4 * ((trow >> 1) & 1);
     const int xcolb = p.cols[e_sub][bmean ? bq : 0];
-    const bool tact = brow || bmean;
+    const int lane4 = lane ^ 4;                                    // column `lane` in rows whose column bit 2 is flipped
+    const int offMc = g * LD + ((N + c4) ^ fx);                    // M[8 ti + g][q = c4] as column N + q of row 8 ti + g: + 8 ti LD
 
     double quad = 0.0, lmant = 1.0;
     int lexp = 0;
@@ -135,14 +141,13 @@ __global__ void __launch_bounds__(128, NB) k_mmarb(const __grid_constant__ RPara
         if (t > 0) {
             const double* __restrict__ Bs = Bsm + s * MAT;
             const double* __restrict__ Gs = rp.Sigm + static_cast<size_t>(R * R) * s + g * R + 2 * c4;
-            // ---------------- border, first product: t_j = [C ; M^T] b_a, a = BASE + j  (the border rows of T = B_s [C | M], pyx:206-241)
+            // ---------------- border, first product: t_j = [C | M]^T b_a, a = BASE + j  (the border rows of T = B_s [C | M], pyx:206-241)
             // Both border products stand AHEAD of the tile rows in program order (ptxas lets the second one sink behind the last
             // DMMAs on its own).  Measured alternatives (profiles/r02_border_variants.txt): pinning the second product ahead of
             // the tile rows with a warp barrier, or placing the products behind tile rows 0 and 1 so that their DFMA chains
             // interleave with DMMAs, both cost 6-7 % at N = 25 - a scalar DFMA waits behind the other warps' DMMAs in the one
             // FP64 pipe wherever it stands, and interleaving delays this warp's own DMMAs as well.
             {
-                const double* __restrict__ rowp = Cb + trow * LD;
 #pragma unroll
                 for (int j = 0; j < RB; ++j) {
                     const double* __restrict__ brp = Bs + (BASE + j) * LD;
@@ -150,28 +155,30 @@ __global__ void __launch_bounds__(128, NB) k_mmarb(const __grid_constant__ RPara
                     double ax = 0.0, ay = 0.0, az = 0.0, aw = 0.0;   // four independent chains
 #pragma unroll
                     for (int k = 0; k < KP; k += 2) {
-                        const double2 c = *reinterpret_cast<const double2*>(rowp + (k ^ ft));
-                        const double2 b = *reinterpret_cast<const double2*>(brp + (k ^ fa));
-                        if (k & 2) { az = fma(c.x, b.x, az); aw = fma(c.y, b.y, aw); }
-                        else { ax = fma(c.x, b.x, ax); ay = fma(c.y, b.y, ay); }
+                        const double2 b = *reinterpret_cast<const double2*>(brp + (k ^ fa));        // B_s[a][k], B_s[a][k+1] (broadcast)
+                        const int cc = ((k >> 1) & 1) ? lane4 : lane;                                // column `lane` of rows k, k + 1
+                        const double c0 = Cb[k * LD + cc];
+                        const double c1 = (k + 1 < BASE + RB) ? Cb[(k + 1) * LD + cc] : 0.0;
+                        if (k & 2) { az = fma(c0, b.x, az); aw = fma(c1, b.y, aw); }
+                        else { ax = fma(c0, b.x, ax); ay = fma(c1, b.y, ay); }
                     }
                     const double tj = (ax + az) + (ay + aw);
                     if (brow) tb[j * R + lane] = tj;
-                    mb[j] = tj;                       // meaningful on the mean lanes only
+                    mb[j] = tj;                       // lanes N + q: column N + q of the buffer rows is M[:, q]
                 }
             }
             __syncwarp();   // t_j complete
             // ---------------- border, second product: C'[:, a] = B_s t_j + Sig[:, a]
             {
-                const double* __restrict__ rowp = Bs + rowi * LD;
                 const double* __restrict__ sgp = rp.Sigm + static_cast<size_t>(R * R) * s + rowi * R + BASE;
 #pragma unroll
                 for (int j = 0; j < RB; ++j) {
                     double ax = __ldg(sgp + j), ay = 0.0, az = 0.0, aw = 0.0;
 #pragma unroll
                     for (int k = 0; k < KP; k += 2) {
-                        const double2 b = *reinterpret_cast<const double2*>(rowp + (k ^ fi));
                         const double2 v = *reinterpret_cast<const double2*>(tb + j * R + k);
+                        const int cc = ((k >> 1) & 1) ? lane4 : lane;                                // B_s[k][i] = B_s[i][k]: column `lane` of rows k, k + 1
+                        const double2 b = make_double2(Bs[k * LD + cc], (k + 1 < BASE + RB) ? Bs[(k + 1) * LD + cc] : 0.0);
                         if (k & 2) { az = fma(b.x, v.x, az); aw = fma(b.y, v.y, aw); }
                         else { ax = fma(b.x, v.x, ax); ay = fma(b.y, v.y, ay); }
                     }
@@ -333,6 +340,7 @@ __global__ void __launch_bounds__(128, NB) k_mmarb(const __grid_constant__ RPara
                     *reinterpret_cast<double2*>(Cb + offP + 8 * ti * LD + 8 * tj) = make_double2(v0, v1);
                 }
                 if (hasq) Cb[offM + 8 * ti] = mu[ti];
+                if (hasq) Cb[offMc + 8 * ti * LD] = mu[ti];
             }
             // border: element (i, a_j) of every row i < N (corner rows included), element (a_j, i) of the border rows for the
             // core columns i (the corner entries are written once, by their row's lane)
@@ -345,6 +353,7 @@ __global__ void __launch_bounds__(128, NB) k_mmarb(const __grid_constant__ RPara
                     if (lane < BASE) Cb[a * LD + (lane ^ fa)] = cbv[j];
                 }
                 if (bmean) Cb[mrb * LD + (a ^ (4 * ((mrb >> 1) & 1)))] = mb[j];
+                if (bmean) Cb[a * LD + ((N + bq) ^ fa)] = mb[j];
             }
         }
         __syncwarp();   // C+ / M+^T complete before the next frame's products
@@ -360,7 +369,6 @@ __global__ void __launch_bounds__(128, NB) k_mmarb(const __grid_constant__ RPara
         p.out[static_cast<size_t>(e_sub) * p.P + pidx] = -0.5 * (quad - ncols * logdet + static_cast<double>(nvalid) * ncols * LOG_2PI);
     }
 #undef UIDX
-    (void)tact;
 }
 
 }  // namespace bildk
