@@ -76,6 +76,12 @@ WORKLOADS = {
     "n18": dict(N=18, T=500, P=65536, p_nan=0.0, desc="N=18, T=500, 64k profiles"),
     "n26": dict(N=26, T=500, P=65536, p_nan=0.0, desc="N=26, T=500, 64k profiles"),
     "n36": dict(N=36, T=500, P=16384, p_nan=0.0, desc="N=36, T=500, 16384 profiles"),
+    "n60": dict(N=60, T=300, P=8192, p_nan=0.0, desc="N=60, T=300, 8192 profiles"),
+    "n64": dict(N=64, T=300, P=8192, p_nan=0.0, desc="N=64, T=300, 8192 profiles"),
+    "n72": dict(N=72, T=300, P=8192, p_nan=0.0, desc="N=72, T=300, 8192 profiles"),
+    "n80": dict(N=80, T=300, P=4096, p_nan=0.0, desc="N=80, T=300, 4096 profiles"),
+    "n96": dict(N=96, T=300, P=4096, p_nan=0.0, desc="N=96, T=300, 4096 profiles"),
+    "n104": dict(N=104, T=300, P=4096, p_nan=0.0, desc="N=104, T=300, 4096 profiles"),
     "n56": dict(N=56, T=500, P=16384, p_nan=0.0, desc="N=56, T=500, 16384 profiles"),
 }
 D_SPATIAL, DIFF, KSPRING, LOC_ERR, KMAX = 3, 1.0, 5.0, 0.3, 10

@@ -353,9 +353,12 @@ def test_no_valid_frames_and_single_frame():
     assert rel_err(eng.logl_states(traj1, np.array([[1]])), want) < TOL
 
 
-def test_multi_trajectory_batch():
-    rng = np.random.default_rng(11)
-    N, d = 20, 3
+@pytest.mark.parametrize("N", [20, 25, 16, 40, 50, 100])   # k_mmar, k_mmarb, k_mmar MX, k_mmar2 MX, k_mmar2, k_mmact
+def test_multi_trajectory_batch(N):
+    """Fused multi-trajectory launch (bildk_logl_runs_multi: trajectories of different lengths and batch sizes in one grid,
+    CTA -> trajectory map) against the C oracle, for every kernel family the dataset driver can meet."""
+    rng = np.random.default_rng(11 + N)
+    d = 3
     mod = oracle_model(N, d=d)
     eng = engine_for(mod)
     s2, Cind = ko.noise_to_s2_cind([0.3] * d)
