@@ -23,12 +23,15 @@ struct R2Params {
     int FPC2;   // filters per CTA (two warps each)
 };
 
-template <int GT>
+// NW = warps per filter: 2 for GT 5..7; 4 for GT = 8 (N = 57..64), where the four COMPLEMENTARY row pairs (ti, GT-1-ti) cost
+// exactly the same - 2 GTC tile products in P1 and GT + 1 in P2 each - and the four warps of a filter sit on the four schedulers.
+template <int GT, int NW = 2>
 struct Mmar2Rows {
-    // role (0 / 1) that owns tile-row block ti; cost of a row = GT (P1) + GT - ti (P2) tile products
+    // role that owns tile-row block ti; cost of a row = GT (P1) + GT - ti (P2) tile products
     // (with the mean in an extra tile column, MX, every row costs one more: the same splits stay the balanced ones)
     __host__ __device__ static constexpr int role(int ti) {
-        return GT == 7 ? (ti <= 2 ? 0 : 1)                       // 14+13+12 = 39 | 11+10+9+8 = 38      MX: 42 | 42
+        return NW == 4 ? (ti < GT - 1 - ti ? ti : GT - 1 - ti)   // GT = 8: rows {0,7} {1,6} {2,5} {3,4}: 25 tile products each (MX: 27)
+             : GT == 7 ? (ti <= 2 ? 0 : 1)                       // 14+13+12 = 39 | 11+10+9+8 = 38      MX: 42 | 42
              : GT == 6 ? ((ti == 0 || ti == 3 || ti == 5) ? 0 : 1)   // 12+9+7 = 28 | 11+10+8 = 29          MX: 31 | 32
              : (ti <= 1 ? 0 : 1);                                // GT = 5: 10+9 = 19 | 8+7+6 = 21      MX: 21 | 24
     }
@@ -58,11 +61,14 @@ struct Mmar2Rows {
     }
 };
 
-template <int GT, int ROLE, bool MX>
+template <int NW>
+__device__ __forceinline__ void filter_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(32 * NW) : "memory"); }
+
+template <int GT, int ROLE, bool MX, int NW = 2>
 __device__ __forceinline__ void mmar2_run(const RParams& rp, const double* __restrict__ Bsm, double* __restrict__ Cb, int pidx, int tjx,
                                           int e_sub, int barid, int lane) {
     using G = MmarGeom<GT, MX>;
-    using RW = Mmar2Rows<GT>;
+    using RW = Mmar2Rows<GT, NW>;
     constexpr int R = G::R, LD = G::LD, MAT = G::MAT, MATC = G::MATC;
     constexpr int KT = G::KT, GTC = G::GTC;
     constexpr int NACC = RW::nacc(ROLE), NROW = RW::nrows(ROLE);
@@ -241,7 +247,7 @@ __device__ __forceinline__ void mmar2_run(const RParams& rp, const double* __res
             }
             if (OWN_LAST && g == cj1) mpub[4 + c4] = mu[RIDX(GT - 1)];
         }
-        pair_sync(barid);   // both warps are done reading C / M^T; published columns and mean rows visible
+        filter_sync<NW>(barid);   // both warps are done reading C / M^T; published columns and mean rows visible
 
         if (is_valid) {
             // C' w once per row (bildk_mmar.cuh): each warp combines the two published columns into its own copy of the vector
@@ -295,7 +301,7 @@ __device__ __forceinline__ void mmar2_run(const RParams& rp, const double* __res
                 if (hasq) Cb[offM + 8 * ti] = mu[RIDX(ti)];
             }
         }
-        pair_sync(barid);   // C+ / M+^T complete before the next frame's fragment loads
+        filter_sync<NW>(barid);   // C+ / M+^T complete before the next frame's fragment loads
     }
 
     if (ROLE == 1) {
@@ -315,8 +321,8 @@ __device__ __forceinline__ void mmar2_run(const RParams& rp, const double* __res
 }
 
 // MAXF: filters per CTA the kernel is compiled for (registers per thread = 65536 / (64 MAXF)).
-template <int GT, int MAXF, bool MX = false>
-__global__ void __launch_bounds__(64 * MAXF, 1) k_mmar2(const __grid_constant__ R2Params rp2) {
+template <int GT, int MAXF, bool MX = false, int NW = 2>
+__global__ void __launch_bounds__(32 * NW * MAXF, 1) k_mmar2(const __grid_constant__ R2Params rp2) {
     constexpr int MAT = MmarGeom<GT, MX>::MAT;
     const RParams& rp = rp2.r;
     const KParams& p = rp.k;
@@ -324,8 +330,9 @@ __global__ void __launch_bounds__(64 * MAXF, 1) k_mmar2(const __grid_constant__ 
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
     double* Bsm = reinterpret_cast<double*>(smem_raw + 16);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int fl = wid >> 1;                          // filter within the CTA
-    const int role = (wid & 1) ^ ((fl >> 1) & 1);     // roles alternate so that every scheduler holds warps of either role
+    const int fl = wid / NW;                          // filter within the CTA
+    // NW = 2: roles alternate so that every scheduler holds warps of either role; NW = 4: warp w of a filter runs on scheduler w
+    const int role = NW == 2 ? ((wid & 1) ^ ((fl >> 1) & 1)) : (wid % NW);
     const int tjx = p.cta_traj ? p.cta_traj[blockIdx.x] : 0;
     const int first = p.cta_first ? p.cta_first[blockIdx.x] : blockIdx.x * rp2.FPC2;
     const int pend = p.traj_first[tjx + 1];
@@ -347,11 +354,13 @@ __global__ void __launch_bounds__(64 * MAXF, 1) k_mmar2(const __grid_constant__ 
     if (!alive) return;   // both warps of a pair leave together; the named barriers below are per pair
     double* Cb = Bsm + MAT * p.S + fl * rp.fstride;
     // padding columns, zero rows and M^T rows must start finite / zero: the pair clears its filter's buffer
-    for (int i = (wid & 1) * 32 + lane; i < rp.fstride; i += 64) Cb[i] = 0.0;
-    pair_sync(1 + fl);
+    for (int i = (wid % NW) * 32 + lane; i < rp.fstride; i += 32 * NW) Cb[i] = 0.0;
+    filter_sync<NW>(1 + fl);
     mbar_wait(mbar, 0);
-    if (role == 0) mmar2_run<GT, 0, MX>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, 1 + fl, lane);
-    else mmar2_run<GT, 1, MX>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, 1 + fl, lane);
+    if (role == 0) mmar2_run<GT, 0, MX, NW>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, 1 + fl, lane);
+    else if (NW == 2 || role == 1) mmar2_run<GT, 1, MX, NW>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, 1 + fl, lane);
+    else if (role == 2) mmar2_run<GT, (NW == 4 ? 2 : 0), MX, NW>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, 1 + fl, lane);
+    else mmar2_run<GT, (NW == 4 ? 3 : 0), MX, NW>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, 1 + fl, lane);
 }
 
 }  // namespace bildk

@@ -41,8 +41,8 @@ CASES = [
     (7, 1, 30, 9, 0.0, 0.5, (None, [(0, -1)]), 2),              # tiny
     (3, 3, 25, 6, 0.0, 0.5, (None, [(0, -1)]), 2),              # N == d
     (2, 3, 25, 6, 0.1, 0.5, (None, [(0, -1, 0.5)]), 2),         # N < d: catch-all kernel
-    (60, 3, 30, 4, 0.1, 0.3, (None, [(0, -1)]), 4),             # GT=8: one CTA per filter, one warp per tile column
-    (64, 3, 20, 3, 0.0, 0.3, (None, [(0, -1)]), 3),             # GT=8, no padding room: mean in an extra tile column
+    (60, 3, 30, 4, 0.1, 0.3, (None, [(0, -1)]), 4),             # GT=8: k_mmar2 with four warps per filter
+    (64, 3, 20, 3, 0.0, 0.3, (None, [(0, -1)]), 3),             # GT=8, r=8: k_mmar2 (four warps), mean in extra rows
     (68, 3, 24, 4, 0.1, 0.3, (None, [(0, -1)]), 3),             # GT=9 = 4k+1 (k_mmact: 12 warps, three P1 helper warps, tile segments)
     (70, 3, 24, 4, 0.1, 0.3, (None, [(0, -1)]), 3),             # GT=9, no padding room for the mean: k_mmac with an extra tile column
     (108, 3, 12, 2, 0.1, 0.3, (None, [(0, -1)]), 2),            # GT=14 (k_mmact without helpers, 7 slots per warp)
@@ -272,6 +272,48 @@ def test_register_chained_kernels_mean_in_extra_rows(N, d, noise, loops, kernel,
     assert np.array_equal(got, eng.logl_states(traj, states))
     monkeypatch.setenv("BILDK_MMAR_MX", "0")             # the older kernels on the same inputs
     assert traj.describe_plan(P).split()[0] in ("mma", "mma2")
+    assert rel_err(eng.logl_st(traj, ss, thetas), got) < 1e-12
+
+
+FOUR_WARP_CASES = [
+    # N, d, noise, loops                      k_mmar2 with FOUR warps per filter (GT = 8: complementary row pairs {0,7} {1,6} {2,5} {3,4})
+    (57, 3, 0.3, (None, [(0, -1)])),          # r=1
+    (58, 2, [0.1, 0.4], (None, [(0, -1)])),   # r=2, d*=2
+    (60, 4, 0.4, (None, [(0, -1)])),          # r=4, d=4: every spare row carries a mean column
+    (60, 3, 0.3, (None, [(0, -1)], [(5, 30), (12, 44, 0.5)])),   # r=4, 3 states: three propagators resident -> fewer filters per CTA
+    (61, 3, 0.3, (None, [(0, -1)])),          # r=5: mean in extra rows
+    (63, 1, 0.3, (None, [(0, -1)])),          # r=7, d=1
+    (64, 3, 0.3, (None, [(0, -1)])),          # r=8
+    (64, 3, [0.2, 0.2, 0.5], (None, [(0, -1)])),                 # ... anisotropic error
+]
+
+
+@pytest.mark.parametrize("fpc", [0, 1, 2], ids=["default", "one-filter-per-cta", "two-filters"])
+@pytest.mark.parametrize("N,d,noise,loops", FOUR_WARP_CASES)
+def test_register_chained_four_warp_kernel(N, d, noise, loops, fpc, monkeypatch):
+    """k_mmar2 at GT = 8 (N = 57..64): the tile rows of a filter split over four warps, vs the C oracle and vs k_mmac (one warp
+    per tile column, T through shared memory) on the same inputs."""
+    rng = np.random.default_rng(477 + N)
+    mod = oracle_model(N, d=d, loops=loops)
+    T, P = 40, 19
+    x, _ = synth_traj(mod, T, rng, noise, p_nan=0.15)
+    x[0] = np.nan if N % 2 else x[0]                     # odd N: first frame missing
+    ss, thetas = random_profiles(rng, P, T, len(loops), 6)
+    err = np.broadcast_to(np.asarray(noise, dtype=float), (d,))
+    s2, Cind = ko.noise_to_s2_cind(err)
+    states = np.array([ko.st2states(s, th, T) for s, th in zip(ss, thetas)])
+    want = ko.logl_c(*(mod[k] for k in MODEL_KEYS), x, s2, Cind, states)
+    eng = engine_for(mod)
+    traj = eng.trajectory(x, err)
+    if fpc:
+        monkeypatch.setenv("BILDK_FPC2", str(fpc))
+    plan = traj.describe_plan(P)
+    assert plan.split()[0] == "mmar2" and "four-warps-per-filter" in plan and ("mean-in-extra-rows" in plan) == (N > 60)
+    got = eng.logl_st(traj, ss, thetas)
+    assert rel_err(got, want) < TOL
+    assert np.array_equal(got, eng.logl_states(traj, states))
+    monkeypatch.setenv("BILDK_MMAR2", "0")               # one CTA per filter, one warp per tile column
+    assert traj.describe_plan(P).split()[0] == "mmac"
     assert rel_err(eng.logl_st(traj, ss, thetas), got) < 1e-12
 
 
