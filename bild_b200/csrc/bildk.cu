@@ -381,7 +381,7 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
             // register-chained kernels: M^T rides in the spare rows of the last tile-row block (rl <= 4: room for d <= 4 mean
             // rows and a zero row) or, for rl >= 5, in an extra row block of the filter buffer ("MX", bildk_mmar.cuh)
             const int rl = N - 8 * (GT - 1);
-            if (GT <= 8 && rl >= 1 && rl <= 8 && d <= 4 && m->wz_idx[0] == 0 && m->wz_idx[1] == N - 1 && N >= 2) {   // end-to-end measurement only
+            if ((GT <= 8 || GT == 13) && rl >= 1 && rl <= 8 && d <= 4 && m->wz_idx[0] == 0 && m->wz_idx[1] == N - 1 && N >= 2) {   // end-to-end measurement only
                 const int R = 8 * GT;
                 const int LDr = (R % 16 == 8) ? R : R + 8;
                 const size_t matr = static_cast<size_t>(R) * LDr;
@@ -394,8 +394,10 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
                 if ((rc = upload(&m->dBr, pad.data(), S * matr))) return rc;
                 m->r_last = rl; m->LDr = LDr;
                 m->mmar_mx = rl > 4;
-                m->fstride_r = static_cast<int>(matr) + (m->mmar_mx ? 8 * LDr : 0) + 2 * R + 8 + (GT >= 8 ? 4 * R : GT >= 5 ? 2 * R : 0);   // k_mmar2: one C' w vector per warp
-                const bool fits = 16 + matr * 8 * S + static_cast<size_t>(m->fstride_r) * 8 * (GT >= 8 ? 2 : 4) <= static_cast<size_t>(m->max_smem_optin);
+                m->fstride_r = static_cast<int>(matr) + (m->mmar_mx ? 8 * LDr : 0) + 2 * R + 8 + (GT == 13 ? 8 * R : GT >= 8 ? 4 * R : GT >= 5 ? 2 * R : 0);   // k_mmar2 / k_mmar8: one C' w vector per warp
+                // GT = 13 (k_mmar8): one filter per CTA next to ONE resident propagator
+                const bool fits = GT == 13 ? 16 + matr * 8 + static_cast<size_t>(m->fstride_r) * 8 <= static_cast<size_t>(m->max_smem_optin)
+                                           : 16 + matr * 8 * S + static_cast<size_t>(m->fstride_r) * 8 * (GT >= 8 ? 2 : 4) <= static_cast<size_t>(m->max_smem_optin);
                 m->mmar_ok = fits && GT <= 4;
                 m->mmar2_ok = fits && GT >= 5;
                 m->mmarb_ok = m->mmar_ok && rl <= 2 && GT >= 2 && N + d <= 32;   // k_mmarb: + [2][R] doubles per filter for t = C b
@@ -490,6 +492,7 @@ struct Plan {
     bool mmarb = false;    // k_mmar with the N mod 8 in {1, 2} border rows / columns in DFMAs (k_mmarb; set together with mmar)
     bool mmar2 = false;    // the same with two warps per filter splitting the tile rows (GT 5..7)
     int maxf = 4;          // k_mmar2: filters per CTA the launched instantiation is compiled for
+    bool mmar8 = false;    // k_mmar8 (GT = 13): one filter per CTA, eight warps (set together with mmar2)
     int nb = 0;            // ... its variant: resident 4-warp CTAs per SM it is compiled for
     unsigned char colmap[40] = {0};
     int WPC = 0;
@@ -622,6 +625,16 @@ static cudaError_t mmar2_launch_for(int GT, int MAXF, bool MX, const R2Params& r
     MMAR2_VARIANTS(X)
 #undef X
     return cudaErrorInvalidValue;
+}
+
+template <int GT, bool MX>
+static cudaError_t mmar8_launch(const R2Params& rp, dim3 grid, size_t smem, cudaStream_t st) {
+    {
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&k_mmar8<GT, MX>), smem);
+        if (e != cudaSuccess) return e;
+    }
+    k_mmar8<GT, MX><<<grid, 256, smem, st>>>(rp);
+    return cudaGetLastError();
 }
 
 // Rows of the last tile-row block that carry M^T (and one all-zero row), placed so that the B-fragment loads of the
@@ -809,7 +822,23 @@ static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
     Plan pl{};
     {
         const char* force0 = getenv("BILDK_KERNEL");
-        if (m->mmar2_ok && !force0 && !env_int("BILDK_FORCE_GENERIC", 0) && env_int("BILDK_MMAR2", 1) && (!m->mmar_mx || env_int("BILDK_MMAR_MX", 1))) {
+        if (m->mmar2_ok && m->GT == 13 && !force0 && !env_int("BILDK_FORCE_GENERIC", 0) && env_int("BILDK_MMAR8", 1)) {
+            // k_mmar8: one filter per CTA, eight warps, one resident propagator
+            const size_t matb = static_cast<size_t>(8 * m->GT) * m->LDr * 8;
+            const size_t fbytes = static_cast<size_t>(m->fstride_r) * 8;
+            pl.mmar2 = true;
+            pl.mmar8 = true;
+            pl.maxf = 1;
+            pl.tile = false;
+            pl.FPC = 1;
+            pl.WPC = 1;
+            pl.threads = 256;
+            pl.smem = 16 + matb + fbytes;
+            pl.fstride = m->fstride_r;
+            pl.bstride = static_cast<int>(matb / 8);
+            return pl;
+        }
+        if (m->mmar2_ok && m->GT <= 8 && !force0 && !env_int("BILDK_FORCE_GENERIC", 0) && env_int("BILDK_MMAR2", 1) && (!m->mmar_mx || env_int("BILDK_MMAR_MX", 1))) {
             const size_t matb = static_cast<size_t>(8 * m->GT) * m->LDr * 8;
             const size_t fbytes = static_cast<size_t>(m->fstride_r) * 8;
             const int maxf = mmar2_maxf(m->GT, m->mmar_mx);
@@ -1114,6 +1143,9 @@ static std::string plan_string(const bildk_model* m, const Plan& pl) {
         snprintf(buf, sizeof buf, "%s (DMMA m8n8k4) GT=%d %s cta-per-filter %s%s B=%s threads=%d smem=%zu", pl.mmact ? "mmact" : "mmac", m->GT,
                  m->mma_mx ? "mean-in-extra-tile" : "mean-in-padding", pl.mmact ? "tile-slots-per-warp" : "warp-per-tile-column",
                  pl.nhelp ? " +3-P1-helper-warps" : "", pl.b_all ? "all" : "one", pl.threads, pl.smem);
+    else if (pl.mmar8)
+        snprintf(buf, sizeof buf, "mmar8 (DMMA m8n8k4) GT=%d%s register-chained cta-per-filter eight-warps (tile rows split) B=one threads=%d smem=%zu", m->GT,
+                 m->mmar_mx ? " mean-in-extra-rows" : "", pl.threads, pl.smem);
     else if (pl.mmar2)
         snprintf(buf, sizeof buf, "mmar2 (DMMA m8n8k4) GT=%d%s register-chained %s-warps-per-filter (tile rows split) FPC=%d of %d threads=%d smem=%zu", m->GT,
                  m->mmar_mx ? " mean-in-extra-rows" : "", m->GT >= 8 ? "four" : "two", pl.FPC, pl.maxf, pl.threads, pl.smem);
@@ -1141,7 +1173,7 @@ extern "C" const char* bildk_describe_plan(bildk_traj_t t, int P) {
 extern "C" int bildk_debug_tables(int kernel, int GT, int r, int ncols, unsigned char* out) {
     if (!out) return fail(BILDK_EINVAL, "out is NULL");
     if (kernel == 0) {
-        if (GT < 1 || GT > 8 || r < 1 || r > 8 || ncols < 1 || ncols > 4) return fail(BILDK_EINVAL, "k_mmar tables need GT in 1..8, r in 1..8, ncols in 1..4");
+        if (GT < 1 || (GT > 8 && GT != 13) || r < 1 || r > 8 || ncols < 1 || ncols > 4) return fail(BILDK_EINVAL, "k_mmar tables need GT in 1..8 or 13, r in 1..8, ncols in 1..4");
         mmar_tables(GT, r, ncols, out, out + 8);
         return 12;
     }
@@ -1268,7 +1300,12 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
             rp.ww00 = m->wz_val[0] * m->wz_val[0]; rp.ww11 = m->wz_val[1] * m->wz_val[1]; rp.ww01 = 2.0 * m->wz_val[0] * m->wz_val[1];
             for (int e = 0; e < dstar; ++e) mmar_tables(m->GT, m->r_last, t0->ncols[e], rp.lastrow[e], rp.mrow[e]);
             r2.FPC2 = pl.FPC;
-            CU(mmar2_launch_for(m->GT, pl.maxf, m->mmar_mx, r2, grid, pl.threads, pl.smem, st));
+            if (pl.mmar8) {
+                if (m->mmar_mx) CU((mmar8_launch<13, true>(r2, grid, pl.smem, st)));
+                else CU((mmar8_launch<13, false>(r2, grid, pl.smem, st)));
+            } else {
+                CU(mmar2_launch_for(m->GT, pl.maxf, m->mmar_mx, r2, grid, pl.threads, pl.smem, st));
+            }
         } else if (pl.mma2) {
             M2Params m2{};
             MParams& mp = m2.m;

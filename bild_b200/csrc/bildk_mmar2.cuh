@@ -29,44 +29,81 @@ template <int GT, int NW = 2>
 struct Mmar2Rows {
     // role that owns tile-row block ti; cost of a row = GT (P1) + GT - ti (P2) tile products
     // (with the mean in an extra tile column, MX, every row costs one more: the same splits stay the balanced ones)
+    // NW = 8 (GT = 13, N = 97..104; one filter per CTA, warp w on scheduler w % 4): rows dealt out so that the four schedulers
+    // carry 65 | 64 | 63 | 68 tile products (MX: 68 | 67 | 66 | 72) - roles {0,12} {3,9} {4,6} {7,11} | {1} {2} {5} {8,10}
     __host__ __device__ static constexpr int role(int ti) {
-        return NW == 4 ? (ti < GT - 1 - ti ? ti : GT - 1 - ti)   // GT = 8: rows {0,7} {1,6} {2,5} {3,4}: 25 tile products each (MX: 27)
+        return NW == 8 ? ((ti == 0 || ti == 12) ? 0 : (ti == 3 || ti == 9) ? 1 : (ti == 4 || ti == 6) ? 2 : (ti == 7 || ti == 11) ? 3
+                          : ti == 1 ? 4 : ti == 2 ? 5 : ti == 5 ? 6 : 7)
+             : NW == 4 ? (ti < GT - 1 - ti ? ti : GT - 1 - ti)   // GT = 8: rows {0,7} {1,6} {2,5} {3,4}: 25 tile products each (MX: 27)
              : GT == 7 ? (ti <= 2 ? 0 : 1)                       // 14+13+12 = 39 | 11+10+9+8 = 38      MX: 42 | 42
              : GT == 6 ? ((ti == 0 || ti == 3 || ti == 5) ? 0 : 1)   // 12+9+7 = 28 | 11+10+8 = 29          MX: 31 | 32
              : (ti <= 1 ? 0 : 1);                                // GT = 5: 10+9 = 19 | 8+7+6 = 21      MX: 21 | 24
     }
+    // NW = 8: closed forms (a role owns one or two rows).  The loops below fold to constants for two and four roles, but with
+    // thirteen rows and eight roles the optimiser gave up on them: run-time indexed accumulators in local memory, jump tables,
+    // a 40-minute compilation and a kernel 30x slower than the one it was to replace.
+    __host__ __device__ static constexpr int first8(int r) { return r == 0 ? 0 : r == 1 ? 3 : r == 2 ? 4 : r == 3 ? 7 : r == 4 ? 1 : r == 5 ? 2 : r == 6 ? 5 : 8; }
+    __host__ __device__ static constexpr int second8(int r) { return r == 0 ? 12 : r == 1 ? 9 : r == 2 ? 6 : r == 3 ? 11 : r == 7 ? 10 : -1; }
     __host__ __device__ static constexpr int nacc(int r) {          // upper tiles owned by role r
+        if (NW == 8) return (GT - first8(r)) + (second8(r) >= 0 ? GT - second8(r) : 0);
         int n = 0;
         for (int ti = 0; ti < GT; ++ti) if (role(ti) == r) n += GT - ti;
         return n;
     }
     __host__ __device__ static constexpr int nrows(int r) {
+        if (NW == 8) return second8(r) >= 0 ? 2 : 1;
         int n = 0;
         for (int ti = 0; ti < GT; ++ti) if (role(ti) == r) ++n;
         return n;
     }
     __host__ __device__ static constexpr int first(int r) {          // lowest row of role r
+        if (NW == 8) return first8(r);
         for (int ti = 0; ti < GT; ++ti) if (role(ti) == r) return ti;
         return GT;
     }
     __host__ __device__ static constexpr int aidx(int ti, int tj) {  // accumulator slot of upper tile (ti, tj) within its owner
+        if (NW == 8) return (ti == first8(role(ti)) ? 0 : GT - first8(role(ti))) + tj - ti;
         int n = 0;
         for (int t = 0; t < ti; ++t) if (role(t) == role(ti)) n += GT - t;
         return n + tj - ti;
     }
     __host__ __device__ static constexpr int ridx(int ti) {          // slot of row ti within its owner (mu, kr)
+        if (NW == 8) return ti == first8(role(ti)) ? 0 : 1;
         int n = 0;
         for (int t = 0; t < ti; ++t) if (role(t) == role(ti)) ++n;
         return n;
     }
 };
 
+// one k-tile of P1 for this warp's tile rows: the GTC fragments of [C | M] are loaded once and serve all of them
+template <int GT, int ROLE, bool MX, int NW>
+__device__ __forceinline__ void mmar2_p1_ktile(double (&Tt)[Mmar2Rows<GT, NW>::nrows(ROLE)][MmarGeom<GT, MX>::GTC][2], const double* __restrict__ Bs,
+                                               const double* __restrict__ Cb, int offP, int offLP, int kt) {
+    using RW = Mmar2Rows<GT, NW>;
+    constexpr int LD = MmarGeom<GT, MX>::LD, GTC = MmarGeom<GT, MX>::GTC;
+    double2 b[GTC];
+#pragma unroll
+    for (int tj = 0; tj < GTC; ++tj)
+        b[tj] = *reinterpret_cast<const double2*>(tj < GTC - 1 ? Cb + offP + 8 * tj * LD + 8 * kt : Cb + offLP + 8 * kt);
+#pragma unroll
+    for (int ti = 0; ti < GT; ++ti) {
+        if (RW::role(ti) != ROLE) continue;
+        const double2 a = *reinterpret_cast<const double2*>(Bs + offP + 8 * ti * LD + 8 * kt);
+#pragma unroll
+        for (int tj = 0; tj < GTC; ++tj) dmma884(Tt[RW::ridx(ti)][tj], a.x, b[tj].x);
+#pragma unroll
+        for (int tj = 0; tj < GTC; ++tj) dmma884(Tt[RW::ridx(ti)][tj], a.y, b[tj].y);
+    }
+}
+
 template <int NW>
 __device__ __forceinline__ void filter_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(32 * NW) : "memory"); }
 
-template <int GT, int ROLE, bool MX, int NW = 2>
-__device__ __forceinline__ void mmar2_run(const RParams& rp, const double* __restrict__ Bsm, double* __restrict__ Cb, int pidx, int tjx,
-                                          int e_sub, int barid, int lane) {
+// BONE: ONE propagator resident in shared memory (two do not fit next to the filter for N >= 89); it is swapped by TMA when the
+// profile changes state (all readers of the old one have passed the barrier that ends the previous frame).
+template <int GT, int ROLE, bool MX, int NW = 2, bool BONE = false>
+__device__ __forceinline__ void mmar2_run(const RParams& rp, double* __restrict__ Bsm, double* __restrict__ Cb, int pidx, int tjx,
+                                          int e_sub, int barid, int lane, uint64_t* mbar = nullptr) {
     using G = MmarGeom<GT, MX>;
     using RW = Mmar2Rows<GT, NW>;
     constexpr int R = G::R, LD = G::LD, MAT = G::MAT, MATC = G::MATC;
@@ -120,6 +157,8 @@ __device__ __forceinline__ void mmar2_run(const RParams& rp, const double* __res
 
     double acc[NACC][2];
     double mu[NROW];
+    int s_loaded = -1;
+    uint32_t bphase = 0;
 
     for (int t = 0; t < T; ++t) {
         while (t >= next_sw) {
@@ -130,8 +169,14 @@ __device__ __forceinline__ void mmar2_run(const RParams& rp, const double* __res
         if ((t & 31) == 0) vword = __ldg(vbits + (t >> 5));
         const bool is_valid = (vword >> (t & 31)) & 1u;
 
+        if (BONE && t > 0 && s != s_loaded) {   // the same decision in every warp of the filter
+            if (ROLE == 0 && lane == 0) tma_stage(Bsm, rp.Br + static_cast<size_t>(MAT) * s, MAT * sizeof(double), mbar);
+            mbar_wait(mbar, bphase);
+            bphase ^= 1;
+            s_loaded = s;
+        }
         if (t > 0) {
-            const double* __restrict__ Bs = Bsm + s * MAT;
+            const double* __restrict__ Bs = BONE ? Bsm : Bsm + s * MAT;
             const double* __restrict__ Gs = rp.Sigm + static_cast<size_t>(R * R) * s + g * R + 2 * c4;
             // ---------------- P1, this warp's tile-row blocks: T[ti][:] = B_s[ti][:] [C | M]   (MSRouse_logL.pyx:206-241)
             // k-tile outermost: the GT fragments of [C | M] of a k-tile are loaded once and serve all of this warp's rows
@@ -140,21 +185,12 @@ __device__ __forceinline__ void mmar2_run(const RParams& rp, const double* __res
             for (int r = 0; r < NROW; ++r)
 #pragma unroll
                 for (int tj = 0; tj < GTC; ++tj) Tt[r][tj][0] = Tt[r][tj][1] = 0.0;
+            if constexpr (NW == 8) {   // eight roles: the k-tile loop of P1 stays rolled (code size; T is indexed by tile column only)
+#pragma unroll 1
+                for (int kt = 0; kt < KT; ++kt) mmar2_p1_ktile<GT, ROLE, MX, NW>(Tt, Bs, Cb, offP, offLP, kt);
+            } else {
 #pragma unroll
-            for (int kt = 0; kt < KT; ++kt) {
-                double2 b[GTC];
-#pragma unroll
-                for (int tj = 0; tj < GTC; ++tj)
-                    b[tj] = *reinterpret_cast<const double2*>(tj < GTC - 1 ? Cb + offP + 8 * tj * LD + 8 * kt : Cb + offLP + 8 * kt);
-#pragma unroll
-                for (int ti = 0; ti < GT; ++ti) {
-                    if (!MINE(ti)) continue;
-                    const double2 a = *reinterpret_cast<const double2*>(Bs + offP + 8 * ti * LD + 8 * kt);
-#pragma unroll
-                    for (int tj = 0; tj < GTC; ++tj) dmma884(Tt[RIDX(ti)][tj], a.x, b[tj].x);
-#pragma unroll
-                    for (int tj = 0; tj < GTC; ++tj) dmma884(Tt[RIDX(ti)][tj], a.y, b[tj].y);
-                }
+                for (int kt = 0; kt < KT; ++kt) mmar2_p1_ktile<GT, ROLE, MX, NW>(Tt, Bs, Cb, offP, offLP, kt);
             }
             if constexpr (!MX) {
                 double b[GT];
@@ -361,6 +397,45 @@ __global__ void __launch_bounds__(32 * NW * MAXF, 1) k_mmar2(const __grid_consta
     else if (NW == 2 || role == 1) mmar2_run<GT, 1, MX, NW>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, 1 + fl, lane);
     else if (role == 2) mmar2_run<GT, (NW == 4 ? 2 : 0), MX, NW>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, 1 + fl, lane);
     else mmar2_run<GT, (NW == 4 ? 3 : 0), MX, NW>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, 1 + fl, lane);
+}
+
+// k_mmar8 - the register-chained scheme for GT = 13 (N = 97..104; BASELINE configs[2] N = 100): ONE filter per CTA, eight warps,
+// the tile rows dealt out so that the four schedulers carry (almost) equal DMMA counts (Mmar2Rows<GT, 8>), one resident
+// propagator swapped by TMA at a state switch.  Against k_mmact (one CTA per filter as well, T through shared memory, the
+// phases separated by CTA barriers; tensor pipe 68 % busy): no barrier between the two products, two CTA barriers per frame, a
+// third of the shared-memory traffic.
+template <int GT, int ROLE, bool MX>
+__device__ __forceinline__ void mmar8_role(const RParams& rp, double* __restrict__ Bsm, double* __restrict__ Cb, int pidx, int tjx, int e_sub,
+                                        int lane, uint64_t* mbar) {
+    mmar2_run<GT, ROLE, MX, 8, true>(rp, Bsm, Cb, pidx, tjx, e_sub, 1, lane, mbar);
+}
+
+template <int GT, bool MX>
+__global__ void __launch_bounds__(256, 1) k_mmar8(const __grid_constant__ R2Params rp2) {
+    constexpr int MAT = MmarGeom<GT, MX>::MAT;
+    const RParams& rp = rp2.r;
+    const KParams& p = rp.k;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
+    double* Bsm = reinterpret_cast<double*>(smem_raw + 16);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tjx = p.cta_traj ? p.cta_traj[blockIdx.x] : 0;
+    const int pidx = p.cta_first ? p.cta_first[blockIdx.x] : blockIdx.x;
+    if (pidx >= p.traj_first[tjx + 1]) return;
+    if (tid == 0) mbar_init(mbar, 1);
+    double* Cb = Bsm + MAT;
+    for (int i = tid; i < rp.fstride; i += 256) Cb[i] = 0.0;   // padding columns, zero rows and M^T rows must start finite / zero
+    __syncthreads();
+    switch (wid) {   // warp w runs on scheduler w % 4: roles w and w + 4 share one
+        case 0: mmar8_role<GT, 0, MX>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, lane, mbar); break;
+        case 1: mmar8_role<GT, 1, MX>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, lane, mbar); break;
+        case 2: mmar8_role<GT, 2, MX>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, lane, mbar); break;
+        case 3: mmar8_role<GT, 3, MX>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, lane, mbar); break;
+        case 4: mmar8_role<GT, 4, MX>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, lane, mbar); break;
+        case 5: mmar8_role<GT, 5, MX>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, lane, mbar); break;
+        case 6: mmar8_role<GT, 6, MX>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, lane, mbar); break;
+        default: mmar8_role<GT, 7, MX>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, lane, mbar); break;
+    }
 }
 
 }  // namespace bildk

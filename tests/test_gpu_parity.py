@@ -47,7 +47,7 @@ CASES = [
     (70, 3, 24, 4, 0.1, 0.3, (None, [(0, -1)]), 3),             # GT=9, no padding room for the mean: k_mmac with an extra tile column
     (108, 3, 12, 2, 0.1, 0.3, (None, [(0, -1)]), 2),            # GT=14 (k_mmact without helpers, 7 slots per warp)
     (96, 2, 16, 3, 0.2, 0.3, (None, [(0, -1)], [(10, 50)]), 3), # GT=12, 3 states: single resident propagator, TMA swaps
-    (100, 2, 14, 3, 0.2, [0.2, 0.4], (None, [(0, -1)], [(10, 50)]), 3),   # GT=13 = 4k+1 (k_mmact: slots), 3 states, d*=2
+    (100, 2, 14, 3, 0.2, [0.2, 0.4], (None, [(0, -1)], [(10, 50)]), 3),   # GT=13: k_mmar8 (eight warps, TMA propagator swaps), 3 states, d*=2
     (110, 3, 12, 2, 0.0, 0.3, (None, [(0, -1)]), 2),            # GT=14
     (120, 2, 12, 3, 0.1, 0.3, (None, [(0, -1)]), 2),            # GT=15, no padding room: tensor cores with the covariance in L2
     (130, 2, 12, 3, 0.0, 0.3, (None, [(0, -1)]), 2),            # GT=17: beyond the shared-memory limit
@@ -317,6 +317,42 @@ def test_register_chained_four_warp_kernel(N, d, noise, loops, fpc, monkeypatch)
     assert rel_err(eng.logl_st(traj, ss, thetas), got) < 1e-12
 
 
+EIGHT_WARP_CASES = [
+    # N, d, noise, loops                      k_mmar8 (GT = 13): one filter per CTA, eight warps, one resident propagator swapped by TMA
+    (97, 3, 0.3, (None, [(0, -1)])),          # r=1
+    (100, 3, 0.3, (None, [(0, -1)])),         # r=4 (BASELINE configs[2])
+    (100, 2, [0.2, 0.4], (None, [(0, -1)], [(10, 50)])),   # 3 states (propagator swaps between three), d*=2
+    (101, 3, 0.3, (None, [(0, -1)])),         # r=5: mean in extra rows
+    (104, 4, 0.4, (None, [(0, -1)])),         # r=8, d=4
+]
+
+
+@pytest.mark.parametrize("N,d,noise,loops", EIGHT_WARP_CASES)
+def test_register_chained_eight_warp_kernel(N, d, noise, loops, monkeypatch):
+    """k_mmar8 vs the C oracle and vs k_mmact / k_mmac (T through shared memory) on the same inputs; profiles with many state
+    switches exercise the TMA swap of the single resident propagator."""
+    rng = np.random.default_rng(577 + N)
+    mod = oracle_model(N, d=d, loops=loops)
+    T, P = 30, 11
+    x, _ = synth_traj(mod, T, rng, noise, p_nan=0.15)
+    x[0] = np.nan if N % 2 else x[0]                     # odd N: first frame missing
+    ss, thetas = random_profiles(rng, P, T, len(loops), 8)
+    err = np.broadcast_to(np.asarray(noise, dtype=float), (d,))
+    s2, Cind = ko.noise_to_s2_cind(err)
+    states = np.array([ko.st2states(s, th, T) for s, th in zip(ss, thetas)])
+    want = ko.logl_c(*(mod[k] for k in MODEL_KEYS), x, s2, Cind, states)
+    eng = engine_for(mod)
+    traj = eng.trajectory(x, err)
+    plan = traj.describe_plan(P)
+    assert plan.split()[0] == "mmar8" and ("mean-in-extra-rows" in plan) == (N > 100)
+    got = eng.logl_st(traj, ss, thetas)
+    assert rel_err(got, want) < TOL
+    assert np.array_equal(got, eng.logl_states(traj, states))
+    monkeypatch.setenv("BILDK_MMAR8", "0")
+    assert traj.describe_plan(P).split()[0] in ("mmact", "mmac")
+    assert rel_err(eng.logl_st(traj, ss, thetas), got) < 1e-12
+
+
 @pytest.mark.parametrize("N,nz", [
     (20, {3: -1.0, 14: 1.0}),            # two interior monomers (k_mma)
     (20, {7: 0.5, 8: -2.0}),             # neighbours in one tile, unequal weights
@@ -363,7 +399,7 @@ def test_dense_measurement_vector():
     assert rel_err(got, want) < TOL
 
 
-@pytest.mark.parametrize("N", [15, 18, 19, 25, 40, 100])   # 15, 40: k_mmar / k_mmar2 with the mean in extra rows; 18, 25: k_mmarb (border means); 19: k_mmar; 100: k_mmact
+@pytest.mark.parametrize("N", [15, 18, 19, 25, 40, 100])   # 15, 40: k_mmar / k_mmar2 with the mean in extra rows; 18, 25: k_mmarb (border means); 19: k_mmar; 100: k_mmar8
 def test_external_force_mean_offset(N):
     """G != 0 (pyx:209): constant force on the chain ends."""
     rng = np.random.default_rng(6)
@@ -395,7 +431,7 @@ def test_no_valid_frames_and_single_frame():
     assert rel_err(eng.logl_states(traj1, np.array([[1]])), want) < TOL
 
 
-@pytest.mark.parametrize("N", [20, 25, 16, 40, 50, 100])   # k_mmar, k_mmarb, k_mmar MX, k_mmar2 MX, k_mmar2, k_mmact
+@pytest.mark.parametrize("N", [20, 25, 16, 40, 50, 100])   # k_mmar, k_mmarb, k_mmar MX, k_mmar2 MX, k_mmar2, k_mmar8
 def test_multi_trajectory_batch(N):
     """Fused multi-trajectory launch (bildk_logl_runs_multi: trajectories of different lengths and batch sizes in one grid,
     CTA -> trajectory map) against the C oracle, for every kernel family the dataset driver can meet."""
@@ -464,7 +500,7 @@ def test_round_trip_properties_full_size():
 FULL_SIZE = [
     # name, N, T, P, p_nan, n_check                                      BASELINE.json sizes, checked on a random sample
     ("north-star N=50 T=1000", 50, 1000, 16384, 0.0, 256),                # k_mma2
-    ("configs[2] N=100 T=1000 10% NaN", 100, 1000, 16384, 0.10, 256),     # k_mmact
+    ("configs[2] N=100 T=1000 10% NaN", 100, 1000, 16384, 0.10, 256),     # k_mmar8
     ("sweep N=200 T=100", 200, 100, 1024, 0.0, 256),                      # k_mmag2
 ]
 
