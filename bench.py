@@ -78,6 +78,7 @@ WORKLOADS = {
     "n36": dict(N=36, T=500, P=16384, p_nan=0.0, desc="N=36, T=500, 16384 profiles"),
     "n60": dict(N=60, T=300, P=8192, p_nan=0.0, desc="N=60, T=300, 8192 profiles"),
     "n64": dict(N=64, T=300, P=8192, p_nan=0.0, desc="N=64, T=300, 8192 profiles"),
+    "n68": dict(N=68, T=300, P=8192, p_nan=0.0, desc="N=68, T=300, 8192 profiles"),
     "n72": dict(N=72, T=300, P=8192, p_nan=0.0, desc="N=72, T=300, 8192 profiles"),
     "n80": dict(N=80, T=300, P=4096, p_nan=0.0, desc="N=80, T=300, 4096 profiles"),
     "n96": dict(N=96, T=300, P=4096, p_nan=0.0, desc="N=96, T=300, 4096 profiles"),

@@ -381,7 +381,7 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
             // register-chained kernels: M^T rides in the spare rows of the last tile-row block (rl <= 4: room for d <= 4 mean
             // rows and a zero row) or, for rl >= 5, in an extra row block of the filter buffer ("MX", bildk_mmar.cuh)
             const int rl = N - 8 * (GT - 1);
-            if ((GT <= 8 || GT == 13) && rl >= 1 && rl <= 8 && d <= 4 && m->wz_idx[0] == 0 && m->wz_idx[1] == N - 1 && N >= 2) {   // end-to-end measurement only
+            if ((GT <= 9 || GT == 13) && rl >= 1 && rl <= 8 && d <= 4 && m->wz_idx[0] == 0 && m->wz_idx[1] == N - 1 && N >= 2) {   // end-to-end measurement only
                 const int R = 8 * GT;
                 const int LDr = (R % 16 == 8) ? R : R + 8;
                 const size_t matr = static_cast<size_t>(R) * LDr;
@@ -394,7 +394,7 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
                 if ((rc = upload(&m->dBr, pad.data(), S * matr))) return rc;
                 m->r_last = rl; m->LDr = LDr;
                 m->mmar_mx = rl > 4;
-                m->fstride_r = static_cast<int>(matr) + (m->mmar_mx ? 8 * LDr : 0) + 2 * R + 8 + (GT == 13 ? 8 * R : GT >= 8 ? 4 * R : GT >= 5 ? 2 * R : 0);   // k_mmar2 / k_mmar8: one C' w vector per warp
+                m->fstride_r = static_cast<int>(matr) + (m->mmar_mx ? 8 * LDr : 0) + 2 * R + 8 + (GT == 13 ? 8 * R : GT == 9 ? 5 * R : GT >= 8 ? 4 * R : GT >= 5 ? 2 * R : 0);   // k_mmar2 / k_mmar8: one C' w vector per warp
                 // GT = 13 (k_mmar8): one filter per CTA next to ONE resident propagator
                 const bool fits = GT == 13 ? 16 + matr * 8 + static_cast<size_t>(m->fstride_r) * 8 <= static_cast<size_t>(m->max_smem_optin)
                                            : 16 + matr * 8 * S + static_cast<size_t>(m->fstride_r) * 8 * (GT >= 8 ? 2 : 4) <= static_cast<size_t>(m->max_smem_optin);
@@ -590,7 +590,7 @@ static cudaError_t mmarb_launch_for(int GT, int NB, int RB, const RParams& rp, d
     return cudaErrorInvalidValue;
 }
 
-constexpr int mmar2_nw(int GT) { return GT >= 8 ? 4 : 2; }   // warps per filter
+constexpr int mmar2_nw(int GT) { return GT == 9 ? 5 : GT >= 8 ? 4 : 2; }   // warps per filter
 template <int GT, int MAXF, bool MX>
 static cudaError_t mmar2_launch(const R2Params& rp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
     {
@@ -604,7 +604,7 @@ static cudaError_t mmar2_launch(const R2Params& rp, dim3 grid, int threads, size
 // 4 (8 warps, 255 registers; 5 or 6 filters spill, see bildk_mmar2.cuh); the smaller tile grids leave room for more warps.
 constexpr int MMAR2_MAXF = 4;
 #define MMAR2_VARIANTS(X) X(5, 4, false) X(6, 4, false) X(7, 4, false) X(5, 4, true) X(6, 4, true) X(7, 4, true) \
-                          X(5, 6, false) X(5, 6, true) X(8, 2, false) X(8, 2, true)
+                          X(5, 6, false) X(5, 6, true) X(8, 2, false) X(8, 2, true) X(9, 2, false) X(9, 2, true)
 static bool mmar2_has(int GT, int MAXF, bool MX) {
 #define X(G_, F_, M_) if (GT == G_ && MAXF == F_ && MX == M_) return true;
     MMAR2_VARIANTS(X)
@@ -616,7 +616,7 @@ static int mmar2_maxf(int GT, bool MX) {
     // (profiles/r02_mx_variants.txt); GT = 6 spills at 168 registers and loses 18 %
     // GT = 8: four warps per filter, 2 filters = 8 warps at 255 registers (spill-free; 3 filters at 168 registers spill 400-600
     // bytes per thread and are 5-12 % slower, profiles/r02_gt8_variants.txt)
-    const int dflt = GT == 5 ? 6 : (GT == 8 ? 2 : MMAR2_MAXF);
+    const int dflt = GT == 5 ? 6 : (GT >= 8 ? 2 : MMAR2_MAXF);
     const int want = env_int("BILDK_MMAR2_MAXF", dflt);
     return mmar2_has(GT, want, MX) ? want : dflt;
 }
@@ -838,7 +838,7 @@ static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
             pl.bstride = static_cast<int>(matb / 8);
             return pl;
         }
-        if (m->mmar2_ok && m->GT <= 8 && !force0 && !env_int("BILDK_FORCE_GENERIC", 0) && env_int("BILDK_MMAR2", 1) && (!m->mmar_mx || env_int("BILDK_MMAR_MX", 1))) {
+        if (m->mmar2_ok && m->GT <= 9 && !force0 && !env_int("BILDK_FORCE_GENERIC", 0) && env_int("BILDK_MMAR2", 1) && (!m->mmar_mx || env_int("BILDK_MMAR_MX", 1))) {
             const size_t matb = static_cast<size_t>(8 * m->GT) * m->LDr * 8;
             const size_t fbytes = static_cast<size_t>(m->fstride_r) * 8;
             const int maxf = mmar2_maxf(m->GT, m->mmar_mx);
@@ -855,7 +855,7 @@ static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
                 static const double wt6[7] = {0.0, 1.0, 0.977, 1.0, 1.0, 1.0, 1.0};
                 static const double wt5[7] = {0.0, 1.0, 0.983, 0.985, 1.0, 1.0, 1.0};
                 static const double wt8[7] = {0.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
-                const double* wave_time = m->GT == 7 ? wt7 : (m->GT == 6 ? wt6 : (m->GT == 8 ? wt8 : wt5));
+                const double* wave_time = m->GT == 7 ? wt7 : (m->GT == 6 ? wt6 : (m->GT >= 8 ? wt8 : wt5));
                 const long long P = std::max(1, P_per_traj_hint);
                 double best = 1e300;
                 for (int c = maxf; c >= 1; --c) {
@@ -1148,7 +1148,7 @@ static std::string plan_string(const bildk_model* m, const Plan& pl) {
                  m->mmar_mx ? " mean-in-extra-rows" : "", pl.threads, pl.smem);
     else if (pl.mmar2)
         snprintf(buf, sizeof buf, "mmar2 (DMMA m8n8k4) GT=%d%s register-chained %s-warps-per-filter (tile rows split) FPC=%d of %d threads=%d smem=%zu", m->GT,
-                 m->mmar_mx ? " mean-in-extra-rows" : "", m->GT >= 8 ? "four" : "two", pl.FPC, pl.maxf, pl.threads, pl.smem);
+                 m->mmar_mx ? " mean-in-extra-rows" : "", m->GT == 9 ? "five" : (m->GT >= 8 ? "four" : "two"), pl.FPC, pl.maxf, pl.threads, pl.smem);
     else if (pl.mmar)
         snprintf(buf, sizeof buf, "mmar (DMMA m8n8k4) GT=%d%s register-chained warp-per-filter WPC=%d CTAs/SM=%d threads=%d smem=%zu", m->GT,
                  m->mmar_mx ? " mean-in-extra-rows" : (pl.mmarb ? " border-in-DFMA" : ""), pl.WPC, pl.nb, pl.threads, pl.smem);
@@ -1173,7 +1173,7 @@ extern "C" const char* bildk_describe_plan(bildk_traj_t t, int P) {
 extern "C" int bildk_debug_tables(int kernel, int GT, int r, int ncols, unsigned char* out) {
     if (!out) return fail(BILDK_EINVAL, "out is NULL");
     if (kernel == 0) {
-        if (GT < 1 || (GT > 8 && GT != 13) || r < 1 || r > 8 || ncols < 1 || ncols > 4) return fail(BILDK_EINVAL, "k_mmar tables need GT in 1..8 or 13, r in 1..8, ncols in 1..4");
+        if (GT < 1 || (GT > 9 && GT != 13) || r < 1 || r > 8 || ncols < 1 || ncols > 4) return fail(BILDK_EINVAL, "k_mmar tables need GT in 1..9 or 13, r in 1..8, ncols in 1..4");
         mmar_tables(GT, r, ncols, out, out + 8);
         return 12;
     }

@@ -24,7 +24,8 @@ struct R2Params {
 };
 
 // NW = warps per filter: 2 for GT 5..7; 4 for GT = 8 (N = 57..64), where the four COMPLEMENTARY row pairs (ti, GT-1-ti) cost
-// exactly the same - 2 GTC tile products in P1 and GT + 1 in P2 each - and the four warps of a filter sit on the four schedulers.
+// exactly the same - 2 GTC tile products in P1 and GT + 1 in P2 each - and the four warps of a filter sit on the four schedulers;
+// 5 for GT = 9 (N = 65..72): four pairs and the middle row, two filters per CTA so that the schedulers carry 70 | 70 | 56 | 56.
 template <int GT, int NW = 2>
 struct Mmar2Rows {
     // role that owns tile-row block ti; cost of a row = GT (P1) + GT - ti (P2) tile products
@@ -34,7 +35,8 @@ struct Mmar2Rows {
     __host__ __device__ static constexpr int role(int ti) {
         return NW == 8 ? ((ti == 0 || ti == 12) ? 0 : (ti == 3 || ti == 9) ? 1 : (ti == 4 || ti == 6) ? 2 : (ti == 7 || ti == 11) ? 3
                           : ti == 1 ? 4 : ti == 2 ? 5 : ti == 5 ? 6 : 7)
-             : NW == 4 ? (ti < GT - 1 - ti ? ti : GT - 1 - ti)   // GT = 8: rows {0,7} {1,6} {2,5} {3,4}: 25 tile products each (MX: 27)
+             : NW >= 4 ? (ti < GT - 1 - ti ? ti : GT - 1 - ti)   // GT = 8: rows {0,7} {1,6} {2,5} {3,4}: 25 tile products each (MX: 27);
+                                                                 // GT = 9 (NW = 5): {0,8} {1,7} {2,6} {3,5} 28 (30) each and the middle row {4} 14 (15)
              : GT == 7 ? (ti <= 2 ? 0 : 1)                       // 14+13+12 = 39 | 11+10+9+8 = 38      MX: 42 | 42
              : GT == 6 ? ((ti == 0 || ti == 3 || ti == 5) ? 0 : 1)   // 12+9+7 = 28 | 11+10+8 = 29          MX: 31 | 32
              : (ti <= 1 ? 0 : 1);                                // GT = 5: 10+9 = 19 | 8+7+6 = 21      MX: 21 | 24
@@ -44,31 +46,38 @@ struct Mmar2Rows {
     // a 40-minute compilation and a kernel 30x slower than the one it was to replace.
     __host__ __device__ static constexpr int first8(int r) { return r == 0 ? 0 : r == 1 ? 3 : r == 2 ? 4 : r == 3 ? 7 : r == 4 ? 1 : r == 5 ? 2 : r == 6 ? 5 : 8; }
     __host__ __device__ static constexpr int second8(int r) { return r == 0 ? 12 : r == 1 ? 9 : r == 2 ? 6 : r == 3 ? 11 : r == 7 ? 10 : -1; }
+    // NW = 4, 5: complementary pairs - role r owns rows r and GT-1-r (the middle row of an odd grid alone)
+    static constexpr bool PAIRS = NW == 4 || NW == 5;
     __host__ __device__ static constexpr int nacc(int r) {          // upper tiles owned by role r
         if (NW == 8) return (GT - first8(r)) + (second8(r) >= 0 ? GT - second8(r) : 0);
+        if (PAIRS) return (GT - r) + (GT - 1 - r != r ? r + 1 : 0);
         int n = 0;
         for (int ti = 0; ti < GT; ++ti) if (role(ti) == r) n += GT - ti;
         return n;
     }
     __host__ __device__ static constexpr int nrows(int r) {
         if (NW == 8) return second8(r) >= 0 ? 2 : 1;
+        if (PAIRS) return GT - 1 - r != r ? 2 : 1;
         int n = 0;
         for (int ti = 0; ti < GT; ++ti) if (role(ti) == r) ++n;
         return n;
     }
     __host__ __device__ static constexpr int first(int r) {          // lowest row of role r
         if (NW == 8) return first8(r);
+        if (PAIRS) return r;
         for (int ti = 0; ti < GT; ++ti) if (role(ti) == r) return ti;
         return GT;
     }
     __host__ __device__ static constexpr int aidx(int ti, int tj) {  // accumulator slot of upper tile (ti, tj) within its owner
         if (NW == 8) return (ti == first8(role(ti)) ? 0 : GT - first8(role(ti))) + tj - ti;
+        if (PAIRS) return (ti <= GT - 1 - ti ? 0 : GT - role(ti)) + tj - ti;
         int n = 0;
         for (int t = 0; t < ti; ++t) if (role(t) == role(ti)) n += GT - t;
         return n + tj - ti;
     }
     __host__ __device__ static constexpr int ridx(int ti) {          // slot of row ti within its owner (mu, kr)
         if (NW == 8) return ti == first8(role(ti)) ? 0 : 1;
+        if (PAIRS) return ti <= GT - 1 - ti ? 0 : 1;
         int n = 0;
         for (int t = 0; t < ti; ++t) if (role(t) == role(ti)) ++n;
         return n;
@@ -395,8 +404,9 @@ __global__ void __launch_bounds__(32 * NW * MAXF, 1) k_mmar2(const __grid_consta
     mbar_wait(mbar, 0);
     if (role == 0) mmar2_run<GT, 0, MX, NW>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, 1 + fl, lane);
     else if (NW == 2 || role == 1) mmar2_run<GT, 1, MX, NW>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, 1 + fl, lane);
-    else if (role == 2) mmar2_run<GT, (NW == 4 ? 2 : 0), MX, NW>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, 1 + fl, lane);
-    else mmar2_run<GT, (NW == 4 ? 3 : 0), MX, NW>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, 1 + fl, lane);
+    else if (NW == 3 || role == 2) mmar2_run<GT, (NW >= 3 ? 2 : 0), MX, NW>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, 1 + fl, lane);
+    else if (NW == 4 || role == 3) mmar2_run<GT, (NW >= 4 ? 3 : 0), MX, NW>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, 1 + fl, lane);
+    else mmar2_run<GT, (NW >= 5 ? 4 : 0), MX, NW>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, 1 + fl, lane);
 }
 
 // k_mmar8 - the register-chained scheme for GT = 13 (N = 97..104; BASELINE configs[2] N = 100): ONE filter per CTA, eight warps,

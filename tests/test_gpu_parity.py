@@ -43,8 +43,8 @@ CASES = [
     (2, 3, 25, 6, 0.1, 0.5, (None, [(0, -1, 0.5)]), 2),         # N < d: catch-all kernel
     (60, 3, 30, 4, 0.1, 0.3, (None, [(0, -1)]), 4),             # GT=8: k_mmar2 with four warps per filter
     (64, 3, 20, 3, 0.0, 0.3, (None, [(0, -1)]), 3),             # GT=8, r=8: k_mmar2 (four warps), mean in extra rows
-    (68, 3, 24, 4, 0.1, 0.3, (None, [(0, -1)]), 3),             # GT=9 = 4k+1 (k_mmact: 12 warps, three P1 helper warps, tile segments)
-    (70, 3, 24, 4, 0.1, 0.3, (None, [(0, -1)]), 3),             # GT=9, no padding room for the mean: k_mmac with an extra tile column
+    (68, 3, 24, 4, 0.1, 0.3, (None, [(0, -1)]), 3),             # GT=9: k_mmar2 with five warps per filter
+    (70, 3, 24, 4, 0.1, 0.3, (None, [(0, -1)]), 3),             # GT=9, r=6: k_mmar2 (five warps), mean in extra rows
     (108, 3, 12, 2, 0.1, 0.3, (None, [(0, -1)]), 2),            # GT=14 (k_mmact without helpers, 7 slots per warp)
     (96, 2, 16, 3, 0.2, 0.3, (None, [(0, -1)], [(10, 50)]), 3), # GT=12, 3 states: single resident propagator, TMA swaps
     (100, 2, 14, 3, 0.2, [0.2, 0.4], (None, [(0, -1)], [(10, 50)]), 3),   # GT=13: k_mmar8 (eight warps, TMA propagator swaps), 3 states, d*=2
@@ -314,6 +314,45 @@ def test_register_chained_four_warp_kernel(N, d, noise, loops, fpc, monkeypatch)
     assert np.array_equal(got, eng.logl_states(traj, states))
     monkeypatch.setenv("BILDK_MMAR2", "0")               # one CTA per filter, one warp per tile column
     assert traj.describe_plan(P).split()[0] == "mmac"
+    assert rel_err(eng.logl_st(traj, ss, thetas), got) < 1e-12
+
+
+FIVE_WARP_CASES = [
+    # N, d, noise, loops                      k_mmar2 with FIVE warps per filter (GT = 9: row pairs {0,8} {1,7} {2,6} {3,5} and the middle row {4})
+    (65, 3, 0.3, (None, [(0, -1)])),          # r=1
+    (68, 2, [0.1, 0.4], (None, [(0, -1)])),   # r=4, d*=2
+    (68, 3, 0.3, (None, [(0, -1)], [(5, 30), (12, 44, 0.5)])),   # r=4, 3 states
+    (69, 3, 0.3, (None, [(0, -1)])),          # r=5: mean in extra rows
+    (72, 4, 0.4, (None, [(0, -1)])),          # r=8, d=4
+]
+
+
+@pytest.mark.parametrize("fpc", [0, 1], ids=["default", "one-filter-per-cta"])
+@pytest.mark.parametrize("N,d,noise,loops", FIVE_WARP_CASES)
+def test_register_chained_five_warp_kernel(N, d, noise, loops, fpc, monkeypatch):
+    """k_mmar2 at GT = 9 (N = 65..72): four complementary row pairs and the middle row on five warps, vs the C oracle and vs
+    k_mmact / k_mmac on the same inputs."""
+    rng = np.random.default_rng(677 + N)
+    mod = oracle_model(N, d=d, loops=loops)
+    T, P = 36, 17
+    x, _ = synth_traj(mod, T, rng, noise, p_nan=0.15)
+    x[0] = np.nan if N % 2 else x[0]                     # odd N: first frame missing
+    ss, thetas = random_profiles(rng, P, T, len(loops), 6)
+    err = np.broadcast_to(np.asarray(noise, dtype=float), (d,))
+    s2, Cind = ko.noise_to_s2_cind(err)
+    states = np.array([ko.st2states(s, th, T) for s, th in zip(ss, thetas)])
+    want = ko.logl_c(*(mod[k] for k in MODEL_KEYS), x, s2, Cind, states)
+    eng = engine_for(mod)
+    traj = eng.trajectory(x, err)
+    if fpc:
+        monkeypatch.setenv("BILDK_FPC2", str(fpc))
+    plan = traj.describe_plan(P)
+    assert plan.split()[0] == "mmar2" and "five-warps-per-filter" in plan and ("mean-in-extra-rows" in plan) == (N > 68)
+    got = eng.logl_st(traj, ss, thetas)
+    assert rel_err(got, want) < TOL
+    assert np.array_equal(got, eng.logl_states(traj, states))
+    monkeypatch.setenv("BILDK_MMAR2", "0")
+    assert traj.describe_plan(P).split()[0] in ("mmact", "mmac")
     assert rel_err(eng.logl_st(traj, ss, thetas), got) < 1e-12
 
 
