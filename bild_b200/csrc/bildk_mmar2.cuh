@@ -366,8 +366,8 @@ __device__ __forceinline__ void mmar2_run(const RParams& rp, double* __restrict_
 }
 
 // MAXF: filters per CTA the kernel is compiled for (registers per thread = 65536 / (64 MAXF)).
-template <int GT, int MAXF, bool MX = false, int NW = 2>
-__global__ void __launch_bounds__(32 * NW * MAXF, 1) k_mmar2(const __grid_constant__ R2Params rp2) {
+template <int GT, int MAXF, bool MX, int NW>
+__device__ __forceinline__ void mmar2_kernel(const R2Params& rp2) {
     constexpr int MAT = MmarGeom<GT, MX>::MAT;
     const RParams& rp = rp2.r;
     const KParams& p = rp.k;
@@ -408,6 +408,14 @@ __global__ void __launch_bounds__(32 * NW * MAXF, 1) k_mmar2(const __grid_consta
     else if (NW == 4 || role == 3) mmar2_run<GT, (NW >= 4 ? 3 : 0), MX, NW>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, 1 + fl, lane);
     else mmar2_run<GT, (NW >= 5 ? 4 : 0), MX, NW>(rp, Bsm, Cb, pidx, tjx, blockIdx.y, 1 + fl, lane);
 }
+
+template <int GT, int MAXF, bool MX = false, int NW = 2>
+__global__ void __launch_bounds__(32 * NW * MAXF, 1) k_mmar2(const __grid_constant__ R2Params rp2) {
+    mmar2_kernel<GT, MAXF, MX, NW>(rp2);
+}
+// (GT = 9 runs ten warps per CTA: the register file is handed out to warps in groups of four, so ptxas budgets 320 threads like
+// 384 - 168 registers, ~1 KB of spills per thread.  Compiling for 200 registers with __maxnreg__ halves the spills but the launch
+// fails with "too many resources requested": measured, reverted.)
 
 // k_mmar8 - the register-chained scheme for GT = 13 (N = 97..104; BASELINE configs[2] N = 100): ONE filter per CTA, eight warps,
 // the tile rows dealt out so that the four schedulers carry (almost) equal DMMA counts (Mmar2Rows<GT, 8>), one resident

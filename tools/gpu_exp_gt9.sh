@@ -1,0 +1,16 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "five_warp or four_warp or (against_c_oracle and (68 or 70))" 2>&1 | tail -3
+run() {  # label, workload, env...
+  local label=$1 wl=$2; shift 2
+  env "$@" timeout 120 python bench.py --workload $wl --steps 3 --warmup 3 --no-cpu --also '' > /tmp/b.json 2> /tmp/b.err || { tail -3 /tmp/b.err; echo "$label $wl FAILED/timeout"; return; }
+  python -c "
+import json; d=json.load(open('/tmp/b.json')); print('$label $wl frac %.4f ms %.3f'%(d['roofline']['frac'], d['ms_per_step']), d['detail']['plan'])"
+}
+{
+run mmact n68 BILDK_MMAR2=0
+run mmar2x5 n68 A=1
+run mmar2x5-fpc1 n68 BILDK_FPC2=1
+run mmac n72 BILDK_MMAR2=0
+run mmar2x5 n72 A=1
+} | tee gpurun_out/exp_gt9.txt
