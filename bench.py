@@ -81,6 +81,7 @@ WORKLOADS = {
     "n68": dict(N=68, T=300, P=8192, p_nan=0.0, desc="N=68, T=300, 8192 profiles"),
     "n72": dict(N=72, T=300, P=8192, p_nan=0.0, desc="N=72, T=300, 8192 profiles"),
     "n80": dict(N=80, T=300, P=4096, p_nan=0.0, desc="N=80, T=300, 4096 profiles"),
+    "n88": dict(N=88, T=300, P=4096, p_nan=0.0, desc="N=88, T=300, 4096 profiles"),
     "n96": dict(N=96, T=300, P=4096, p_nan=0.0, desc="N=96, T=300, 4096 profiles"),
     "n104": dict(N=104, T=300, P=4096, p_nan=0.0, desc="N=104, T=300, 4096 profiles"),
     "n56": dict(N=56, T=500, P=16384, p_nan=0.0, desc="N=56, T=500, 16384 profiles"),

@@ -381,7 +381,7 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
             // register-chained kernels: M^T rides in the spare rows of the last tile-row block (rl <= 4: room for d <= 4 mean
             // rows and a zero row) or, for rl >= 5, in an extra row block of the filter buffer ("MX", bildk_mmar.cuh)
             const int rl = N - 8 * (GT - 1);
-            if ((GT <= 9 || GT == 13) && rl >= 1 && rl <= 8 && d <= 4 && m->wz_idx[0] == 0 && m->wz_idx[1] == N - 1 && N >= 2) {   // end-to-end measurement only
+            if (GT <= 13 && rl >= 1 && rl <= 8 && d <= 4 && m->wz_idx[0] == 0 && m->wz_idx[1] == N - 1 && N >= 2) {   // end-to-end measurement only
                 const int R = 8 * GT;
                 const int LDr = (R % 16 == 8) ? R : R + 8;
                 const size_t matr = static_cast<size_t>(R) * LDr;
@@ -394,9 +394,9 @@ extern "C" int bildk_model_create(int N, int d, int S, const double* B, const do
                 if ((rc = upload(&m->dBr, pad.data(), S * matr))) return rc;
                 m->r_last = rl; m->LDr = LDr;
                 m->mmar_mx = rl > 4;
-                m->fstride_r = static_cast<int>(matr) + (m->mmar_mx ? 8 * LDr : 0) + 2 * R + 8 + (GT == 13 ? 8 * R : GT == 9 ? 5 * R : GT >= 8 ? 4 * R : GT >= 5 ? 2 * R : 0);   // k_mmar2 / k_mmar8: one C' w vector per warp
-                // GT = 13 (k_mmar8): one filter per CTA next to ONE resident propagator
-                const bool fits = GT == 13 ? 16 + matr * 8 + static_cast<size_t>(m->fstride_r) * 8 <= static_cast<size_t>(m->max_smem_optin)
+                m->fstride_r = static_cast<int>(matr) + (m->mmar_mx ? 8 * LDr : 0) + 2 * R + 8 + (GT >= 10 ? 8 * R : GT == 9 ? 5 * R : GT >= 8 ? 4 * R : GT >= 5 ? 2 * R : 0);   // k_mmar2 / k_mmar8: one C' w vector per warp
+                // GT >= 10 (k_mmar8): one filter per CTA next to ONE resident propagator
+                const bool fits = GT >= 10 ? 16 + matr * 8 + static_cast<size_t>(m->fstride_r) * 8 <= static_cast<size_t>(m->max_smem_optin)
                                            : 16 + matr * 8 * S + static_cast<size_t>(m->fstride_r) * 8 * (GT >= 8 ? 2 : 4) <= static_cast<size_t>(m->max_smem_optin);
                 m->mmar_ok = fits && GT <= 4;
                 m->mmar2_ok = fits && GT >= 5;
@@ -822,7 +822,7 @@ static Plan make_plan(const bildk_model* m, int P_per_traj_hint) {
     Plan pl{};
     {
         const char* force0 = getenv("BILDK_KERNEL");
-        if (m->mmar2_ok && m->GT == 13 && !force0 && !env_int("BILDK_FORCE_GENERIC", 0) && env_int("BILDK_MMAR8", 1)) {
+        if (m->mmar2_ok && m->GT >= 10 && !force0 && !env_int("BILDK_FORCE_GENERIC", 0) && env_int("BILDK_MMAR8", 1)) {
             // k_mmar8: one filter per CTA, eight warps, one resident propagator
             const size_t matb = static_cast<size_t>(8 * m->GT) * m->LDr * 8;
             const size_t fbytes = static_cast<size_t>(m->fstride_r) * 8;
@@ -1173,7 +1173,7 @@ extern "C" const char* bildk_describe_plan(bildk_traj_t t, int P) {
 extern "C" int bildk_debug_tables(int kernel, int GT, int r, int ncols, unsigned char* out) {
     if (!out) return fail(BILDK_EINVAL, "out is NULL");
     if (kernel == 0) {
-        if (GT < 1 || (GT > 9 && GT != 13) || r < 1 || r > 8 || ncols < 1 || ncols > 4) return fail(BILDK_EINVAL, "k_mmar tables need GT in 1..9 or 13, r in 1..8, ncols in 1..4");
+        if (GT < 1 || GT > 13 || r < 1 || r > 8 || ncols < 1 || ncols > 4) return fail(BILDK_EINVAL, "k_mmar tables need GT in 1..13, r in 1..8, ncols in 1..4");
         mmar_tables(GT, r, ncols, out, out + 8);
         return 12;
     }
@@ -1301,8 +1301,18 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
             for (int e = 0; e < dstar; ++e) mmar_tables(m->GT, m->r_last, t0->ncols[e], rp.lastrow[e], rp.mrow[e]);
             r2.FPC2 = pl.FPC;
             if (pl.mmar8) {
-                if (m->mmar_mx) CU((mmar8_launch<13, true>(r2, grid, pl.smem, st)));
-                else CU((mmar8_launch<13, false>(r2, grid, pl.smem, st)));
+                cudaError_t e8 = cudaErrorInvalidValue;
+                switch (m->GT * 2 + (m->mmar_mx ? 1 : 0)) {
+                    case 20: e8 = mmar8_launch<10, false>(r2, grid, pl.smem, st); break;
+                    case 21: e8 = mmar8_launch<10, true>(r2, grid, pl.smem, st); break;
+                    case 22: e8 = mmar8_launch<11, false>(r2, grid, pl.smem, st); break;
+                    case 23: e8 = mmar8_launch<11, true>(r2, grid, pl.smem, st); break;
+                    case 24: e8 = mmar8_launch<12, false>(r2, grid, pl.smem, st); break;
+                    case 25: e8 = mmar8_launch<12, true>(r2, grid, pl.smem, st); break;
+                    case 26: e8 = mmar8_launch<13, false>(r2, grid, pl.smem, st); break;
+                    case 27: e8 = mmar8_launch<13, true>(r2, grid, pl.smem, st); break;
+                }
+                CU(e8);
             } else {
                 CU(mmar2_launch_for(m->GT, pl.maxf, m->mmar_mx, r2, grid, pl.threads, pl.smem, st));
             }

@@ -30,11 +30,10 @@ template <int GT, int NW = 2>
 struct Mmar2Rows {
     // role that owns tile-row block ti; cost of a row = GT (P1) + GT - ti (P2) tile products
     // (with the mean in an extra tile column, MX, every row costs one more: the same splits stay the balanced ones)
-    // NW = 8 (GT = 13, N = 97..104; one filter per CTA, warp w on scheduler w % 4): rows dealt out so that the four schedulers
-    // carry 65 | 64 | 63 | 68 tile products (MX: 68 | 67 | 66 | 72) - roles {0,12} {3,9} {4,6} {7,11} | {1} {2} {5} {8,10}
+    // NW = 8 (GT = 10..13, N = 73..104; one filter per CTA, warp w on scheduler w % 4): rows dealt out so that the four schedulers
+    // carry (almost) equal numbers of tile products (tables below)
     __host__ __device__ static constexpr int role(int ti) {
-        return NW == 8 ? ((ti == 0 || ti == 12) ? 0 : (ti == 3 || ti == 9) ? 1 : (ti == 4 || ti == 6) ? 2 : (ti == 7 || ti == 11) ? 3
-                          : ti == 1 ? 4 : ti == 2 ? 5 : ti == 5 ? 6 : 7)
+        return NW == 8 ? role8(ti)
              : NW >= 4 ? (ti < GT - 1 - ti ? ti : GT - 1 - ti)   // GT = 8: rows {0,7} {1,6} {2,5} {3,4}: 25 tile products each (MX: 27);
                                                                  // GT = 9 (NW = 5): {0,8} {1,7} {2,6} {3,5} 28 (30) each and the middle row {4} 14 (15)
              : GT == 7 ? (ti <= 2 ? 0 : 1)                       // 14+13+12 = 39 | 11+10+9+8 = 38      MX: 42 | 42
@@ -44,8 +43,26 @@ struct Mmar2Rows {
     // NW = 8: closed forms (a role owns one or two rows).  The loops below fold to constants for two and four roles, but with
     // thirteen rows and eight roles the optimiser gave up on them: run-time indexed accumulators in local memory, jump tables,
     // a 40-minute compilation and a kernel 30x slower than the one it was to replace.
-    __host__ __device__ static constexpr int first8(int r) { return r == 0 ? 0 : r == 1 ? 3 : r == 2 ? 4 : r == 3 ? 7 : r == 4 ? 1 : r == 5 ? 2 : r == 6 ? 5 : 8; }
-    __host__ __device__ static constexpr int second8(int r) { return r == 0 ? 12 : r == 1 ? 9 : r == 2 ? 6 : r == 3 ? 11 : r == 7 ? 10 : -1; }
+    // row tables of the eight-warp kernel (one or two rows per warp; warps w and w + 4 share a scheduler), found by a greedy search
+    // over the per-scheduler sums of the row costs GTC + GT - ti (tools/mmar8_tables.py): per-scheduler maximum / mean
+    //   GT = 10: {6} {5,9} {3} {1} | {0} {2} {4} {7,8}          44 / 38.75      GT = 12: {7,10} {4,9} {2} {1} | {0} {3} {6,8} {5,11}   56 / 55.5
+    //   GT = 11: {5} {0} {1} {2} | {3,8} {7,9} {6,10} {4}       50 / 46.75      GT = 13: {0,12} {3,9} {4,6} {7,11} | {1} {2} {5} {8,10} 68 / 65
+    __host__ __device__ static constexpr int first8(int r) {
+        return GT == 10 ? (r == 0 ? 6 : r == 1 ? 5 : r == 2 ? 3 : r == 3 ? 1 : r == 4 ? 0 : r == 5 ? 2 : r == 6 ? 4 : 7)
+             : GT == 11 ? (r == 0 ? 5 : r == 1 ? 0 : r == 2 ? 1 : r == 3 ? 2 : r == 4 ? 3 : r == 5 ? 7 : r == 6 ? 6 : 4)
+             : GT == 12 ? (r == 0 ? 7 : r == 1 ? 4 : r == 2 ? 2 : r == 3 ? 1 : r == 4 ? 0 : r == 5 ? 3 : r == 6 ? 6 : 5)
+             : (r == 0 ? 0 : r == 1 ? 3 : r == 2 ? 4 : r == 3 ? 7 : r == 4 ? 1 : r == 5 ? 2 : r == 6 ? 5 : 8);
+    }
+    __host__ __device__ static constexpr int second8(int r) {
+        return GT == 10 ? (r == 1 ? 9 : r == 7 ? 8 : -1)
+             : GT == 11 ? (r == 4 ? 8 : r == 5 ? 9 : r == 6 ? 10 : -1)
+             : GT == 12 ? (r == 0 ? 10 : r == 1 ? 9 : r == 6 ? 8 : r == 7 ? 11 : -1)
+             : (r == 0 ? 12 : r == 1 ? 9 : r == 2 ? 6 : r == 3 ? 11 : r == 7 ? 10 : -1);
+    }
+    __host__ __device__ static constexpr bool owns8(int r, int ti) { return ti == first8(r) || ti == second8(r); }
+    __host__ __device__ static constexpr int role8(int ti) {
+        return owns8(0, ti) ? 0 : owns8(1, ti) ? 1 : owns8(2, ti) ? 2 : owns8(3, ti) ? 3 : owns8(4, ti) ? 4 : owns8(5, ti) ? 5 : owns8(6, ti) ? 6 : 7;
+    }
     // NW = 4, 5: complementary pairs - role r owns rows r and GT-1-r (the middle row of an odd grid alone)
     static constexpr bool PAIRS = NW == 4 || NW == 5;
     __host__ __device__ static constexpr int nacc(int r) {          // upper tiles owned by role r

@@ -46,7 +46,7 @@ CASES = [
     (68, 3, 24, 4, 0.1, 0.3, (None, [(0, -1)]), 3),             # GT=9: k_mmar2 with five warps per filter
     (70, 3, 24, 4, 0.1, 0.3, (None, [(0, -1)]), 3),             # GT=9, r=6: k_mmar2 (five warps), mean in extra rows
     (108, 3, 12, 2, 0.1, 0.3, (None, [(0, -1)]), 2),            # GT=14 (k_mmact without helpers, 7 slots per warp)
-    (96, 2, 16, 3, 0.2, 0.3, (None, [(0, -1)], [(10, 50)]), 3), # GT=12, 3 states: single resident propagator, TMA swaps
+    (96, 2, 16, 3, 0.2, 0.3, (None, [(0, -1)], [(10, 50)]), 3), # GT=12, 3 states: k_mmar8, single resident propagator, TMA swaps
     (100, 2, 14, 3, 0.2, [0.2, 0.4], (None, [(0, -1)], [(10, 50)]), 3),   # GT=13: k_mmar8 (eight warps, TMA propagator swaps), 3 states, d*=2
     (110, 3, 12, 2, 0.0, 0.3, (None, [(0, -1)]), 2),            # GT=14
     (120, 2, 12, 3, 0.1, 0.3, (None, [(0, -1)]), 2),            # GT=15, no padding room: tensor cores with the covariance in L2
@@ -357,8 +357,14 @@ def test_register_chained_five_warp_kernel(N, d, noise, loops, fpc, monkeypatch)
 
 
 EIGHT_WARP_CASES = [
-    # N, d, noise, loops                      k_mmar8 (GT = 13): one filter per CTA, eight warps, one resident propagator swapped by TMA
-    (97, 3, 0.3, (None, [(0, -1)])),          # r=1
+    # N, d, noise, loops                      k_mmar8 (GT = 10..13): one filter per CTA, eight warps, one resident propagator swapped by TMA
+    (73, 3, 0.3, (None, [(0, -1)])),          # GT=10, r=1
+    (80, 2, [0.1, 0.4], (None, [(0, -1)], [(10, 50)])),    # GT=10, r=8, 3 states, d*=2
+    (84, 3, 0.3, (None, [(0, -1)])),          # GT=11, r=4
+    (87, 1, 0.3, (None, [(0, -1)])),          # GT=11, r=7, d=1
+    (89, 3, 0.3, (None, [(0, -1)])),          # GT=12, r=1
+    (96, 4, 0.4, (None, [(0, -1)])),          # GT=12, r=8, d=4
+    (97, 3, 0.3, (None, [(0, -1)])),          # GT=13, r=1
     (100, 3, 0.3, (None, [(0, -1)])),         # r=4 (BASELINE configs[2])
     (100, 2, [0.2, 0.4], (None, [(0, -1)], [(10, 50)])),   # 3 states (propagator swaps between three), d*=2
     (101, 3, 0.3, (None, [(0, -1)])),         # r=5: mean in extra rows
@@ -383,7 +389,7 @@ def test_register_chained_eight_warp_kernel(N, d, noise, loops, monkeypatch):
     eng = engine_for(mod)
     traj = eng.trajectory(x, err)
     plan = traj.describe_plan(P)
-    assert plan.split()[0] == "mmar8" and ("mean-in-extra-rows" in plan) == (N > 100)
+    assert plan.split()[0] == "mmar8" and ("mean-in-extra-rows" in plan) == ((N - 1) % 8 + 1 > 4)
     got = eng.logl_st(traj, ss, thetas)
     assert rel_err(got, want) < TOL
     assert np.array_equal(got, eng.logl_states(traj, states))

@@ -200,7 +200,7 @@ def test_register_chained_kernel_tables():
                     assert pair_conf == 0 and quad_conf == 0, (GT, r, ncols, lastrow)
     # mean in an extra row block (r = N - 8 (GT - 1) in 5..8; k_mmar GT <= 4, k_mmar2 GT 5..8): zero row 8 GT in the even
     # slots, mean row q = 8 GT + 2 q + 1 in the odd ones - the two rows of every lane pair differ in parity
-    for GT in range(1, 10):
+    for GT in range(1, 14):
         for r in (5, 6, 7, 8):
             for ncols in (1, 2, 3, 4):
                 assert lib.bildk_debug_tables(0, GT, r, ncols, _lib.ptr(out, _lib.c_uint8_p)) == 12
@@ -209,7 +209,7 @@ def test_register_chained_kernel_tables():
                 assert [int(v) for v in mrow[:ncols]] == [8 * GT + 2 * q + 1 for q in range(ncols)]
                 assert all(lastrow[2 * i + 1] == (mrow[i] if i < ncols else 8 * GT) for i in range(4))
                 assert all(8 * GT <= v < 8 * GT + 8 for v in lastrow)
-    assert lib.bildk_debug_tables(0, 10, 1, 1, _lib.ptr(out, _lib.c_uint8_p)) < 0      # out of the kernels' range
+    assert lib.bildk_debug_tables(0, 14, 1, 1, _lib.ptr(out, _lib.c_uint8_p)) < 0      # out of the kernels' range
     assert lib.bildk_debug_tables(0, 3, 9, 1, _lib.ptr(out, _lib.c_uint8_p)) < 0
 
 
