@@ -34,7 +34,7 @@ if has launches; then
   tail -3 gpurun_out/launches_$TAG.csv
 fi
 if has ncu; then
-  for spec in "n50:k_mmar2:100" "n50small:k_mmar2:100" "n200:k_mmag2:20" "c2:k_mmar:500" "c3:k_mmact:40"; do
+  for spec in "n50:k_mmar2:100" "n50small:k_mmar2:100" "n200:k_mmag2:20" "c2:k_mmar:500" "c3:k_mmar8:40"; do
     IFS=: read wl kern frames <<< "$spec"
     timeout 600 ncu --set full --import-source on --clock-control none -k regex:$kern -c 1 -f -o /tmp/prof_${wl}_$TAG \
         python tools/run_kernel.py --workload $wl --frames $frames --reps 1 > gpurun_out/ncu_full_${wl}_$TAG.log 2>&1
