@@ -463,6 +463,37 @@ def test_external_force_mean_offset(N):
     assert rel_err(got, want) < TOL
 
 
+def test_every_polymer_size():
+    """Every N from 2 to 116 once (kernel selection has a dozen classes by tile grid and N mod 8): a short trajectory with a
+    missing frame, a handful of profiles, d = 3, against the C oracle; the plan must be one of the register-chained kernels
+    wherever DESIGN.md section 4 says so."""
+    expect = {}
+    for N in range(2, 117):
+        GT, r = (N + 7) // 8, N - 8 * ((N + 7) // 8 - 1)
+        expect[N] = "mmar" if GT <= 4 else "mmar2" if GT <= 9 else "mmar8" if GT <= 13 else None
+    rng = np.random.default_rng(4242)
+    s2, Cind = ko.noise_to_s2_cind([0.3] * 3)
+    worst = 0.0
+    for N in range(2, 117):
+        mod = oracle_model(N, d=3)
+        T, P = 7, 4
+        x, _ = synth_traj(mod, T, rng, 0.3)
+        x[3] = np.nan
+        ss, thetas = random_profiles(rng, P, T, 2, 3)
+        states = np.array([ko.st2states(s, th, T) for s, th in zip(ss, thetas)])
+        want = ko.logl_c(*(mod[k] for k in MODEL_KEYS), x, s2, Cind, states)
+        eng = engine_for(mod)
+        traj = eng.trajectory(x, [0.3] * 3)
+        plan = traj.describe_plan(P).split()[0]
+        if expect[N] is not None:
+            assert plan == expect[N], (N, plan)
+        got = eng.logl_st(traj, ss, thetas)
+        err = rel_err(got, want)
+        assert err < TOL, (N, plan, err)
+        worst = max(worst, err)
+    assert worst < 1e-11
+
+
 def test_no_valid_frames_and_single_frame():
     mod = oracle_model(12, d=2)
     eng = engine_for(mod)
