@@ -1,5 +1,10 @@
-// k_mmar2 - the register-chained FP64 tensor-core filter (k_mmar) for 33 <= N <= 56, TWO WARPS PER FILTER
-// (5 <= GT <= 7 with N mod 8 in 1..4: the north-star shape N = 50 is GT = 7, r = 2).
+// k_mmar2 / k_mmar8 - the register-chained FP64 tensor-core filter (k_mmar) with SEVERAL WARPS PER FILTER:
+//   33 <= N <= 56  (GT 5..7; the north-star shape N = 50 is GT = 7, r = 2)   two warps, up to 6 filters per CTA     k_mmar2<GT, MAXF, MX, 2>
+//   57 <= N <= 64  (GT = 8)                                                  four warps (complementary row pairs)   k_mmar2<8, 2, MX, 4>
+//   65 <= N <= 72  (GT = 9)                                                  five warps (four pairs + middle row)   k_mmar2<9, 2, MX, 5>
+//   73 <= N <= 104 (GT 10..13; BASELINE configs[2] N = 100)                  eight warps, one filter per CTA, one resident propagator  k_mmar8<GT, MX>
+// All of them run the same frame, mmar2_run<GT, ROLE, MX, NW, BONE>; only the row -> warp tables (Mmar2Rows) differ.
+// MX: N mod 8 in {0, 5, 6, 7}, the mean in an extra row block (bildk_mmar.cuh).
 //
 // Why: ncu of k_mma2<7> on the N = 50 target (profiles/r02_ncu_n50.txt, source view) shows the tensor pipe 79 % busy
 // and each warp away from it 40-55 % of its time: k_mma2 splits the work of a frame by tile COLUMNS - P1 (T = B C, in
@@ -20,7 +25,7 @@ namespace bildk {
 
 struct R2Params {
     RParams r;
-    int FPC2;   // filters per CTA (two warps each)
+    int FPC2;   // filters per CTA (NW warps each)
 };
 
 // NW = warps per filter: 2 for GT 5..7; 4 for GT = 8 (N = 57..64), where the four COMPLEMENTARY row pairs (ti, GT-1-ti) cost
