@@ -12,6 +12,7 @@
 #include "bildk_mmag2.cuh"
 #include "bildk_mmact.cuh"
 #include "bildk_amis.cuh"
+#include "bildk_launch.h"
 
 #include <algorithm>
 #include <atomic>
@@ -58,7 +59,7 @@ struct NvtxRange {
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: remember the largest value
 // configured for every (device, kernel) pair (a process-wide `static` would skip the call on a second device).
-static cudaError_t ensure_dyn_smem(const void* kernel, size_t smem) {
+cudaError_t ensure_dyn_smem(const void* kernel, size_t smem) {   // declared in bildk_launch.h
     static std::mutex mu;
     static std::map<std::pair<int, const void*>, size_t> configured;
     int dev = 0;
@@ -541,76 +542,10 @@ static cudaError_t mma_launch_for(int GT, bool MX, const MParams& mp, dim3 grid,
     return cudaErrorInvalidValue;
 }
 
-template <int GT, int NB, bool MX>
-static cudaError_t mmar_launch(const RParams& rp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-    {
-        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&k_mmar<GT, NB, MX>), smem);
-        if (e != cudaSuccess) return e;
-    }
-    k_mmar<GT, NB, MX><<<grid, threads, smem, st>>>(rp);
-    return cudaGetLastError();
-}
-// compiled register budgets (resident 4-warp CTAs per SM = warps per scheduler); MX = mean in an extra row block
-#define MMAR_VARIANTS(X) X(1, 4, false) X(1, 7, false) X(2, 4, false) X(2, 5, false) X(2, 7, false) X(3, 4, false) X(3, 5, false) X(3, 7, false) \
-                         X(4, 3, false) X(4, 4, false) X(4, 5, false) \
-                         X(1, 4, true) X(2, 4, true) X(3, 4, true) X(3, 3, true) X(4, 3, true)
-static bool mmar_has(int GT, int NB, bool MX) {
-#define X(G_, N_, M_) if (GT == G_ && NB == N_ && MX == M_) return true;
-    MMAR_VARIANTS(X)
-#undef X
-    return false;
-}
-static cudaError_t mmar_launch_for(int GT, int NB, bool MX, const RParams& rp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-#define X(G_, N_, M_) if (GT == G_ && NB == N_ && MX == M_) return mmar_launch<G_, N_, M_>(rp, grid, threads, smem, st);
-    MMAR_VARIANTS(X)
-#undef X
-    return cudaErrorInvalidValue;
-}
-
-template <int GT, int NB, int RB>
-static cudaError_t mmarb_launch(const RParams& rp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-    {
-        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&k_mmarb<GT, NB, RB>), smem);
-        if (e != cudaSuccess) return e;
-    }
-    k_mmarb<GT, NB, RB><<<grid, threads, smem, st>>>(rp);
-    return cudaGetLastError();
-}
-#define MMARB_VARIANTS(X) X(2, 4, 1) X(2, 4, 2) X(3, 4, 1) X(3, 4, 2) X(4, 3, 1) X(4, 3, 2)
-static bool mmarb_has(int GT, int NB, int RB) {
-#define X(G_, N_, R_) if (GT == G_ && NB == N_ && RB == R_) return true;
-    MMARB_VARIANTS(X)
-#undef X
-    return false;
-}
-static cudaError_t mmarb_launch_for(int GT, int NB, int RB, const RParams& rp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-#define X(G_, N_, R_) if (GT == G_ && NB == N_ && RB == R_) return mmarb_launch<G_, N_, R_>(rp, grid, threads, smem, st);
-    MMARB_VARIANTS(X)
-#undef X
-    return cudaErrorInvalidValue;
-}
-
-constexpr int mmar2_nw(int GT) { return GT == 9 ? 5 : GT >= 8 ? 4 : 2; }   // warps per filter
-template <int GT, int MAXF, bool MX>
-static cudaError_t mmar2_launch(const R2Params& rp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-    {
-        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&k_mmar2<GT, MAXF, MX, mmar2_nw(GT)>), smem);
-        if (e != cudaSuccess) return e;
-    }
-    k_mmar2<GT, MAXF, MX, mmar2_nw(GT)><<<grid, threads, smem, st>>>(rp);
-    return cudaGetLastError();
-}
-// MAXF = filters per CTA the kernel is compiled for (registers per thread = 65536 / (64 MAXF)): GT = 7 is spill-free only at
-// 4 (8 warps, 255 registers; 5 or 6 filters spill, see bildk_mmar2.cuh); the smaller tile grids leave room for more warps.
+// The launchers of the register-chained kernels (k_mmar / k_mmarb / k_mmar2 / k_mmar8) live in translation units of their own
+// (bildk_tu_*.cu, declared in bildk_launch.h): NVVM spends four of the five minutes of a single-file build on their unrolled
+// template instantiations, and the translation units compile in parallel (bild_b200/build.py).
 constexpr int MMAR2_MAXF = 4;
-#define MMAR2_VARIANTS(X) X(5, 4, false) X(6, 4, false) X(7, 4, false) X(5, 4, true) X(6, 4, true) X(7, 4, true) \
-                          X(5, 6, false) X(5, 6, true) X(8, 2, false) X(8, 2, true) X(9, 2, false) X(9, 2, true)
-static bool mmar2_has(int GT, int MAXF, bool MX) {
-#define X(G_, F_, M_) if (GT == G_ && MAXF == F_ && MX == M_) return true;
-    MMAR2_VARIANTS(X)
-#undef X
-    return false;
-}
 static int mmar2_maxf(int GT, bool MX) {
     // GT = 5: 12 warps at 168 registers (spill-free without MX, 76 bytes with) beat 8 warps at 194 / 210 by 3-4 %
     // (profiles/r02_mx_variants.txt); GT = 6 spills at 168 registers and loses 18 %
@@ -619,22 +554,6 @@ static int mmar2_maxf(int GT, bool MX) {
     const int dflt = GT == 5 ? 6 : (GT >= 8 ? 2 : MMAR2_MAXF);
     const int want = env_int("BILDK_MMAR2_MAXF", dflt);
     return mmar2_has(GT, want, MX) ? want : dflt;
-}
-static cudaError_t mmar2_launch_for(int GT, int MAXF, bool MX, const R2Params& rp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-#define X(G_, F_, M_) if (GT == G_ && MAXF == F_ && MX == M_) return mmar2_launch<G_, F_, M_>(rp, grid, threads, smem, st);
-    MMAR2_VARIANTS(X)
-#undef X
-    return cudaErrorInvalidValue;
-}
-
-template <int GT, bool MX>
-static cudaError_t mmar8_launch(const R2Params& rp, dim3 grid, size_t smem, cudaStream_t st) {
-    {
-        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&k_mmar8<GT, MX>), smem);
-        if (e != cudaSuccess) return e;
-    }
-    k_mmar8<GT, MX><<<grid, 256, smem, st>>>(rp);
-    return cudaGetLastError();
 }
 
 // Rows of the last tile-row block that carry M^T (and one all-zero row), placed so that the B-fragment loads of the
@@ -1301,17 +1220,7 @@ static int launch_device(bildk_model* m, const bildk_traj* t0, int n_traj, const
             for (int e = 0; e < dstar; ++e) mmar_tables(m->GT, m->r_last, t0->ncols[e], rp.lastrow[e], rp.mrow[e]);
             r2.FPC2 = pl.FPC;
             if (pl.mmar8) {
-                cudaError_t e8 = cudaErrorInvalidValue;
-                switch (m->GT * 2 + (m->mmar_mx ? 1 : 0)) {
-                    case 20: e8 = mmar8_launch<10, false>(r2, grid, pl.smem, st); break;
-                    case 21: e8 = mmar8_launch<10, true>(r2, grid, pl.smem, st); break;
-                    case 22: e8 = mmar8_launch<11, false>(r2, grid, pl.smem, st); break;
-                    case 23: e8 = mmar8_launch<11, true>(r2, grid, pl.smem, st); break;
-                    case 24: e8 = mmar8_launch<12, false>(r2, grid, pl.smem, st); break;
-                    case 25: e8 = mmar8_launch<12, true>(r2, grid, pl.smem, st); break;
-                    case 26: e8 = mmar8_launch<13, false>(r2, grid, pl.smem, st); break;
-                    case 27: e8 = mmar8_launch<13, true>(r2, grid, pl.smem, st); break;
-                }
+                const cudaError_t e8 = mmar8_launch_for(m->GT, m->mmar_mx, r2, grid, pl.smem, st);
                 CU(e8);
             } else {
                 CU(mmar2_launch_for(m->GT, pl.maxf, m->mmar_mx, r2, grid, pl.threads, pl.smem, st));

@@ -482,6 +482,9 @@ struct GParams {
     double* work;              // [gridDim.x*gridDim.y][2*N*N + 3*N*D + 2*N]
 };
 
+// The non-template kernels below are compiled in the main translation unit only (bildk.cu); the launcher translation units
+// (bildk_tu_*.cu, BILDK_SATELLITE_TU) include this header for the shared helpers and parameter structs.
+#ifndef BILDK_SATELLITE_TU
 __global__ void __launch_bounds__(256) k_generic(const __grid_constant__ GParams p) {
     const int N = p.N, D = p.D;
     const int e = blockIdx.y;
@@ -764,5 +767,7 @@ __global__ void __launch_bounds__(256) k_marginal_posterior(int n, int K1, int T
         for (int s = 0; s < S; ++s) out[static_cast<size_t>(s) * T + t] = lse[s] - norm;
     }
 }
+
+#endif  // BILDK_SATELLITE_TU
 
 }  // namespace bildk
