@@ -2,6 +2,12 @@
 // -DBILDK_MMAR8_MX=<0|1> (bild_b200/build.py compiles this file once per instantiation, all in parallel: NVVM needs about a
 // minute for each of them).  See bildk_launch.h.
 #define BILDK_SATELLITE_TU 1
+#ifndef BILDK_MMAR8_GT   // a plain `nvcc -c` of this file compiles the BASELINE configs[2] instantiation
+#define BILDK_MMAR8_GT 13
+#endif
+#ifndef BILDK_MMAR8_MX
+#define BILDK_MMAR8_MX 0
+#endif
 #include "bildk_launch.h"
 
 using namespace bildk;
